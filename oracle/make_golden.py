@@ -1,0 +1,161 @@
+#!/usr/bin/env python
+"""Generate tests/golden/* by running the UNMODIFIED reference modules on CPU.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (where /root/reference exists):
+
+    PYTHONDONTWRITEBYTECODE=1 python oracle/make_golden.py
+
+The reference never seeds and hard-codes ``.cuda()`` in its constructors
+(OS_CNN/OS_CNN.py:56), so this script (a) seeds torch itself and (b) installs the
+``torch.Tensor.cuda = identity`` shim described in SURVEY.md F2.  Nothing from the
+reference is copied: it is imported, executed, and only its numeric outputs are stored.
+The GPU box has no /root/reference -- tests there read the committed vectors only.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF = os.environ.get("TSC_REFERENCE_ROOT", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def import_reference():
+    sys.dont_write_bytecode = True
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    torch.Tensor.cuda = lambda self, *a, **k: self          # SURVEY F2 shim
+    torch.nn.Module.cuda = lambda self, *a, **k: self
+    from OS_CNN import OS_CNN as ref_os                      # noqa
+    from OS_CNN import OS_CNN_Structure_build as ref_sb      # noqa
+    return ref_os, ref_sb
+
+
+def to_np(sd):
+    return {k: v.detach().cpu().numpy().copy() for k, v in sd.items()}
+
+
+def run_pair(ref_os, lpl_ext, n_class, x, y, seed):
+    """extractor + classifier, one training forward/backward, then one eval forward."""
+    from oracle import os_cnn as O
+    torch.manual_seed(seed)
+    fe = ref_os.OS_CNN_res(lpl_ext)
+    cf = O.feature_channels(lpl_ext)
+    lpl_cls = ref_os.layer_parameter_list_input_change(lpl_ext, cf)
+    cl = ref_os.OS_CNN(lpl_cls, n_class)
+    init_fe, init_cl = to_np(fe.state_dict()), to_np(cl.state_dict())
+
+    fe.train(); cl.train()
+    xin = x.clone().requires_grad_(True)
+    feat = fe(xin)
+    feat.retain_grad()
+    logits, pooled = cl(feat)
+    loss = torch.nn.functional.cross_entropy(logits, y)
+    loss.backward()
+    out = dict(x=x.numpy(), y=y.numpy(), feat=feat.detach().numpy(), logits=logits.detach().numpy(),
+               pooled=pooled.detach().numpy(), loss=np.float64(loss.item()),
+               dfeat=feat.grad.numpy(), dx=xin.grad.numpy())
+    grads = {}
+    for name, mod in (("fe", fe), ("cl", cl)):
+        for k, p in mod.named_parameters():
+            grads[f"{name}.{k}"] = p.grad.detach().numpy()
+    after_fe, after_cl = to_np(fe.state_dict()), to_np(cl.state_dict())
+    fe.eval(); cl.eval()
+    with torch.no_grad():
+        feat_e = fe(x)
+        logits_e, pooled_e = cl(feat_e)
+    out.update(feat_eval=feat_e.numpy(), logits_eval=logits_e.numpy(), pooled_eval=pooled_e.numpy())
+    return init_fe, init_cl, after_fe, after_cl, grads, out, lpl_cls
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    sys.path.insert(0, os.path.dirname(HERE))
+    ref_os, ref_sb = import_reference()
+    from oracle import os_cnn as O
+
+    # ---- integer tables: mask indices, layer lists, state_dict keys ---------------------------
+    tables = {"mask_index": {}, "layer_lists": {}, "state_dict": {}}
+    for kmax in (2, 7, 31, 89):
+        primes = ref_sb.get_Prime_number_in_a_range(1, kmax)
+        tables["mask_index"][str(kmax)] = {str(k): list(ref_os.calculate_mask_index(k, kmax)) for k in primes}
+    for (C, L) in ((1, 128), (9, 128), (3, 1024), (7, 1152), (2, 64)):
+        budgets = [8 * 128 * C, 5 * 128 * 256 + 2 * 256 * 128]           # train_and_test.py:38
+        rf = min(int(L / 4), 89)                                           # train_and_test.py:40-42
+        lpl = ref_sb.generate_layer_parameter_list(1, rf, budgets, C)
+        tables["layer_lists"][f"C{C}_L{L}"] = lpl
+    tables["primes_1_31"] = ref_sb.get_Prime_number_in_a_range(1, 31)
+    tables["primes_1_89"] = ref_sb.get_Prime_number_in_a_range(1, 89)
+
+    # ---- small model with full weights, outputs and gradients ---------------------------------
+    lpl_small = ref_sb.generate_layer_parameter_list(1, 7, [216, 2160], 3)   # widths 20 / 30 / 40
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(6, 3, 32, generator=g)
+    y = torch.randint(0, 4, (6,), generator=g)
+    init_fe, init_cl, after_fe, after_cl, grads, out, lpl_cls = run_pair(ref_os, lpl_small, 4, x, y, seed=0)
+    tables["small"] = {"lpl_ext": lpl_small, "lpl_cls": lpl_cls, "n_class": 4, "seed": 0}
+    tables["state_dict"]["small_fe"] = {k: list(v.shape) for k, v in init_fe.items()}
+    tables["state_dict"]["small_cl"] = {k: list(v.shape) for k, v in init_cl.items()}
+    np.savez_compressed(
+        os.path.join(OUT, "small_pair.npz"),
+        **{f"init_fe/{k}": v for k, v in init_fe.items()}, **{f"init_cl/{k}": v for k, v in init_cl.items()},
+        **{f"after_fe/{k}": v for k, v in after_fe.items() if "running" in k or "num_batches" in k},
+        **{f"after_cl/{k}": v for k, v in after_cl.items() if "running" in k or "num_batches" in k},
+        **{f"grad/{k}": v for k, v in grads.items()}, **{f"out/{k}": v for k, v in out.items()})
+
+    # ---- second small model: even-free odd Kmax=13 bank, univariate, longer series -------------
+    lpl_uni = ref_sb.generate_layer_parameter_list(1, 13, [8 * 8 * 1, 5 * 8 * 16 + 2 * 16 * 8], 1)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(4, 1, 160, generator=g)
+    y = torch.randint(0, 3, (4,), generator=g)
+    init_fe, init_cl, after_fe, after_cl, grads, out, lpl_cls = run_pair(ref_os, lpl_uni, 3, x, y, seed=1)
+    tables["uni"] = {"lpl_ext": lpl_uni, "lpl_cls": lpl_cls, "n_class": 3, "seed": 1}
+    np.savez_compressed(
+        os.path.join(OUT, "uni_pair.npz"),
+        **{f"init_fe/{k}": v for k, v in init_fe.items()}, **{f"init_cl/{k}": v for k, v in init_cl.items()},
+        **{f"after_fe/{k}": v for k, v in after_fe.items() if "running" in k or "num_batches" in k},
+        **{f"after_cl/{k}": v for k, v in after_cl.items() if "running" in k or "num_batches" in k},
+        **{f"grad/{k}": v for k, v in grads.items()}, **{f"out/{k}": v for k, v in out.items()})
+
+    # ---- cfg1 at full width, seed-only (weights are reproduced by init replay) ----------------
+    C, L, K, B = 1, 128, 5, 16
+    lpl = tables["layer_lists"]["C1_L128"]
+    lpl = [[tuple(t) for t in layer] for layer in lpl]
+    x, y = O.synthetic_batch(B, C, L, K, domain_id=0)
+    init_fe, init_cl, after_fe, after_cl, grads, out, lpl_cls = run_pair(ref_os, lpl, K, x, y, seed=0)
+    tables["state_dict"]["cfg1_fe"] = {k: list(v.shape) for k, v in init_fe.items()}
+    tables["state_dict"]["cfg1_cl"] = {k: list(v.shape) for k, v in init_cl.items()}
+    checks = {f"fe.{k}": [float(v.astype(np.float64).sum()), float(np.abs(v.astype(np.float64)).sum())]
+              for k, v in init_fe.items()}
+    checks.update({f"cl.{k}": [float(v.astype(np.float64).sum()), float(np.abs(v.astype(np.float64)).sum())]
+                   for k, v in init_cl.items()})
+    tables["cfg1"] = {"param_checksums": checks, "seed": 0, "B": B, "C": C, "L": L, "n_class": K,
+                      "loss": float(out["loss"]), "argmax": np.argmax(out["logits"], axis=1).tolist(),
+                      "argmax_eval": np.argmax(out["logits_eval"], axis=1).tolist()}
+    masks = {f"cl.net.{i}.conv1d.weight": O.build_mask(lpl_cls[i]) for i in range(3)}
+    masks.update({f"fe.net_1.net.net.{i}.conv1d.weight": O.build_mask(lpl[i]) for i in range(3)})
+    gnorm = {k: float(np.linalg.norm((v * masks[k]) if k in masks else v)) for k, v in grads.items()}
+    tables["cfg1"]["masked_grad_norms"] = gnorm
+    np.savez_compressed(
+        os.path.join(OUT, "cfg1_seeded.npz"),
+        logits=out["logits"], pooled=out["pooled"], logits_eval=out["logits_eval"],
+        feat_b0=out["feat"][0], feat_eval_b0=out["feat_eval"][0], dfeat_b0=out["dfeat"][0],
+        **{f"grad/{k}": v for k, v in grads.items() if v.ndim == 1 or "hidden" in k},
+        **{"grad/fe.net_1.net.net.0.conv1d.weight": grads["fe.net_1.net.net.0.conv1d.weight"]},
+        **{f"after_fe/{k}": v for k, v in after_fe.items() if "running" in k},
+        **{f"after_cl/{k}": v for k, v in after_cl.items() if "running" in k})
+
+    with open(os.path.join(OUT, "tables.json"), "w") as f:
+        json.dump(tables, f, indent=1, sort_keys=True)
+    print("golden vectors written to", OUT)
+    for fn in sorted(os.listdir(OUT)):
+        print(f"  {fn}: {os.path.getsize(os.path.join(OUT, fn))} bytes")
+
+
+if __name__ == "__main__":
+    main()
