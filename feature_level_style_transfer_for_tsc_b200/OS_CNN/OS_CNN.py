@@ -1,0 +1,210 @@
+"""OS-CNN modules -- drop-in mirror of the reference's ``OS_CNN/OS_CNN.py`` on the B200 kernels.
+
+Same class names, constructor / forward signatures, attributes (``.net``, ``.net_1``, ``.res``, ``.hidden``,
+``.conv1d``, ``.bn``, ``.weight_mask``, ``.length_before_classification``) and ``state_dict`` keys as the
+reference, and the same consumption of the torch RNG at construction (so one seed gives bit-identical
+initial parameters -- SURVEY.md appendix A5).  The arithmetic does not go through torch: every forward is one
+``os_stack`` autograd node that runs the hand-written sm_100a kernels (masked multi-size Conv1d as an
+implicit GEMM, BatchNorm statistics / apply, ReLU, shortcut add) on the c8 device layout.
+
+There is no CPU path: inputs must be CUDA fp32 tensors and ``libtsc_b200.so`` must be built.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..functional import LayerSpec, StackSpec, os_stack
+
+
+def calculate_mask_index(kernel_length_now, largest_kernel_lenght):
+    """(left, right): the taps [left, right) a size-``kernel_length_now`` kernel occupies inside the common
+    ``largest_kernel_lenght`` window (reference lines 9-12; even kernels lean right)."""
+    right_zero = math.ceil((largest_kernel_lenght - 1) / 2) - math.ceil((kernel_length_now - 1) / 2)
+    left_zero = largest_kernel_lenght - kernel_length_now - right_zero
+    return left_zero, left_zero + kernel_length_now
+
+
+def creat_mask(number_of_input_channel, number_of_output_channel, kernel_length_now, largest_kernel_lenght):
+    """ones inside the live window, zeros outside; shape (arg0, arg1, largest) as in the reference (lines 15-20)."""
+    left, right = calculate_mask_index(kernel_length_now, largest_kernel_lenght)
+    mask = torch.zeros(number_of_input_channel, number_of_output_channel, largest_kernel_lenght)
+    mask[:, :, left:right] = 1.0
+    return mask.numpy()
+
+
+def creak_layer_mask(layer_parameter_list):
+    """mask, initial weight and bias of one OS layer (reference lines 23-43).  Every prime kernel is drawn
+    from its own ``nn.Conv1d`` (its own fan-in bound) in list order, which is what fixes the RNG stream."""
+    largest = layer_parameter_list[-1][-1]
+    masks, weights, biases = [], [], []
+    for (ic, oc, k) in layer_parameter_list:
+        conv = nn.Conv1d(in_channels=ic, out_channels=oc, kernel_size=k)
+        left, right = calculate_mask_index(k, largest)
+        big = torch.zeros(oc, ic, largest)
+        big[:, :, left:right] = conv.weight.detach()
+        weights.append(big)
+        biases.append(conv.bias.detach().clone())
+        m = torch.zeros(oc, ic, largest)
+        m[:, :, left:right] = 1.0
+        masks.append(m)
+    return (torch.cat(masks, 0).numpy().astype("float32"), torch.cat(weights, 0).numpy().astype("float32"),
+            torch.cat(biases, 0).numpy().astype("float32"))
+
+
+def _bn_layer_spec(geom, bn, relu, zero_masked=True):
+    """LayerSpec for one conv+BN pair; advances ``num_batches_tracked`` like nn.BatchNorm1d.forward."""
+    use_batch_stats = bn.training or bn.running_mean is None
+    momentum = 0.0
+    if bn.training and bn.track_running_stats and bn.running_mean is not None:
+        bn.num_batches_tracked.add_(1)
+        momentum = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked.item())
+    return LayerSpec(geom=geom, relu=relu, training=use_batch_stats, momentum=float(momentum), eps=float(bn.eps),
+                     running_mean=bn.running_mean, running_var=bn.running_var, zero_masked=zero_masked)
+
+
+def _bn_params(conv, bn):
+    if bn.weight is None:
+        raise RuntimeError("BatchNorm1d(affine=False) is not supported by the OS-CNN kernels")
+    return [conv.weight, conv.bias, bn.weight, bn.bias]
+
+
+def _run_stack(layers, x, shortcut=None, final_relu=False):
+    specs, params = [], []
+    for layer in layers:
+        specs.append(_bn_layer_spec(layer.geometry, layer.bn, layer.relu_or_not_at_last_layer))
+        params += _bn_params(layer.conv1d, layer.bn)
+    sc_spec = None
+    if shortcut is not None:
+        sc_spec = _bn_layer_spec(shortcut.geometry, shortcut.bn, False, zero_masked=False)
+        params += _bn_params(shortcut.conv1d, shortcut.bn)
+    spec = StackSpec(layers=specs, shortcut=sc_spec, final_relu=final_relu, engine=ops.get_engine("conv"),
+                     wgrad_engine=ops.get_engine("wgrad"))
+    if x.dtype != torch.float32:
+        raise RuntimeError(f"OS-CNN input must be float32 (the reference casts with .float()), got {x.dtype}")
+    return os_stack(spec, x.contiguous(), params)
+
+
+class build_layer_with_layer_parameter(nn.Module):
+    """One OS layer: mask*W -> zero pad -> Conv1d(Cin, sum Cout, Kmax) -> BatchNorm1d -> optional ReLU
+    (reference lines 46-77)."""
+
+    def __init__(self, layer_parameters, relu_or_not_at_last_layer=True, with_nvidia=True):
+        super(build_layer_with_layer_parameter, self).__init__()
+        self.relu_or_not_at_last_layer = relu_or_not_at_last_layer
+        os_mask, init_weight, init_bias = creak_layer_mask(layer_parameters)
+        out_channels, in_channels, max_kernel_size = os_mask.shape
+        # not in the state_dict (the reference keeps it as a plain attribute); follows .cuda()/.to()
+        self.register_buffer("weight_mask", torch.from_numpy(os_mask).float(), persistent=False)
+        self.padding = nn.ConstantPad1d((int((max_kernel_size - 1) / 2), int(max_kernel_size / 2)), 0)
+        # the big Conv1d draws (and discards) its own init: part of the reference's RNG stream
+        self.conv1d = nn.Conv1d(in_channels=in_channels, out_channels=out_channels, kernel_size=max_kernel_size)
+        self.conv1d.weight = nn.Parameter(torch.from_numpy(init_weight), requires_grad=True)
+        self.conv1d.bias = nn.Parameter(torch.from_numpy(init_bias), requires_grad=True)
+        self.bn = nn.BatchNorm1d(num_features=out_channels)
+        self.geometry = ops.bank_geometry(layer_parameters)
+
+    def forward(self, X):
+        return _run_stack([self], X)
+
+
+class OS_CNN(nn.Module):
+    """Classifier head over extracted features: OS layers (all ReLU) -> global average pool -> Linear
+    (reference lines 80-110).  Returns ``(logits, pooled)``; with ``few_shot`` both are the pooled features."""
+
+    def __init__(self, layer_parameter_list, n_class, few_shot=False):
+        super(OS_CNN, self).__init__()
+        self.few_shot = few_shot
+        self.layer_parameter_list = layer_parameter_list
+        self.layer_list = [build_layer_with_layer_parameter(p) for p in layer_parameter_list]
+        self.net = nn.Sequential(*self.layer_list)
+        self.averagepool = nn.AdaptiveAvgPool1d(1)
+        out_put_channel_numebr = sum(p[1] for p in layer_parameter_list[-1])
+        self.hidden = nn.Linear(out_put_channel_numebr, n_class)
+        self.length_before_classification = out_put_channel_numebr
+
+    def forward(self, X):
+        X = _run_stack(list(self.net), X)
+        X_f = X.mean(dim=-1)                      # AdaptiveAvgPool1d(1) + squeeze(-1)
+        if not self.few_shot:
+            return self.hidden(X_f), X_f
+        return X_f.unsqueeze(-1), X_f
+
+
+class OS_block(nn.Module):
+    """A chain of OS layers; the last one may skip its ReLU (reference lines 117-139)."""
+
+    def __init__(self, layer_parameter_list, relu_or_not_at_last_layer=True):
+        super(OS_block, self).__init__()
+        self.layer_parameter_list = layer_parameter_list
+        self.relu_or_not_at_last_layer = relu_or_not_at_last_layer
+        n = len(layer_parameter_list)
+        self.layer_list = [
+            build_layer_with_layer_parameter(p, True if i != n - 1 else relu_or_not_at_last_layer)
+            for i, p in enumerate(layer_parameter_list)]
+        self.net = nn.Sequential(*self.layer_list)
+
+    def forward(self, X):
+        return _run_stack(list(self.net), X)
+
+
+def layer_parameter_list_input_change(layer_parameter_list, input_channel):
+    """Same list with layer 0 re-targeted to ``input_channel`` inputs (reference lines 142-152)."""
+    return [[(input_channel, oc, k) for (_, oc, k) in layer] if i == 0 else layer
+            for i, layer in enumerate(layer_parameter_list)]
+
+
+class SampaddingConv1D_BN(nn.Module):
+    """'same'-padded Conv1d + BatchNorm1d, used as the 1x1 shortcut (reference lines 155-166)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size):
+        super(SampaddingConv1D_BN, self).__init__()
+        self.padding = nn.ConstantPad1d((int((kernel_size - 1) / 2), int(kernel_size / 2)), 0)
+        self.conv1d = nn.Conv1d(in_channels=in_channels, out_channels=out_channels, kernel_size=kernel_size)
+        self.bn = nn.BatchNorm1d(num_features=out_channels)
+        self.geometry = ops.dense_geometry(in_channels, out_channels, kernel_size)
+        self.relu_or_not_at_last_layer = False
+
+    def forward(self, X):
+        return _run_stack([self], X)
+
+
+class Res_OS_layer(nn.Module):
+    """relu(BN(conv1x1(X)) + OS_block(X)) with the block's last layer un-activated (reference lines 169-180).
+    One fused stack: the add and the ReLU happen in the BatchNorm-apply kernel of the two branches."""
+
+    def __init__(self, layer_parameter_list, out_put_channel_numebr):
+        super(Res_OS_layer, self).__init__()
+        self.layer_parameter_list = layer_parameter_list
+        self.net = OS_block(layer_parameter_list, False)
+        self.res = SampaddingConv1D_BN(layer_parameter_list[0][0][0], out_put_channel_numebr, 1)
+
+    def forward(self, X):
+        return _run_stack(list(self.net.net), X, shortcut=self.res, final_relu=True)
+
+
+class OS_CNN_res(nn.Module):
+    """Feature extractor: ``n_layers`` residual OS layers, no pooling / classifier (reference lines 183-220)."""
+
+    def __init__(self, layer_parameter_list, n_layers=1):
+        super(OS_CNN_res, self).__init__()
+        self.layer_parameter_list = layer_parameter_list
+        self.n_layers = n_layers
+        out_put_channel_numebr = sum(p[1] for p in layer_parameter_list[-1])
+        new_layer_parameter_list = layer_parameter_list_input_change(layer_parameter_list, out_put_channel_numebr)
+        self.net_1 = Res_OS_layer(layer_parameter_list, out_put_channel_numebr)
+        self.net_list = [Res_OS_layer(new_layer_parameter_list, out_put_channel_numebr) for _ in range(n_layers - 1)]
+        if self.n_layers > 1:
+            self.net = nn.Sequential(*self.net_list)
+
+    def forward(self, X):
+        temp = self.net_1(X)
+        if self.n_layers > 1:
+            temp = self.net(temp)
+        return temp
+
+    def return_last_layer(self):
+        """The OS_block of the (single) residual layer -- what GradNorm differentiates against
+        (train_and_test.py:681-690)."""
+        return self.net_1.net

@@ -1,0 +1,116 @@
+"""ctypes binding of libtsc_b200.so (C-ABI in include/tsc_b200.h).
+
+The library is built in-tree by ``build()`` (also called from ``__graft_entry__.build()``) and is the
+only compute path of this package: there is no CPU or alternate-backend fallback.  Importing the
+package without the built library works (so CPU-only tooling can introspect it), but every operator
+raises ``RuntimeError`` the moment it is asked to compute.
+"""
+from __future__ import annotations
+
+import ctypes
+import glob
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "libtsc_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+HEADER = os.path.join(_ROOT, "include", "tsc_b200.h")
+
+TSC_F32, TSC_BF16 = 0, 1
+ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1
+DIR_FWD, DIR_DGRAD = 0, 1
+OUT_C8_F32, OUT_C8_BF16, OUT_NCL_F32 = 0, 1, 2
+MAX_TAPS, MAX_CHANNELS = 96, 256
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+_lock = threading.Lock()
+_lib = None
+
+_p, _i, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+_ip = ctypes.POINTER(ctypes.c_int)
+
+# name -> (restype, argtypes); must list every symbol declared in include/tsc_b200.h
+SIGNATURES = {
+    "tsc_version": (_i, []),
+    "tsc_last_error": (ctypes.c_char_p, []),
+    "tsc_pad_channels": (_i, [_i]),
+    "tsc_device_supports_tcgen05": (_i, []),
+    "tsc_ncl_to_c8": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "tsc_c8_to_ncl": (_i, [_p, _p, _i, _i, _i, _p]),
+    "tsc_packed_weight_bytes": (_sz, [_i, _i, _i, _i, _i, _ip]),
+    "tsc_pack_weights": (_i, [_i, _i, _p, _p, _i, _i, _i, _ip, _i, _p]),
+    "tsc_osconv": (_i, [_i, _i, _p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _ip, _p]),
+    "tsc_oswgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "tsc_oswgrad": (_i, [_i, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _ip, _p]),
+    "tsc_bn_workspace_bytes": (_sz, [_i, _i, _i]),
+    "tsc_bn_stats": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _f, _f, _i, _i, _i, _p]),
+    "tsc_bn_eval_coeffs": (_i, [_p, _p, _p, _p, _f, _p, _p, _p, _p, _i, _p]),
+    "tsc_bn_apply": (_i, [_p, _p, _p, _p, _p, _p, _i, _p, _i, _i, _i, _i, _p]),
+    "tsc_bn_bwd_reduce": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "tsc_bn_bwd_apply": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "tsc_rowstats_welford": (_i, [_p, _p, _p, _i, _i, _p]),
+    "tsc_adain_fwd": (_i, [_p, _p, _p, _p, _f, _i, _i, _p]),
+    "tsc_adain_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _p]),
+    "tsc_gram_workspace_bytes": (_sz, [_i, _i, _i]),
+    "tsc_gram_loss_fwd": (_i, [_i, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "tsc_gram_loss_bwd": (_i, [_i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "tsc_debug_read_and_clear_watchdog": (_i, [_ip]),
+}
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into libtsc_b200.so (nvcc cross-compiles without a GPU)."""
+    srcs = sources()
+    deps = srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + [HEADER]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH] + srcs
+    if verbose:
+        print(" ".join(cmd))
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return LIB_PATH
+
+
+def load():
+    """Load the library (once).  Raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback for the OS-CNN / style-transfer kernels)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        if lib.tsc_version() != 100:
+            raise RuntimeError(f"libtsc_b200.so version {lib.tsc_version()} does not match the Python host (100)")
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        lib = load()
+        msg = lib.tsc_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (rc={rc}): {msg}")
+
+
+def int_array(values):
+    return (ctypes.c_int * len(values))(*[int(v) for v in values])

@@ -1,0 +1,66 @@
+// C-ABI entry points of the convolution family: engine dispatch (SIMT fp32 / tcgen05 bf16).
+#include "common.cuh"
+
+namespace tsc {
+int osconv_simt(int direction, const void* x, int dtype, const void* w, const float* bias, float* y, int B, int L, int Cin,
+                int Cout, int Kmax, const int* s_of_tap, cudaStream_t cs);
+int osconv_tc(int direction, const void* x, int dtype, const void* w, const float* bias, float* y, int B, int L, int Cin,
+              int Cout, int Kmax, const int* s_of_tap, cudaStream_t cs);
+int oswgrad_simt(const void* dy, const void* x, int dtype, float* dW, void* workspace, int B, int L, int Cin, int Cout,
+                 int Kmax, const int* s_of_tap, cudaStream_t cs);
+int oswgrad_tc(const void* dy, const void* x, int dtype, float* dW, void* workspace, int B, int L, int Cin, int Cout,
+               int Kmax, const int* s_of_tap, cudaStream_t cs);
+int wgrad_simt_splits(int B, int L, int Cin, int Cout, int Kmax);
+int wgrad_tc_splits(int B, int L, int Cin, int Cout, int Kmax);
+int read_clear_watchdog_conv(int* code);
+int read_clear_watchdog_wgrad(int* code);
+int read_clear_watchdog_gram(int* code);
+}  // namespace tsc
+
+extern "C" {
+
+int tsc_osconv(int engine, int direction, const void* x, int dtype, const void* w, const float* bias, float* y, int B,
+               int L, int Cin, int Cout, int Kmax, const int* s_of_tap, tsc_stream_t stream) {
+    using namespace tsc;
+    TSC_REQUIRE(x && w && y, "NULL tensor");
+    TSC_REQUIRE(B > 0 && L > 0, "bad shape B=%d L=%d", B, L);
+    TSC_REQUIRE(dtype == TSC_F32 || dtype == TSC_BF16, "bad dtype %d", dtype);
+    if (engine == TSC_ENGINE_SIMT)
+        return osconv_simt(direction, x, dtype, w, bias, y, B, L, Cin, Cout, Kmax, s_of_tap, (cudaStream_t)stream);
+    if (engine == TSC_ENGINE_TCGEN05)
+        return osconv_tc(direction, x, dtype, w, bias, y, B, L, Cin, Cout, Kmax, s_of_tap, (cudaStream_t)stream);
+    TSC_REQUIRE(false, "bad engine %d", engine);
+}
+
+size_t tsc_oswgrad_workspace_bytes(int engine, int B, int L, int Cin, int Cout, int Kmax) {
+    using namespace tsc;
+    const int S = engine == TSC_ENGINE_TCGEN05 ? wgrad_tc_splits(B, L, Cin, Cout, Kmax) : wgrad_simt_splits(B, L, Cin, Cout, Kmax);
+    return (size_t)S * Kmax * pad16(Cout) * pad16(Cin) * sizeof(float);
+}
+
+int tsc_oswgrad(int engine, const void* dy, const void* x, int dtype, float* dW, void* workspace, int B, int L, int Cin,
+                int Cout, int Kmax, const int* s_of_tap, tsc_stream_t stream) {
+    using namespace tsc;
+    TSC_REQUIRE(dy && x && dW && workspace, "NULL tensor");
+    TSC_REQUIRE(B > 0 && L > 0, "bad shape B=%d L=%d", B, L);
+    TSC_REQUIRE(dtype == TSC_F32 || dtype == TSC_BF16, "bad dtype %d", dtype);
+    TSC_REQUIRE(Kmax >= 1 && Kmax <= TSC_MAX_TAPS && s_of_tap, "bad kernel bank");
+    TSC_REQUIRE(Cin >= 1 && Cin <= TSC_MAX_CHANNELS && Cout >= 1 && Cout <= TSC_MAX_CHANNELS, "bad channel counts");
+    if (engine == TSC_ENGINE_SIMT)
+        return oswgrad_simt(dy, x, dtype, dW, workspace, B, L, Cin, Cout, Kmax, s_of_tap, (cudaStream_t)stream);
+    if (engine == TSC_ENGINE_TCGEN05)
+        return oswgrad_tc(dy, x, dtype, dW, workspace, B, L, Cin, Cout, Kmax, s_of_tap, (cudaStream_t)stream);
+    TSC_REQUIRE(false, "bad engine %d", engine);
+}
+
+int tsc_debug_read_and_clear_watchdog(int* host_code) {
+    using namespace tsc;
+    int a = 0, b = 0, c = 0, r;
+    if ((r = read_clear_watchdog_conv(&a)) != 0) return r;
+    if ((r = read_clear_watchdog_wgrad(&b)) != 0) return r;
+    if ((r = read_clear_watchdog_gram(&c)) != 0) return r;
+    *host_code = a ? a : (b ? b : c);
+    return 0;
+}
+
+}  // extern "C"

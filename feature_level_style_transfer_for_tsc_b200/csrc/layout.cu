@@ -1,0 +1,176 @@
+// Layout conversion (NCL fp32 <-> c8) and kernel-bank packing.  HBM-bound helpers.
+#include "common.cuh"
+
+namespace tsc {
+
+// ---- NCL fp32 -> c8 (T).  One thread per (b, chunk, l) row of 8 channels.  Reads are coalesced
+// along l for each of the 8 channels (8 x 128 B per warp), the write is one 16/32 B row per thread
+// (contiguous across the warp). ------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) ncl_to_c8_kernel(const float* __restrict__ src, T* __restrict__ dst,
+                                                         int B, int C, int Cpc, int L) {
+    const long long total = (long long)B * Cpc * L;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int l = (int)(i % L);
+        const long long bc = i / L;
+        const int ch = (int)(bc % Cpc);
+        const int b = (int)(bc / Cpc);
+        Row8<T> r;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = ch * 8 + j;
+            r.v[j] = c < C ? __ldg(src + ((long long)b * C + c) * L + l) : 0.f;
+        }
+        r.store(dst + i * 8);
+    }
+}
+
+__global__ void __launch_bounds__(256) c8_to_ncl_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                         int B, int C, int Cpc, int L) {
+    const long long total = (long long)B * Cpc * L;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int l = (int)(i % L);
+        const long long bc = i / L;
+        const int ch = (int)(bc % Cpc);
+        const int b = (int)(bc / Cpc);
+        Row8<float> r;
+        r.load(src + i * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = ch * 8 + j;
+            if (c < C) dst[((long long)b * C + c) * L + l] = r.v[j];
+        }
+    }
+}
+
+// ---- kernel-bank packing -------------------------------------------------------------------------
+// s(t) travels to the device inside the kernel parameter block (no allocation, graph safe).
+// blockIdx.y = index into tt.order; threads stride over the tap's blob [kc-kc_lo][np-n_lo][8].
+static int grid_for(long long n, int block = 256) {
+    long long g = (n + block - 1) / block;
+    const long long cap = 148LL * 16;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ W, T* __restrict__ packed,
+                                                             int direction, int Cin, int Cout, int Kmax,
+                                                             const __grid_constant__ TapTable tt,
+                                                             const __grid_constant__ STable st) {
+    const int t = tt.order[blockIdx.y];
+    const int n_lo = tt.n_lo[t], kc_lo = tt.kc_lo[t];
+    const int nrows = tt.np - n_lo;
+    const int elems = (tt.kc - kc_lo) * nrows * 8;
+    const int wt = direction == TSC_DIR_FWD ? t : Kmax - 1 - t;
+    const int s = st.s[wt];
+    T* blob = packed + (long long)tt.w_off[t] * 8;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < elems; e += gridDim.x * blockDim.x) {
+        const int j = e & 7;
+        const int n = n_lo + (e >> 3) % nrows;
+        const int kch = kc_lo + (e >> 3) / nrows;
+        const int k = kch * 8 + j;
+        const int co = direction == TSC_DIR_FWD ? n : k;
+        const int ci = direction == TSC_DIR_FWD ? k : n;
+        float v = 0.f;
+        if (co < Cout && ci < Cin && co >= s) v = W[((long long)co * Cin + ci) * Kmax + wt];
+        blob[e] = from_f32<T>(v);
+    }
+}
+
+__global__ void __launch_bounds__(256) zero_masked_kernel(float* __restrict__ W, int Cin, int Cout, int Kmax,
+                                                            const __grid_constant__ STable st) {
+    const int total = Cout * Cin * Kmax;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int t = i % Kmax;
+        const int co = i / (Kmax * Cin);
+        if (co < st.s[t]) W[i] = 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dW,
+                                                             int S, int Cin, int Cout, int Kmax, int np, int kcp,
+                                                             const __grid_constant__ STable st) {
+    const int total = Cout * Cin * Kmax;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int t = i % Kmax;
+        const int ci = (i / Kmax) % Cin;
+        const int co = i / (Kmax * Cin);
+        float acc = 0.f;
+        if (co >= st.s[t]) {
+            const long long stride = (long long)Kmax * np * kcp;
+            const float* p = part + ((long long)t * np + co) * kcp + ci;
+            for (int s = 0; s < S; ++s) acc += p[s * stride];
+        }
+        dW[i] = acc;
+    }
+}
+
+int launch_wgrad_reduce(const float* part, float* dW, int S, int Cin, int Cout, int Kmax, int np, int kcp,
+                        const int* s_of_tap, cudaStream_t stream) {
+    STable st;
+    for (int t = 0; t < TSC_MAX_TAPS; ++t) st.s[t] = t < Kmax ? s_of_tap[t] : 0x7fffffff;
+    wgrad_reduce_kernel<<<grid_for((long long)Cout * Cin * Kmax), 256, 0, stream>>>(part, dW, S, Cin, Cout, Kmax,
+                                                                                    np, kcp, st);
+    TSC_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace tsc
+
+extern "C" {
+
+int tsc_ncl_to_c8(const float* src, void* dst, int dst_dtype, int B, int C, int L, tsc_stream_t stream) {
+    using namespace tsc;
+    TSC_REQUIRE(src && dst, "NULL tensor");
+    TSC_REQUIRE(B > 0 && C > 0 && L > 0, "bad shape [%d,%d,%d]", B, C, L);
+    const int Cpc = pad16(C) / 8;
+    const long long rows = (long long)B * Cpc * L;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dst_dtype == TSC_BF16)
+        ncl_to_c8_kernel<__nv_bfloat16><<<grid_for(rows), 256, 0, st>>>(src, (__nv_bfloat16*)dst, B, C, Cpc, L);
+    else if (dst_dtype == TSC_F32)
+        ncl_to_c8_kernel<float><<<grid_for(rows), 256, 0, st>>>(src, (float*)dst, B, C, Cpc, L);
+    else
+        TSC_REQUIRE(false, "bad dtype %d", dst_dtype);
+    TSC_LAUNCH_CHECK();
+    return 0;
+}
+
+int tsc_c8_to_ncl(const float* src, float* dst, int B, int C, int L, tsc_stream_t stream) {
+    using namespace tsc;
+    TSC_REQUIRE(src && dst, "NULL tensor");
+    TSC_REQUIRE(B > 0 && C > 0 && L > 0, "bad shape [%d,%d,%d]", B, C, L);
+    const int Cpc = pad16(C) / 8;
+    c8_to_ncl_kernel<<<grid_for((long long)B * Cpc * L), 256, 0, (cudaStream_t)stream>>>(src, dst, B, C, Cpc, L);
+    TSC_LAUNCH_CHECK();
+    return 0;
+}
+
+int tsc_pack_weights(int direction, int dtype, float* W, void* packed, int Cin, int Cout, int Kmax,
+                     const int* s_of_tap, int zero_masked, tsc_stream_t stream) {
+    using namespace tsc;
+    TSC_REQUIRE(W && packed, "NULL tensor");
+    TapTable tt;
+    if (build_tap_table(direction, Cin, Cout, Kmax, s_of_tap, &tt) != 0) return -1;
+    STable st;
+    for (int t = 0; t < TSC_MAX_TAPS; ++t) st.s[t] = t < Kmax ? s_of_tap[t] : 0x7fffffff;
+    cudaStream_t cs = (cudaStream_t)stream;
+    if (zero_masked) {
+        zero_masked_kernel<<<grid_for((long long)Cout * Cin * Kmax), 256, 0, cs>>>(W, Cin, Cout, Kmax, st);
+        TSC_LAUNCH_CHECK();
+    }
+    const int max_elems = tt.kc * tt.np * 8;
+    dim3 grid(cdiv(max_elems, 256 * 4), tt.n_order);
+    if (dtype == TSC_BF16)
+        pack_weights_kernel<__nv_bfloat16><<<grid, 256, 0, cs>>>(W, (__nv_bfloat16*)packed, direction, Cin, Cout, Kmax, tt, st);
+    else if (dtype == TSC_F32)
+        pack_weights_kernel<float><<<grid, 256, 0, cs>>>(W, (float*)packed, direction, Cin, Cout, Kmax, tt, st);
+    else
+        TSC_REQUIRE(false, "bad dtype %d", dtype);
+    TSC_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,216 @@
+"""Autograd operators of the hot path, built on the C-ABI kernels (ops.py).
+
+* ``os_stack``     -- a chain of OS layers (masked multi-size Conv1d -> BatchNorm1d -> ReLU), optionally with
+                      the 1x1 shortcut branch and the final ``relu(shortcut + block)`` of ``Res_OS_layer``
+                      (reference: OS_CNN/OS_CNN.py:46-77,117-139,155-180).  One autograd node for the whole
+                      chain: activations stay in the c8 device layout between layers, in the engine's operand
+                      dtype, and only the module boundary is NCL fp32.
+* ``adain``        -- per-(b, c) mean/std swap (spec SURVEY.md 8c; site train_and_test.py:552-561).
+* ``gram_style_loss`` -- mean((G(a) - G(b))^2) with G = x x^T / (C L).
+
+The backward of ``os_stack`` never mutates what the forward saved, so ``retain_graph=True``, repeated
+``backward()`` calls and ``torch.autograd.grad`` on sub-losses (train_and_test.py:678-690,741) work.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+
+from . import _lib as L
+from . import ops
+
+ADAIN_EPS = 1e-5
+
+
+@dataclass
+class LayerSpec:
+    """Static description of one conv+BN(+ReLU) layer of a stack."""
+    geom: ops.BankGeometry
+    relu: bool
+    training: bool          # BN mode of this layer for this call
+    momentum: float         # effective momentum for the running statistics (0 disables the update)
+    eps: float
+    running_mean: Optional[torch.Tensor]
+    running_var: Optional[torch.Tensor]
+    zero_masked: bool = True
+
+
+@dataclass
+class StackSpec:
+    layers: List[LayerSpec]
+    shortcut: Optional[LayerSpec]     # 1x1 conv + BN branch added before the final ReLU
+    final_relu: bool                   # relu(shortcut + block) of Res_OS_layer
+    engine: int                        # conv (forward + dgrad) engine; fixes the operand dtype
+    wgrad_engine: int
+
+
+class _Saved:
+    """Per-call buffers kept for backward (all read-only after forward)."""
+    __slots__ = ("x_ops", "ys", "coeffs", "wd", "y_r", "co_r", "wd_r", "B", "Ln")
+
+
+class OSStackFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, spec: StackSpec, x: torch.Tensor, *params: torch.Tensor):
+        eng = spec.engine
+        dt = ops.op_dtype(eng)
+        ops._req(x, name="input")
+        B, C, Ln = x.shape
+        if C != spec.layers[0].geom.cin:
+            raise RuntimeError(f"input has {C} channels, the first OS layer expects {spec.layers[0].geom.cin}")
+        sv = _Saved()
+        sv.B, sv.Ln = B, Ln
+        sv.x_ops, sv.ys, sv.coeffs, sv.wd = [], [], [], []
+        nl = len(spec.layers)
+        h = ops.ncl_to_c8(x, dt)
+        x_op = h
+        out = None
+        need_dgrad_first = x.requires_grad
+        for i, ls in enumerate(spec.layers):
+            W, bias, gamma, beta = params[4 * i: 4 * i + 4]
+            g = ls.geom
+            with torch.no_grad():
+                wf = ops.pack_weights(g, W, L.DIR_FWD, dt, ls.zero_masked)
+                sv.wd.append(ops.pack_weights(g, W, L.DIR_DGRAD, dt, False) if (i > 0 or need_dgrad_first) else None)
+            y = ops.osconv(eng, L.DIR_FWD, g, h, wf, bias)
+            if ls.training:
+                co = ops.bn_stats(y, g.cout, gamma, beta, ls.running_mean if ls.momentum > 0 else None,
+                                  ls.running_var if ls.momentum > 0 else None, ls.momentum, ls.eps)
+            else:
+                co = ops.bn_eval_coeffs(g.cout, gamma, beta, ls.running_mean, ls.running_var, ls.eps)
+            sv.x_ops.append(h)
+            sv.ys.append(y)
+            sv.coeffs.append(co)
+            if i < nl - 1:
+                h = ops.bn_apply(y, co, g.cout, ls.relu, L.OUT_C8_BF16 if dt == L.TSC_BF16 else L.OUT_C8_F32)
+            elif spec.shortcut is None:
+                out = ops.bn_apply(y, co, g.cout, ls.relu, L.OUT_NCL_F32)
+            else:
+                sc = spec.shortcut
+                Wr, br, gr, betar = params[4 * nl: 4 * nl + 4]
+                with torch.no_grad():
+                    wfr = ops.pack_weights(sc.geom, Wr, L.DIR_FWD, dt, False)
+                    sv.wd_r = ops.pack_weights(sc.geom, Wr, L.DIR_DGRAD, dt, False) if need_dgrad_first else None
+                y_r = ops.osconv(eng, L.DIR_FWD, sc.geom, x_op, wfr, br)
+                if sc.training:
+                    co_r = ops.bn_stats(y_r, sc.geom.cout, gr, betar, sc.running_mean if sc.momentum > 0 else None,
+                                        sc.running_var if sc.momentum > 0 else None, sc.momentum, sc.eps)
+                else:
+                    co_r = ops.bn_eval_coeffs(sc.geom.cout, gr, betar, sc.running_mean, sc.running_var, sc.eps)
+                sv.y_r, sv.co_r = y_r, co_r
+                out = ops.bn_apply(y, co, g.cout, spec.final_relu, L.OUT_NCL_F32, y2=y_r, co2=co_r)
+        ctx.spec, ctx.sv = spec, sv
+        ctx.save_for_backward(*params)
+        ctx.x_requires_grad = need_dgrad_first
+        return out
+
+    @staticmethod
+    def backward(ctx, dout: torch.Tensor):
+        spec, sv = ctx.spec, ctx.sv
+        params = ctx.saved_tensors
+        eng = spec.engine
+        dt = ops.op_dtype(eng)
+        nl = len(spec.layers)
+        dout = dout.contiguous().float()
+        dz = ops.ncl_to_c8(dout, L.TSC_F32)
+        grads: List[Optional[torch.Tensor]] = [None] * len(params)
+        dx_short = None
+        # masks of the top of the stack
+        last = spec.layers[-1]
+        if spec.shortcut is not None:
+            top_mask1 = (sv.ys[-1], sv.coeffs[-1]) if spec.final_relu else None
+            top_mask2 = (sv.y_r, sv.co_r) if spec.final_relu else None
+            sc = spec.shortcut
+            Wr, br, gr, betar = params[4 * nl: 4 * nl + 4]
+            s1, s2 = ops.bn_bwd_reduce(dz, sv.y_r, sv.co_r, sc.geom.cout, top_mask1, top_mask2)
+            dy_r = ops.bn_bwd_apply(dz, sv.y_r, sv.co_r, gr, s1, s2, sc.training, sc.geom.cout, dt, top_mask1, top_mask2)
+            C = sc.geom.cout
+            grads[4 * nl + 2] = s2[:C].clone()
+            grads[4 * nl + 3] = s1[:C].clone()
+            grads[4 * nl + 1] = torch.zeros_like(br) if sc.training else (gr * sv.co_r.invstd[:C] * s1[:C])
+            grads[4 * nl + 0] = ops.oswgrad(spec.wgrad_engine, sc.geom, dy_r, sv.x_ops[0])
+            if ctx.x_requires_grad:
+                dx_short = ops.osconv(eng, L.DIR_DGRAD, sc.geom, dy_r, sv.wd_r, None)
+        else:
+            top_mask1 = (sv.ys[-1], sv.coeffs[-1]) if last.relu else None
+            top_mask2 = None
+        for i in range(nl - 1, -1, -1):
+            ls = spec.layers[i]
+            g = ls.geom
+            W, bias, gamma, beta = params[4 * i: 4 * i + 4]
+            y, co = sv.ys[i], sv.coeffs[i]
+            if i == nl - 1:
+                m1, m2 = top_mask1, top_mask2
+            else:
+                m1, m2 = ((y, co) if ls.relu else None), None
+            s1, s2 = ops.bn_bwd_reduce(dz, y, co, g.cout, m1, m2)
+            dy = ops.bn_bwd_apply(dz, y, co, gamma, s1, s2, ls.training, g.cout, dt, m1, m2)
+            C = g.cout
+            grads[4 * i + 2] = s2[:C].clone()
+            grads[4 * i + 3] = s1[:C].clone()
+            # d(bias) = sum dY: identically 0 behind a train-mode BN, gamma*invstd*S1 behind an eval-mode BN
+            grads[4 * i + 1] = torch.zeros_like(bias) if ls.training else (gamma * co.invstd[:C] * s1[:C])
+            grads[4 * i + 0] = ops.oswgrad(spec.wgrad_engine, g, dy, sv.x_ops[i])
+            if i > 0 or ctx.x_requires_grad:
+                dz = ops.osconv(eng, L.DIR_DGRAD, g, dy, sv.wd[i], None)
+        dx = None
+        if ctx.x_requires_grad:
+            if dx_short is not None:
+                dz = dz + dx_short
+            dx = ops.c8_to_ncl(dz, spec.layers[0].geom.cin)
+        return (None, dx, *grads)
+
+
+def os_stack(spec: StackSpec, x: torch.Tensor, params: List[torch.Tensor]) -> torch.Tensor:
+    return OSStackFunction.apply(spec, x, *params)
+
+
+class AdaINFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, content, style, eps):
+        content = content.contiguous()
+        style = style.contiguous()
+        out, stats = ops.adain_fwd(content, style, eps)
+        ctx.save_for_backward(content, style, stats)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        content, style, stats = ctx.saved_tensors
+        dc, ds = ops.adain_bwd(dy.contiguous(), content, style, stats)
+        return dc, ds, None
+
+
+def adain(content: torch.Tensor, style: torch.Tensor, eps: float = ADAIN_EPS) -> torch.Tensor:
+    """out = (content - mu_c)/sigma_c * sigma_s + mu_s per (b, c) row over L; sigma = sqrt(var_unbiased + eps).
+    content/style: [B, C, L] fp32 CUDA, paired by batch index (truncate to the smaller batch)."""
+    if content.shape[0] != style.shape[0]:
+        n = min(content.shape[0], style.shape[0])
+        content, style = content[:n], style[:n]
+    return AdaINFunction.apply(content, style, eps)
+
+
+class GramStyleLossFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, engine):
+        a = a.contiguous()
+        b = b.contiguous()
+        loss, D = ops.gram_loss_fwd(engine, a, b)
+        ctx.save_for_backward(a, b, D)
+        ctx.engine = engine
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        a, b, D = ctx.saved_tensors
+        da, db = ops.gram_loss_bwd(ctx.engine, D, a, b, dloss.contiguous().float())
+        return da, db, None
+
+
+def gram_style_loss(a: torch.Tensor, b: torch.Tensor, engine: Optional[int] = None) -> torch.Tensor:
+    """mean over B*C*C of (G(a) - G(b))^2, G(x) = x x^T / (C L); a, b: [B, C, L] fp32 CUDA."""
+    if a.shape != b.shape:
+        raise RuntimeError(f"gram_style_loss needs equal shapes, got {tuple(a.shape)} and {tuple(b.shape)}")
+    return GramStyleLossFunction.apply(a, b, ops.get_engine("gram") if engine is None else engine)

@@ -1,0 +1,337 @@
+"""Tensor-level wrappers over the C-ABI (one Python function per entry point of include/tsc_b200.h).
+
+PyTorch here is plumbing only: it owns device memory and the current stream.  Every function takes
+CUDA tensors, allocates its outputs with torch, and passes raw pointers + the current stream to
+libtsc_b200.so.  Nothing in this module computes on the host and nothing falls back to torch ops.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+_ENGINE_NAMES = {"simt": L.ENGINE_SIMT, "fp32": L.ENGINE_SIMT, "tcgen05": L.ENGINE_TCGEN05, "bf16": L.ENGINE_TCGEN05}
+# engine per kernel family.  'conv' (forward + dgrad) decides the operand dtype of the whole OS stack:
+# tcgen05 -> bf16 operands (<= 1e-2), simt -> fp32 operands (<= 1e-5).
+_TC_READY = ("conv",)          # families whose tcgen05 kernel exists (the others stay on the SIMT engine)
+_ENGINES = {"conv": L.ENGINE_TCGEN05, "wgrad": L.ENGINE_SIMT, "gram": L.ENGINE_SIMT}
+
+
+def set_engine(name: str, family: Optional[str] = None) -> None:
+    """'tcgen05' (bf16/tf32 operands on the tensor cores, <=1e-2) or 'simt' (fp32 CUDA cores, <=1e-5).
+    family: None (all), 'conv', 'wgrad' or 'gram'."""
+    e = _ENGINE_NAMES[name]
+    for fam in ([family] if family else list(_ENGINES)):
+        if fam not in _ENGINES:
+            raise KeyError(fam)
+        if e == L.ENGINE_TCGEN05 and family is None and fam not in _TC_READY:
+            continue
+        _ENGINES[fam] = e
+    if _ENGINES["conv"] == L.ENGINE_SIMT and _ENGINES["wgrad"] == L.ENGINE_TCGEN05:
+        raise ValueError("the tcgen05 wgrad needs bf16 operands, i.e. the tcgen05 conv engine")
+
+
+def get_engine(family: str = "conv") -> int:
+    return _ENGINES[family]
+
+
+def engine_name(engine: Optional[int] = None) -> str:
+    return "tcgen05" if (engine if engine is not None else _ENGINES["conv"]) == L.ENGINE_TCGEN05 else "simt"
+
+
+def op_dtype(engine: int) -> int:
+    return L.TSC_BF16 if engine == L.ENGINE_TCGEN05 else L.TSC_F32
+
+
+def torch_dtype(dt: int):
+    return torch.bfloat16 if dt == L.TSC_BF16 else torch.float32
+
+
+def pad16(c: int) -> int:
+    return (c + 15) & ~15
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _req(t: torch.Tensor, dtype=torch.float32, name="tensor"):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the tsc_b200 operators have no CPU fallback")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    return t
+
+
+# --------------------------------------------------------------------------------------------------
+# kernel-bank geometry (host integers; mirrors OS_CNN/OS_CNN.py:9-12,23-43,59 of the reference)
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class BankGeometry:
+    cin: int
+    cout: int
+    kmax: int
+    s_of_tap: List[int]
+    lo: List[int] = field(default_factory=list)      # per out channel: first live tap
+    hi: List[int] = field(default_factory=list)      # per out channel: one past the last live tap
+
+    def __post_init__(self):
+        if not (1 <= self.kmax <= L.MAX_TAPS):
+            raise ValueError(f"kernel size {self.kmax} outside [1, {L.MAX_TAPS}]")
+        if not (1 <= self.cin <= L.MAX_CHANNELS and 1 <= self.cout <= L.MAX_CHANNELS):
+            raise ValueError(f"channel counts ({self.cin}, {self.cout}) outside [1, {L.MAX_CHANNELS}]")
+        self.cin_p, self.cout_p = pad16(self.cin), pad16(self.cout)
+        self.s_arr = L.int_array(self.s_of_tap)
+        self.pad_l, self.pad_r = (self.kmax - 1) // 2, self.kmax // 2
+        self._packed_bytes = {}
+
+    def packed_bytes(self, direction: int, dt: int) -> int:
+        key = (direction, dt)
+        if key not in self._packed_bytes:
+            n = L.load().tsc_packed_weight_bytes(direction, dt, self.cin, self.cout, self.kmax, self.s_arr)
+            if n == 0:
+                raise RuntimeError("tsc_packed_weight_bytes failed: " + L.load().tsc_last_error().decode())
+            self._packed_bytes[key] = int(n)
+        return self._packed_bytes[key]
+
+    def live_macs_per_position(self) -> int:
+        return self.cin * sum(h - l for l, h in zip(self.lo, self.hi))
+
+
+def mask_interval(k: int, kmax: int):
+    """Live taps [left, left+k) of a size-k kernel inside the kmax window (OS_CNN/OS_CNN.py:9-12)."""
+    right_zero = -((-(kmax - 1)) // 2) - (-((-(k - 1)) // 2))     # ceil((kmax-1)/2) - ceil((k-1)/2)
+    left = kmax - k - right_zero
+    return left, left + k
+
+
+def bank_geometry(layer_parameters: Sequence[Sequence[int]]) -> BankGeometry:
+    """Geometry of one OS layer from its [(in_ch, out_ch, kernel), ...] list."""
+    kmax = layer_parameters[-1][-1]
+    cin = layer_parameters[0][0]
+    lo, hi = [], []
+    for (_, oc, k) in layer_parameters:
+        l, r = mask_interval(k, kmax)
+        lo += [l] * oc
+        hi += [r] * oc
+    cout = len(lo)
+    s_of_tap = []
+    for t in range(kmax):
+        live = [c for c in range(cout) if lo[c] <= t < hi[c]]
+        first = live[0] if live else cout
+        if live != list(range(first, cout)):
+            raise ValueError("kernel bank is not nested (live channels at a tap must form a suffix)")
+        s_of_tap.append(first)
+    return BankGeometry(cin, cout, kmax, s_of_tap, lo, hi)
+
+
+def dense_geometry(cin: int, cout: int, kernel: int) -> BankGeometry:
+    """A plain Conv1d (every tap live for every channel), e.g. the 1x1 shortcut (OS_CNN.py:155-166)."""
+    return BankGeometry(cin, cout, kernel, [0] * kernel, [0] * cout, [kernel] * cout)
+
+
+# --------------------------------------------------------------------------------------------------
+# wrappers
+# --------------------------------------------------------------------------------------------------
+def ncl_to_c8(x: torch.Tensor, dt: int) -> torch.Tensor:
+    _req(x, name="x")
+    B, C, Ln = x.shape
+    out = torch.empty((B, pad16(C) // 8, Ln, 8), device=x.device, dtype=torch_dtype(dt))
+    L.check(L.load().tsc_ncl_to_c8(_ptr(x), _ptr(out), dt, B, C, Ln, _stream()), "tsc_ncl_to_c8")
+    return out
+
+
+def c8_to_ncl(x8: torch.Tensor, C: int) -> torch.Tensor:
+    _req(x8, name="x_c8")
+    B, _, Ln, _ = x8.shape
+    out = torch.empty((B, C, Ln), device=x8.device, dtype=torch.float32)
+    L.check(L.load().tsc_c8_to_ncl(_ptr(x8), _ptr(out), B, C, Ln, _stream()), "tsc_c8_to_ncl")
+    return out
+
+
+def pack_weights(g: BankGeometry, W: torch.Tensor, direction: int, dt: int, zero_masked: bool) -> torch.Tensor:
+    _req(W, name="weight")
+    if tuple(W.shape) != (g.cout, g.cin, g.kmax):
+        raise RuntimeError(f"weight shape {tuple(W.shape)} != {(g.cout, g.cin, g.kmax)}")
+    nbytes = g.packed_bytes(direction, dt)
+    packed = torch.empty(nbytes // (2 if dt == L.TSC_BF16 else 4), device=W.device, dtype=torch_dtype(dt))
+    L.check(L.load().tsc_pack_weights(direction, dt, _ptr(W), _ptr(packed), g.cin, g.cout, g.kmax, g.s_arr,
+                                      1 if zero_masked else 0, _stream()), "tsc_pack_weights")
+    return packed
+
+
+def osconv(engine: int, direction: int, g: BankGeometry, x8: torch.Tensor, w_packed: torch.Tensor,
+           bias: Optional[torch.Tensor]) -> torch.Tensor:
+    dt = L.TSC_BF16 if x8.dtype == torch.bfloat16 else L.TSC_F32
+    _req(x8, torch_dtype(dt), "x_c8")
+    _req(w_packed, torch_dtype(dt), "w_packed")
+    B, kc, Ln, _ = x8.shape
+    cin_side = g.cin_p if direction == L.DIR_FWD else g.cout_p
+    cout_side = g.cout_p if direction == L.DIR_FWD else g.cin_p
+    if kc * 8 != cin_side:
+        raise RuntimeError(f"x_c8 has {kc * 8} padded channels, expected {cin_side}")
+    if bias is not None:
+        _req(bias, name="bias")
+    y = torch.empty((B, cout_side // 8, Ln, 8), device=x8.device, dtype=torch.float32)
+    L.check(L.load().tsc_osconv(engine, direction, _ptr(x8), dt, _ptr(w_packed), _ptr(bias), _ptr(y), B, Ln,
+                                g.cin, g.cout, g.kmax, g.s_arr, _stream()), "tsc_osconv")
+    return y
+
+
+def oswgrad(engine: int, g: BankGeometry, dy8: torch.Tensor, x8: torch.Tensor) -> torch.Tensor:
+    dt = L.TSC_BF16 if x8.dtype == torch.bfloat16 else L.TSC_F32
+    _req(x8, torch_dtype(dt), "x_c8")
+    _req(dy8, torch_dtype(dt), "dy_c8")
+    B, _, Ln, _ = x8.shape
+    lib = L.load()
+    ws = torch.empty(int(lib.tsc_oswgrad_workspace_bytes(engine, B, Ln, g.cin, g.cout, g.kmax)) // 4 + 4,
+                     device=x8.device, dtype=torch.float32)
+    dW = torch.empty((g.cout, g.cin, g.kmax), device=x8.device, dtype=torch.float32)
+    L.check(lib.tsc_oswgrad(engine, _ptr(dy8), _ptr(x8), dt, _ptr(dW), _ptr(ws), B, Ln, g.cin, g.cout, g.kmax,
+                            g.s_arr, _stream()), "tsc_oswgrad")
+    return dW
+
+
+@dataclass
+class BNCoeffs:
+    mean: torch.Tensor
+    invstd: torch.Tensor
+    scale: torch.Tensor
+    shift: torch.Tensor
+
+
+def _bn_ws(B, C, Ln, device):
+    n = int(L.load().tsc_bn_workspace_bytes(B, C, Ln)) // 4 + 4
+    return torch.empty(n, device=device, dtype=torch.float32)
+
+
+def bn_stats(y8: torch.Tensor, C: int, gamma, beta, running_mean, running_var, momentum: float, eps: float) -> BNCoeffs:
+    _req(y8, name="y_c8")
+    B, cpc, Ln, _ = y8.shape
+    cp = cpc * 8
+    buf = torch.empty((4, cp), device=y8.device, dtype=torch.float32)
+    co = BNCoeffs(buf[0], buf[1], buf[2], buf[3])
+    L.check(L.load().tsc_bn_stats(_ptr(y8), _ptr(gamma), _ptr(beta), _ptr(_bn_ws(B, C, Ln, y8.device)), _ptr(co.mean),
+                                  _ptr(co.invstd), _ptr(co.scale), _ptr(co.shift), _ptr(running_mean),
+                                  _ptr(running_var), float(momentum), float(eps), B, C, Ln, _stream()), "tsc_bn_stats")
+    return co
+
+
+def bn_eval_coeffs(C: int, gamma, beta, running_mean, running_var, eps: float) -> BNCoeffs:
+    cp = pad16(C)
+    buf = torch.empty((4, cp), device=gamma.device, dtype=torch.float32)
+    co = BNCoeffs(buf[0], buf[1], buf[2], buf[3])
+    L.check(L.load().tsc_bn_eval_coeffs(_ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), float(eps),
+                                        _ptr(co.mean), _ptr(co.invstd), _ptr(co.scale), _ptr(co.shift), C, _stream()),
+            "tsc_bn_eval_coeffs")
+    return co
+
+
+def bn_apply(y8, co: BNCoeffs, C: int, relu: bool, out_kind: int, y2=None, co2: Optional[BNCoeffs] = None):
+    _req(y8, name="y_c8")
+    B, cpc, Ln, _ = y8.shape
+    if out_kind == L.OUT_NCL_F32:
+        out = torch.empty((B, C, Ln), device=y8.device, dtype=torch.float32)
+    else:
+        out = torch.empty((B, cpc, Ln, 8), device=y8.device,
+                          dtype=torch.bfloat16 if out_kind == L.OUT_C8_BF16 else torch.float32)
+    L.check(L.load().tsc_bn_apply(_ptr(y8), _ptr(co.scale), _ptr(co.shift), _ptr(y2),
+                                  _ptr(co2.scale if co2 else None), _ptr(co2.shift if co2 else None),
+                                  1 if relu else 0, _ptr(out), out_kind, B, C, Ln, _stream()), "tsc_bn_apply")
+    return out
+
+
+def bn_bwd_reduce(dz8, y8, co: BNCoeffs, C: int, mask1=None, mask2=None):
+    """mask1/mask2: optional (y_c8, BNCoeffs) pre-activation operands the ReLU mask is recomputed from."""
+    B, cpc, Ln, _ = y8.shape
+    buf = torch.empty((2, cpc * 8), device=y8.device, dtype=torch.float32)
+    m1y, m1c = mask1 if mask1 else (None, None)
+    m2y, m2c = mask2 if mask2 else (None, None)
+    L.check(L.load().tsc_bn_bwd_reduce(_ptr(dz8), _ptr(y8), _ptr(co.mean), _ptr(co.invstd),
+                                       _ptr(m1y), _ptr(m1c.scale if m1c else None), _ptr(m1c.shift if m1c else None),
+                                       _ptr(m2y), _ptr(m2c.scale if m2c else None), _ptr(m2c.shift if m2c else None),
+                                       _ptr(_bn_ws(B, C, Ln, y8.device)), _ptr(buf[0]), _ptr(buf[1]), B, C, Ln,
+                                       _stream()), "tsc_bn_bwd_reduce")
+    return buf[0], buf[1]
+
+
+def bn_bwd_apply(dz8, y8, co: BNCoeffs, gamma, s1, s2, training: bool, C: int, dt: int, mask1=None, mask2=None):
+    B, cpc, Ln, _ = y8.shape
+    dy = torch.empty((B, cpc, Ln, 8), device=y8.device, dtype=torch_dtype(dt))
+    m1y, m1c = mask1 if mask1 else (None, None)
+    m2y, m2c = mask2 if mask2 else (None, None)
+    L.check(L.load().tsc_bn_bwd_apply(_ptr(dz8), _ptr(y8), _ptr(co.mean), _ptr(co.invstd), _ptr(gamma), _ptr(s1), _ptr(s2),
+                                      1 if training else 0,
+                                      _ptr(m1y), _ptr(m1c.scale if m1c else None), _ptr(m1c.shift if m1c else None),
+                                      _ptr(m2y), _ptr(m2c.scale if m2c else None), _ptr(m2c.shift if m2c else None),
+                                      _ptr(dy), dt, B, C, Ln, _stream()), "tsc_bn_bwd_apply")
+    return dy
+
+
+def rowstats(x: torch.Tensor):
+    _req(x, name="x")
+    Ln = x.shape[-1]
+    R = x.numel() // Ln
+    mean = torch.empty(x.shape[:-1], device=x.device, dtype=torch.float32)
+    var = torch.empty_like(mean)
+    L.check(L.load().tsc_rowstats_welford(_ptr(x), _ptr(mean), _ptr(var), R, Ln, _stream()), "tsc_rowstats_welford")
+    return mean, var
+
+
+def adain_fwd(content, style, eps: float):
+    _req(content, name="content"); _req(style, name="style")
+    if content.shape != style.shape:
+        raise RuntimeError(f"content {tuple(content.shape)} and style {tuple(style.shape)} must have the same shape")
+    Ln = content.shape[-1]
+    R = content.numel() // Ln
+    out = torch.empty_like(content)
+    stats = torch.empty((R, 4), device=content.device, dtype=torch.float32)
+    L.check(L.load().tsc_adain_fwd(_ptr(content), _ptr(style), _ptr(out), _ptr(stats), float(eps), R, Ln, _stream()),
+            "tsc_adain_fwd")
+    return out, stats
+
+
+def adain_bwd(dy, content, style, stats):
+    _req(dy, name="dy")
+    Ln = content.shape[-1]
+    R = content.numel() // Ln
+    dc, ds = torch.empty_like(content), torch.empty_like(style)
+    L.check(L.load().tsc_adain_bwd(_ptr(dy), _ptr(content), _ptr(style), _ptr(stats), _ptr(dc), _ptr(ds), R, Ln, _stream()),
+            "tsc_adain_bwd")
+    return dc, ds
+
+
+def gram_loss_fwd(engine: int, a, s):
+    _req(a, name="a"); _req(s, name="s")
+    B, C, Ln = a.shape
+    D = torch.empty((B, C, C), device=a.device, dtype=torch.float32)
+    loss = torch.empty((), device=a.device, dtype=torch.float32)
+    ws = torch.empty(int(L.load().tsc_gram_workspace_bytes(B, C, Ln)) // 4 + 4, device=a.device, dtype=torch.float32)
+    L.check(L.load().tsc_gram_loss_fwd(engine, _ptr(a), _ptr(s), _ptr(D), _ptr(loss), _ptr(ws), B, C, Ln, _stream()),
+            "tsc_gram_loss_fwd")
+    return loss, D
+
+
+def gram_loss_bwd(engine: int, D, a, s, dloss):
+    B, C, Ln = a.shape
+    _req(dloss, name="dloss")
+    da, ds = torch.empty_like(a), torch.empty_like(s)
+    L.check(L.load().tsc_gram_loss_bwd(engine, _ptr(D), _ptr(a), _ptr(s), _ptr(dloss), _ptr(da), _ptr(ds), B, C, Ln,
+                                       _stream()), "tsc_gram_loss_bwd")
+    return da, ds
+
+
+def read_watchdog() -> int:
+    code = ctypes.c_int(0)
+    L.check(L.load().tsc_debug_read_and_clear_watchdog(ctypes.byref(code)), "tsc_debug_read_and_clear_watchdog")
+    return code.value

@@ -1,0 +1,141 @@
+/*
+ * tsc_b200.h -- C-ABI of libtsc_b200.so: the sm_100a kernels behind the OS-CNN + feature-level
+ * style-transfer training hot path.
+ *
+ * The reference (BaeHann/feature_level_style_transfer_for_TSC) is pure Python/PyTorch: it has no
+ * FFI of its own, its nn.Module classes ARE the boundary.  Each entry point below
+ * therefore cites the reference *operation* (file:line under /root/reference) it replaces; the
+ * Python host side (feature_level_style_transfer_for_tsc_b200/) binds these with ctypes and keeps
+ * the reference's module names, constructor/forward signatures and state_dict keys.
+ *
+ * Conventions (all functions):
+ *   - plain pointers and sizes only; every buffer (incl. workspace) is owned by the caller;
+ *     device pointers unless the parameter is documented as HOST;
+ *   - no allocation, no host synchronisation, no global mutable state: safe to capture in a
+ *     CUDA graph, reentrant across streams and threads;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - return 0 = OK; < 0 = bad argument / unsupported shape (text via tsc_last_error(), thread
+ *     local); > 0 = a cudaError_t from the launch.  Nothing throws, nothing aborts;
+ *   - there is no CPU fallback: without a CUDA device every launch returns a cudaError_t.
+ *
+ * Device data layout "c8": a logical [B, C, L] activation is stored as [B][Cp/8][L][8] with
+ * Cp = tsc_pad_channels(C) (multiple of 16); pad channels hold zeros.  One (b, chunk) slab is
+ * L rows of 8 channels (16 B in bf16, 32 B in fp32).  It is K-major for the forward/dgrad
+ * implicit GEMM (contraction over channels) and MN-major for wgrad / Gram (contraction over
+ * positions), and a convolution tap is a pure row offset in it.
+ */
+#ifndef TSC_B200_H
+#define TSC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSC_VERSION 100
+#define TSC_MAX_TAPS 96          /* largest supported Kmax (reference caps it at 89, train_and_test.py:40) */
+#define TSC_MAX_CHANNELS 256     /* largest padded channel count of one OS layer (reference: <= 228) */
+
+typedef void* tsc_stream_t;      /* cudaStream_t */
+
+enum tsc_dtype { TSC_F32 = 0, TSC_BF16 = 1 };
+/* engine: SIMT = fp32 CUDA-core arithmetic (the "fp32, <=1e-5" mode; also accepts bf16 operands,
+ * which makes it the bit-faithful checker of the tensor-core engine); TCGEN05 = bf16 operands,
+ * fp32 accumulation in TMEM (the "<=1e-2" mode). */
+enum tsc_engine { TSC_ENGINE_SIMT = 0, TSC_ENGINE_TCGEN05 = 1 };
+enum tsc_direction { TSC_DIR_FWD = 0, TSC_DIR_DGRAD = 1 };
+enum tsc_out_kind { TSC_OUT_C8_F32 = 0, TSC_OUT_C8_BF16 = 1, TSC_OUT_NCL_F32 = 2 };
+
+int tsc_version(void);
+const char* tsc_last_error(void);
+int tsc_pad_channels(int C);                       /* round up to 16 */
+/* 1 when the current device can run the tcgen05 engine (compute capability 10.x) */
+int tsc_device_supports_tcgen05(void);
+
+/* ---- layout conversion at the module boundary (reference tensors are NCL fp32, OS_CNN.py:67) ---- */
+int tsc_ncl_to_c8(const float* src_ncl, void* dst_c8, int dst_dtype, int B, int C, int L, tsc_stream_t stream);
+int tsc_c8_to_ncl(const float* src_c8, float* dst_ncl, int B, int C, int L, tsc_stream_t stream);
+
+/* ---- masked kernel bank: replaces `weight.data = weight * weight_mask` (OS_CNN.py:68) ----------
+ * s_of_tap (HOST, Kmax ints): first out channel whose prime kernel covers tap t; channels >= s(t)
+ * are live at t (the bank is nested, OS_CNN.py:9-12,28-42).  s(t) >= Cout marks a dead tap.
+ * W is the reference parameter [Cout, Cin, Kmax] fp32.  FWD packs W for Y = conv(X); DGRAD packs
+ * the tap-reversed transpose for dX = conv^T(dY).  Only live (channel, tap) pairs are stored.
+ * When zero_masked != 0 the masked taps of W itself are zeroed in place, as the reference does. */
+size_t tsc_packed_weight_bytes(int direction, int dtype, int Cin, int Cout, int Kmax, const int* s_of_tap);
+int tsc_pack_weights(int direction, int dtype, float* W, void* packed, int Cin, int Cout, int Kmax,
+                     const int* s_of_tap, int zero_masked, tsc_stream_t stream);
+
+/* ---- multi-kernel-size Conv1d as one implicit GEMM: replaces ConstantPad1d + Conv1d
+ * (OS_CNN.py:70-71, 163-164) and their cuDNN/oneDNN dgrad -------------------------------------
+ * FWD  : x = X  [B, Cin, L] c8(dtype), y = Y  [B, Cout, L] c8 fp32, bias[Cout] or NULL.
+ * DGRAD: x = dY [B, Cout, L] c8(dtype), y = dX [B, Cin, L] c8 fp32, bias ignored.
+ * Zero padding (pad_left=(Kmax-1)/2, pad_right=Kmax/2, OS_CNN.py:59) is implicit. */
+int tsc_osconv(int engine, int direction, const void* x_c8, int dtype, const void* w_packed, const float* bias,
+               float* y_c8, int B, int L, int Cin, int Cout, int Kmax, const int* s_of_tap, tsc_stream_t stream);
+
+/* ---- weight gradient on live taps only (masked taps get exact zeros) ---------------
+ * dW[co,ci,t] = sum_{b,l} dY[b,co,l] * X[b,ci,l+t-pad_left];  dy/x c8(dtype); dW [Cout,Cin,Kmax] fp32.
+ * Deterministic: partial sums per position split, then an ordered reduction (no float atomics). */
+size_t tsc_oswgrad_workspace_bytes(int engine, int B, int L, int Cin, int Cout, int Kmax);
+int tsc_oswgrad(int engine, const void* dy_c8, const void* x_c8, int dtype, float* dW, void* workspace,
+                int B, int L, int Cin, int Cout, int Kmax, const int* s_of_tap, tsc_stream_t stream);
+
+/* ---- BatchNorm1d (+ReLU, + shortcut add): replaces OS_CNN.py:72-74, 165, 176-180 --------------
+ * tsc_bn_stats: per-channel Welford over (B, L) of y [B,C,L] c8 fp32 -> mean, invstd=1/sqrt(var_b+eps),
+ *   scale = gamma*invstd, shift = beta - mean*scale (all [Cp]); running stats (nullable) updated with
+ *   momentum and the UNBIASED variance, as torch does.
+ * tsc_bn_eval_coeffs: the same coefficients from the running statistics (eval mode with grad,
+ *   train_and_test.py:583-586). */
+size_t tsc_bn_workspace_bytes(int B, int C, int L);
+int tsc_bn_stats(const float* y_c8, const float* gamma, const float* beta, float* workspace,
+                 float* mean, float* invstd, float* scale, float* shift,
+                 float* running_mean, float* running_var, float momentum, float eps,
+                 int B, int C, int L, tsc_stream_t stream);
+int tsc_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                       float eps, float* mean, float* invstd, float* scale, float* shift, int C, tsc_stream_t stream);
+/* out = act(scale*y + shift [+ scale2*y2 + shift2]), act = relu when relu != 0. */
+int tsc_bn_apply(const float* y_c8, const float* scale, const float* shift,
+                 const float* y2_c8, const float* scale2, const float* shift2,
+                 int relu, void* out, int out_kind, int B, int C, int L, tsc_stream_t stream);
+/* backward, pass 1: d = dz * [act'(.)] ; S1 = sum d ; S2 = sum d * (y-mean)*invstd  (per channel).
+ * The activation mask is recomputed from (ym, scale, shift [, ym2, scale2, shift2]); pass ym = NULL
+ * for "no ReLU". */
+int tsc_bn_bwd_reduce(const float* dz_c8, const float* y_c8, const float* mean, const float* invstd,
+                      const float* ym_c8, const float* scale, const float* shift,
+                      const float* ym2_c8, const float* scale2, const float* shift2,
+                      float* workspace, float* s1, float* s2, int B, int C, int L, tsc_stream_t stream);
+/* backward, pass 2: dy = gamma*invstd * (d - S1/N - yhat*S2/N) (training) or gamma*invstd*d (eval),
+ * written as c8 (dy_dtype) -- the operand of dgrad and wgrad. */
+int tsc_bn_bwd_apply(const float* dz_c8, const float* y_c8, const float* mean, const float* invstd,
+                     const float* gamma, const float* s1, const float* s2, int training,
+                     const float* ym_c8, const float* scale, const float* shift,
+                     const float* ym2_c8, const float* scale2, const float* shift2,
+                     void* dy_c8, int dy_dtype, int B, int C, int L, tsc_stream_t stream);
+
+/* ---- feature-level style transfer (inserted at train_and_test.py:552-561; no reference operator,
+ * spec = SURVEY 8c).  Rows are the (b, c) rows of an NCL fp32 tensor: R = B*C rows of L floats. ---- */
+int tsc_rowstats_welford(const float* x, float* mean, float* var_unbiased, int R, int L, tsc_stream_t stream);
+/* stats[R][4] = (mu_c, sigma_c, mu_s, sigma_s), sigma = sqrt(var_unbiased + eps) */
+int tsc_adain_fwd(const float* content, const float* style, float* out, float* stats, float eps,
+                  int R, int L, tsc_stream_t stream);
+int tsc_adain_bwd(const float* dy, const float* content, const float* style, const float* stats,
+                  float* dcontent, float* dstyle, int R, int L, tsc_stream_t stream);
+/* D[b] = (a_b a_b^T - s_b s_b^T)/(C L)  ([B,C,C] fp32, kept for backward); loss = mean(D^2). */
+size_t tsc_gram_workspace_bytes(int B, int C, int L);
+int tsc_gram_loss_fwd(int engine, const float* a, const float* s, float* D, float* loss, float* workspace,
+                      int B, int C, int L, tsc_stream_t stream);
+/* da = g * 4/(B C^3 L) * D a ; ds = -g * 4/(B C^3 L) * D s ; g = *dloss (device scalar). */
+int tsc_gram_loss_bwd(int engine, const float* D, const float* a, const float* s, const float* dloss,
+                      float* da, float* ds, int B, int C, int L, tsc_stream_t stream);
+
+/* ---- debugging aid: the tcgen05 kernels bound every mbarrier wait; a timed-out wait stores a
+ * non-zero code here (device word, read back by the caller when it wants to). */
+int tsc_debug_read_and_clear_watchdog(int* host_code);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSC_B200_H */

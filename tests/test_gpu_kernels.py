@@ -1,0 +1,275 @@
+"""Op-level parity of every C-ABI kernel against the oracle, on identical inputs (test kernels
+op by op; tolerances: fp32 SIMT engine <= 1e-5 scale-relative, tcgen05/bf16 engine <= 1e-2).
+All tests call through the C-ABI (ctypes -> libtsc_b200.so)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+from oracle import os_cnn as O
+from oracle import style as S
+
+pytestmark = pytest.mark.gpu
+
+TOL_F32 = 1e-5
+TOL_BF16 = 1e-2
+
+
+@pytest.fixture(scope="module")
+def T():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import feature_level_style_transfer_for_tsc_b200 as pkg
+    pkg._lib.load()          # fails loudly when the extension is missing
+    return pkg
+
+
+def c8_ref(x, dtype=torch.float32):
+    """independent torch statement of the c8 layout: [B,C,L] -> [B,Cp/8,L,8]"""
+    B, C, L = x.shape
+    Cp = (C + 15) // 16 * 16
+    xp = F.pad(x, (0, 0, 0, Cp - C))
+    return xp.reshape(B, Cp // 8, 8, L).permute(0, 1, 3, 2).contiguous().to(dtype)
+
+
+def c8_to_ncl_ref(x8, C):
+    B, cpc, L, _ = x8.shape
+    return x8.float().permute(0, 1, 3, 2).reshape(B, cpc * 8, L)[:, :C].contiguous()
+
+
+BANKS = {
+    "small7": [(3, 4, 1), (3, 4, 2), (3, 4, 3), (3, 4, 5), (3, 4, 7)],
+    "mid13": [(20, 5, k) for k in (1, 2, 3, 5, 7, 11, 13)],
+    "even2": [(30, 20, 1), (30, 20, 2)],
+    "cfg2_l1": O.trainer_layer_lists(9, 128)[0][1],       # 72 -> 228, Kmax 31
+    "cfg2_l0": O.trainer_layer_lists(9, 128)[0][0],       # 9 -> 72
+    "cfg2_l2": O.trainer_layer_lists(9, 128)[0][2],       # 228 -> 144, Kmax 2
+    "cfg4_l1": O.trainer_layer_lists(3, 1024)[0][1],      # 25 -> 225, Kmax 89
+    "one": [(5, 7, 1)],
+}
+SHAPES = {"small7": (3, 50), "mid13": (2, 160), "even2": (2, 96), "cfg2_l1": (3, 128), "cfg2_l0": (2, 128),
+          "cfg2_l2": (2, 128), "cfg4_l1": (1, 300), "one": (2, 33)}
+
+
+def make_case(name, seed=0):
+    layer = BANKS[name]
+    g = O.bank_geometry(layer)
+    B, L = SHAPES[name]
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, g["cin"], L, generator=gen)
+    w = torch.randn(g["cout"], g["cin"], g["kmax"], generator=gen) / np.sqrt(g["cin"] * 3.0)
+    b = torch.randn(g["cout"], generator=gen)
+    dy = torch.randn(B, g["cout"], L, generator=gen)
+    return layer, g, x, w, b, dy
+
+
+def test_layout_roundtrip(T):
+    ops, L = T.ops, T._lib
+    x = torch.randn(3, 21, 77)
+    xd = x.cuda()
+    for dt, td in ((L.TSC_F32, torch.float32), (L.TSC_BF16, torch.bfloat16)):
+        x8 = ops.ncl_to_c8(xd, dt)
+        assert x8.shape == (3, 4, 77, 8) and x8.dtype == td
+        assert torch.equal(x8.cpu(), c8_ref(x, td))
+    back = ops.c8_to_ncl(ops.ncl_to_c8(xd, L.TSC_F32), 21)
+    assert torch.equal(back.cpu(), x)
+
+
+@pytest.mark.parametrize("name", list(BANKS))
+def test_conv_fwd_dgrad_wgrad_simt_fp32(T, name):
+    ops, L = T.ops, T._lib
+    layer, g, x, w, b, dy = make_case(name)
+    geom = ops.bank_geometry(layer)
+    assert geom.s_of_tap == g["s_of_tap"]
+    wd = w.clone().cuda()
+    wf = ops.pack_weights(geom, wd, L.DIR_FWD, L.TSC_F32, True)
+    mask = torch.from_numpy(O.build_mask(layer))
+    assert torch.equal(wd.cpu(), w * mask)            # weight.data = weight * mask (OS_CNN.py:68)
+    y8 = ops.osconv(L.ENGINE_SIMT, L.DIR_FWD, geom, ops.ncl_to_c8(x.cuda(), L.TSC_F32), wf, b.cuda())
+    y = c8_to_ncl_ref(y8.cpu(), g["cout"])
+    y_ref = O.masked_conv(x.double(), w.double(), b.double(), layer)
+    assert rel_err(y, y_ref) < TOL_F32
+    full = y8.cpu().permute(0, 1, 3, 2).reshape(x.shape[0], -1, x.shape[2])
+    if geom.cout_p > g["cout"]:
+        assert float(full[:, g["cout"]:].abs().max()) == 0.0          # pad channels stay zero
+    # dgrad
+    wdg = ops.pack_weights(geom, wd, L.DIR_DGRAD, L.TSC_F32, False)
+    dx8 = ops.osconv(L.ENGINE_SIMT, L.DIR_DGRAD, geom, ops.ncl_to_c8(dy.cuda(), L.TSC_F32), wdg, None)
+    dx = ops.c8_to_ncl(dx8, g["cin"]).cpu()
+    assert rel_err(dx, O.conv_dgrad(dy.double(), w.double(), layer)) < TOL_F32
+    # wgrad
+    dw = ops.oswgrad(L.ENGINE_SIMT, geom, ops.ncl_to_c8(dy.cuda(), L.TSC_F32), ops.ncl_to_c8(x.cuda(), L.TSC_F32)).cpu()
+    dw_ref = O.conv_wgrad(dy.double(), x.double(), layer)
+    assert rel_err(dw, dw_ref) < TOL_F32
+    assert float((dw * (1 - mask)).abs().max()) == 0.0      # masked taps: exact zeros
+
+
+@pytest.mark.parametrize("name", list(BANKS))
+def test_conv_tcgen05_matches_simt_on_bf16_operands(T, name):
+    """The tensor-core engine against (a) the SIMT engine fed the same bf16 operands (same products, fp32
+    accumulation: only the summation order differs) and (b) the fp64 oracle at the bf16 tolerance."""
+    ops, L = T.ops, T._lib
+    if not L.load().tsc_device_supports_tcgen05():
+        pytest.skip("device has no tcgen05")
+    layer, g, x, w, b, dy = make_case(name, seed=1)
+    geom = ops.bank_geometry(layer)
+    wd = w.clone().cuda()
+    for direction, inp, bias in ((L.DIR_FWD, x, b.cuda()), (L.DIR_DGRAD, dy, None)):
+        wp = ops.pack_weights(geom, wd, direction, L.TSC_BF16, direction == L.DIR_FWD)
+        in8 = ops.ncl_to_c8(inp.cuda(), L.TSC_BF16)
+        y_tc = ops.osconv(L.ENGINE_TCGEN05, direction, geom, in8, wp, bias)
+        torch.cuda.synchronize()
+        assert ops.read_watchdog() == 0, "tcgen05 pipeline timed out"
+        y_simt = ops.osconv(L.ENGINE_SIMT, direction, geom, in8, wp, bias)
+        assert rel_err(y_tc.cpu(), y_simt.cpu()) < 2e-5, f"direction {direction}"
+        cout = g["cout"] if direction == L.DIR_FWD else g["cin"]
+        ref = (O.masked_conv(x.double(), w.double(), b.double(), layer) if direction == L.DIR_FWD
+               else O.conv_dgrad(dy.double(), w.double(), layer))
+        assert rel_err(c8_to_ncl_ref(y_tc.cpu(), cout), ref) < TOL_BF16
+
+
+@pytest.mark.parametrize("name", list(BANKS))
+def test_wgrad_tcgen05(T, name):
+    ops, L = T.ops, T._lib
+    if not L.load().tsc_device_supports_tcgen05():
+        pytest.skip("device has no tcgen05")
+    layer, g, x, w, b, dy = make_case(name, seed=2)
+    geom = ops.bank_geometry(layer)
+    dy8, x8 = ops.ncl_to_c8(dy.cuda(), L.TSC_BF16), ops.ncl_to_c8(x.cuda(), L.TSC_BF16)
+    dw_tc = ops.oswgrad(L.ENGINE_TCGEN05, geom, dy8, x8)
+    torch.cuda.synchronize()
+    assert ops.read_watchdog() == 0, "tcgen05 pipeline timed out"
+    dw_simt = ops.oswgrad(L.ENGINE_SIMT, geom, dy8, x8)
+    assert rel_err(dw_tc.cpu(), dw_simt.cpu()) < 5e-5
+    mask = torch.from_numpy(O.build_mask(layer))
+    assert float((dw_tc.cpu() * (1 - mask)).abs().max()) == 0.0
+    assert rel_err(dw_tc.cpu(), O.conv_wgrad(dy.double(), x.double(), layer)) < TOL_BF16
+
+
+@pytest.mark.parametrize("B,C,L", [(4, 20, 50), (16, 72, 128), (3, 228, 128), (2, 7, 1000)])
+def test_batchnorm_fwd_bwd(T, B, C, L):
+    ops, Lb = T.ops, T._lib
+    gen = torch.Generator().manual_seed(3)
+    y = torch.randn(B, C, L, generator=gen) * 2 + 0.5
+    y2 = torch.randn(B, C, L, generator=gen)
+    gamma = torch.rand(C, generator=gen) + 0.5
+    beta = torch.randn(C, generator=gen)
+    dz = torch.randn(B, C, L, generator=gen)
+    rm, rv = torch.randn(C, generator=gen) * 0.1, torch.rand(C, generator=gen) + 0.5
+    y8 = ops.ncl_to_c8(y.cuda(), Lb.TSC_F32)
+    # --- training statistics
+    rm_d, rv_d = rm.clone().cuda(), rv.clone().cuda()
+    co = ops.bn_stats(y8, C, gamma.cuda(), beta.cuda(), rm_d, rv_d, 0.1, 1e-5)
+    yd = y.double()
+    mean, var = yd.mean((0, 2)), yd.var((0, 2), unbiased=False)
+    assert rel_err(co.mean.cpu()[:C], mean) < 1e-6
+    assert rel_err(co.invstd.cpu()[:C], 1 / torch.sqrt(var + 1e-5)) < 1e-6
+    n = B * L
+    assert rel_err(rm_d.cpu(), 0.9 * rm + 0.1 * mean) < 1e-6
+    assert rel_err(rv_d.cpu(), 0.9 * rv + 0.1 * var * n / (n - 1)) < 1e-6
+    # --- apply (+relu), all output kinds
+    sd = {"weight": gamma.double(), "bias": beta.double(), "running_mean": rm.double(), "running_var": rv.double(),
+          "num_batches_tracked": torch.tensor(0)}
+    z_ref = torch.relu(O.batch_norm(yd, sd, "", True, update_running=False))
+    z_ncl = ops.bn_apply(y8, co, C, True, Lb.OUT_NCL_F32).cpu()
+    assert rel_err(z_ncl, z_ref) < TOL_F32
+    z8 = ops.bn_apply(y8, co, C, True, Lb.OUT_C8_F32).cpu()
+    assert torch.equal(c8_to_ncl_ref(z8, C), z_ncl)
+    zb = ops.bn_apply(y8, co, C, True, Lb.OUT_C8_BF16).cpu()
+    assert torch.equal(zb, c8_ref(z_ncl, torch.bfloat16))
+    # --- backward, train mode with relu
+    dz8 = ops.ncl_to_c8(dz.cuda(), Lb.TSC_F32)
+    s1, s2 = ops.bn_bwd_reduce(dz8, y8, co, C, (y8, co))
+    dy8 = ops.bn_bwd_apply(dz8, y8, co, gamma.cuda(), s1, s2, True, C, Lb.TSC_F32, (y8, co))
+    dy_ref, dg_ref, db_ref = O.bn_relu_backward(dz.double(), yd, gamma.double(), mean, var, (z_ref > 0).double(), True)
+    assert rel_err(ops.c8_to_ncl(dy8, C).cpu(), dy_ref) < 2e-5
+    assert rel_err(s2.cpu()[:C], dg_ref) < 2e-5 and rel_err(s1.cpu()[:C], db_ref) < 2e-5
+    # --- eval mode (running stats, gradient still flows: train_and_test.py:583-586)
+    coe = ops.bn_eval_coeffs(C, gamma.cuda(), beta.cuda(), rm.cuda(), rv.cuda(), 1e-5)
+    ze_ref = torch.relu(O.batch_norm(yd, sd, "", False))
+    assert rel_err(ops.bn_apply(y8, coe, C, True, Lb.OUT_NCL_F32).cpu(), ze_ref) < TOL_F32
+    s1, s2 = ops.bn_bwd_reduce(dz8, y8, coe, C, (y8, coe))
+    dy8 = ops.bn_bwd_apply(dz8, y8, coe, gamma.cuda(), s1, s2, False, C, Lb.TSC_F32, (y8, coe))
+    dy_ref, dg_ref, db_ref = O.bn_relu_backward(dz.double(), yd, gamma.double(), rm.double(), rv.double(),
+                                                (ze_ref > 0).double(), False)
+    assert rel_err(ops.c8_to_ncl(dy8, C).cpu(), dy_ref) < 2e-5
+    assert rel_err(s2.cpu()[:C], dg_ref) < 2e-5 and rel_err(s1.cpu()[:C], db_ref) < 2e-5
+    # --- two-branch apply (shortcut add + relu) and its shared mask
+    y28 = ops.ncl_to_c8(y2.cuda(), Lb.TSC_F32)
+    co2 = ops.bn_stats(y28, C, gamma.cuda(), beta.cuda(), None, None, 0.0, 1e-5)
+    a = O.batch_norm(yd, sd, "", True, update_running=False)
+    bb = O.batch_norm(y2.double(), sd, "", True, update_running=False)
+    out = ops.bn_apply(y8, co, C, True, Lb.OUT_NCL_F32, y2=y28, co2=co2).cpu()
+    assert rel_err(out, torch.relu(a + bb)) < TOL_F32
+    s1, s2 = ops.bn_bwd_reduce(dz8, y8, co, C, (y8, co), (y28, co2))
+    dy8 = ops.bn_bwd_apply(dz8, y8, co, gamma.cuda(), s1, s2, True, C, Lb.TSC_F32, (y8, co), (y28, co2))
+    dy_ref, _, _ = O.bn_relu_backward(dz.double(), yd, gamma.double(), mean, var, ((a + bb) > 0).double(), True)
+    # elements whose pre-activation is within rounding of 0 may flip the mask (F7): compare away from them
+    safe = ((a + bb).abs() > 1e-5).double()
+    assert rel_err(ops.c8_to_ncl(dy8, C).cpu() * safe, dy_ref * safe) < 1e-4
+
+
+@pytest.mark.parametrize("B,C,L", [(4, 6, 32), (8, 144, 128), (3, 5, 100), (2, 50, 1024), (2, 3, 4096), (2, 3, 777)])
+def test_rowstats_and_adain(T, B, C, L):
+    ops = T.ops
+    gen = torch.Generator().manual_seed(4)
+    c = torch.randn(B, C, L, generator=gen) * 3 + 10          # large mean: exercises Welford's stability
+    s = torch.randn(B, C, L, generator=gen) * 0.5 - 2
+    dy = torch.randn(B, C, L, generator=gen)
+    m, v = ops.rowstats(c.cuda())
+    m_ref, v_ref = S.row_stats(c.double())
+    assert rel_err(m.cpu(), m_ref) < 1e-6 and rel_err(v.cpu(), v_ref) < 1e-5
+    out = T.adain(c.cuda().requires_grad_(True), s.cuda().requires_grad_(True))
+    assert rel_err(out.detach().cpu(), S.adain(c.double(), s.double())) < TOL_F32
+    cd, sd_ = c.cuda().requires_grad_(True), s.cuda().requires_grad_(True)
+    T.adain(cd, sd_).backward(dy.cuda())
+    dc_ref, ds_ref = S.adain_backward(dy.double(), c.double(), s.double())
+    assert rel_err(cd.grad.cpu(), dc_ref) < 5e-5 and rel_err(sd_.grad.cpu(), ds_ref) < 5e-5
+
+
+@pytest.mark.parametrize("B,C,L", [(2, 6, 11), (4, 144, 128), (2, 50, 300)])
+def test_gram_style_loss_simt(T, B, C, L):
+    Lb = T._lib
+    gen = torch.Generator().manual_seed(5)
+    a = torch.randn(B, C, L, generator=gen)
+    s = torch.randn(B, C, L, generator=gen) * 1.5
+    ad, sd_ = a.cuda().requires_grad_(True), s.cuda().requires_grad_(True)
+    loss = T.gram_style_loss(ad, sd_, engine=Lb.ENGINE_SIMT)
+    ref = S.gram_style_loss(a.double(), s.double())
+    assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref))
+    (3.0 * loss).backward()
+    da_ref, ds_ref = S.gram_style_loss_backward(a.double(), s.double())
+    assert rel_err(ad.grad.cpu(), 3.0 * da_ref) < 2e-5 and rel_err(sd_.grad.cpu(), 3.0 * ds_ref) < 2e-5
+
+
+@pytest.mark.parametrize("B,C,L", [(2, 16, 64), (4, 144, 128), (2, 50, 300)])
+def test_gram_style_loss_tcgen05(T, B, C, L):
+    Lb, ops = T._lib, T.ops
+    if not Lb.load().tsc_device_supports_tcgen05():
+        pytest.skip("device has no tcgen05")
+    gen = torch.Generator().manual_seed(6)
+    a = torch.randn(B, C, L, generator=gen)
+    s = torch.randn(B, C, L, generator=gen) * 1.5
+    ad, sd_ = a.cuda().requires_grad_(True), s.cuda().requires_grad_(True)
+    loss = T.gram_style_loss(ad, sd_, engine=Lb.ENGINE_TCGEN05)
+    torch.cuda.synchronize()
+    assert ops.read_watchdog() == 0
+    ref = S.gram_style_loss(a.double(), s.double())
+    assert abs(float(loss) - float(ref)) <= TOL_BF16 * abs(float(ref))
+    loss.backward()
+    da_ref, ds_ref = S.gram_style_loss_backward(a.double(), s.double())
+    assert rel_err(ad.grad.cpu(), da_ref) < TOL_BF16 and rel_err(sd_.grad.cpu(), ds_ref) < TOL_BF16
+
+
+def test_bad_arguments_raise(T):
+    ops, L = T.ops, T._lib
+    with pytest.raises(RuntimeError):
+        ops.ncl_to_c8(torch.randn(2, 3, 4), L.TSC_F32)            # CPU tensor
+    with pytest.raises(ValueError):
+        ops.dense_geometry(3, 300, 1)                              # too many channels
+    with pytest.raises(ValueError):
+        ops.bank_geometry([(1, 2, 3), (1, 2, 1), (1, 2, 3)])       # not nested
+    geom = ops.dense_geometry(3, 4, 1)
+    with pytest.raises(RuntimeError):
+        ops.pack_weights(geom, torch.zeros(4, 3, 2, device="cuda"), L.DIR_FWD, L.TSC_F32, False)

@@ -1,0 +1,190 @@
+"""Module-level parity of the drop-in OS_CNN classes on the GPU against (a) the committed golden vectors the
+reference itself produced and (b) the oracle; plus the autograd semantics the reference trainer relies on."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import as_lpl, rel_err
+from oracle import os_cnn as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def T():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import feature_level_style_transfer_for_tsc_b200 as pkg
+    pkg._lib.load()
+    return pkg
+
+
+def build_modules(T, lpl_e, lpl_c, n_class, seed, init_fe=None, init_cl=None):
+    from feature_level_style_transfer_for_tsc_b200.OS_CNN.OS_CNN import OS_CNN, OS_CNN_res
+    torch.manual_seed(seed)
+    fe = OS_CNN_res(lpl_e)
+    cl = OS_CNN(lpl_c, n_class)
+    if init_fe is not None:
+        for k, v in fe.state_dict().items():
+            assert np.array_equal(v.numpy(), init_fe[k]), k      # same seed -> bit-identical init (A5)
+        for k, v in cl.state_dict().items():
+            assert np.array_equal(v.numpy(), init_cl[k]), k
+    return fe.cuda(), cl.cuda()
+
+
+def run_pair(T, tables, pair, name, engine, tol_out, tol_grad):
+    T.set_engine(engine)
+    meta = tables[name]
+    lpl_e, lpl_c = as_lpl(meta["lpl_ext"]), as_lpl(meta["lpl_cls"])
+    fe, cl = build_modules(T, lpl_e, lpl_c, meta["n_class"], meta["seed"], pair["init_fe"], pair["init_cl"])
+    out = pair["out"]
+    x = torch.from_numpy(out["x"]).cuda().requires_grad_(True)
+    y = torch.from_numpy(out["y"]).cuda()
+    fe.train(); cl.train()
+    feat = fe(x)
+    feat.retain_grad()
+    logits, pooled = cl(feat)
+    loss = torch.nn.functional.cross_entropy(logits, y)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert T.ops.read_watchdog() == 0
+    assert rel_err(feat.detach().cpu(), out["feat"]) < tol_out
+    assert rel_err(logits.detach().cpu(), out["logits"]) < tol_out
+    assert rel_err(pooled.detach().cpu(), out["pooled"]) < tol_out
+    assert abs(float(loss) - float(out["loss"])) < tol_out * 10
+    assert rel_err(feat.grad.cpu(), out["dfeat"]) < tol_grad
+    assert rel_err(x.grad.cpu(), out["dx"]) < tol_grad
+    for key, gref in pair["grad"].items():
+        mod, pname = key.split(".", 1)
+        m, lpl = (fe, lpl_e) if mod == "fe" else (cl, lpl_c)
+        g = dict(m.named_parameters())[pname].grad.cpu().numpy()
+        if pname.endswith("conv1d.weight") and "res" not in pname:
+            idx = int(pname.split(".conv1d")[0].split(".")[-1])
+            mask = O.build_mask(lpl[idx])
+            assert np.abs(g * (1 - mask)).max() == 0.0          # exact zeros at masked taps (F4)
+            gref = gref * mask
+        if pname.endswith("conv1d.bias"):
+            assert np.abs(g).max() < 1e-5                        # BN cancels the conv bias
+            continue
+        assert rel_err(g, gref) < tol_grad, key
+    for prefix, m in (("after_fe", fe), ("after_cl", cl)):
+        sd = m.state_dict()
+        for k, v in pair[prefix].items():
+            got = sd[k].cpu().numpy()
+            assert np.array_equal(got, v) or rel_err(got, v) < max(tol_out, 1e-5), k
+    # masked taps of the parameter itself are zero after forward (weight.data = weight*mask)
+    for i in range(3):
+        w = fe.net_1.net.net[i].conv1d.weight.detach().cpu().numpy()
+        assert np.abs(w * (1 - O.build_mask(lpl_e[i]))).max() == 0.0
+    fe.eval(); cl.eval()
+    with torch.no_grad():
+        feat_e = fe(x.detach())
+        logits_e, _ = cl(feat_e)
+    assert rel_err(feat_e.cpu(), out["feat_eval"]) < tol_out
+    assert rel_err(logits_e.cpu(), out["logits_eval"]) < tol_out
+    ref_arg = np.argmax(out["logits_eval"], axis=1)
+    top2 = np.sort(out["logits_eval"], axis=1)
+    decided = (top2[:, -1] - top2[:, -2]) > 4 * tol_out * np.abs(out["logits_eval"]).max()
+    got_arg = np.argmax(logits_e.cpu().numpy(), axis=1)         # host argmax, utils.py:34-36
+    assert np.array_equal(got_arg[decided], ref_arg[decided])
+    T.set_engine("tcgen05")
+
+
+def test_small_pair_fp32_engine(T, tables, small_pair):
+    run_pair(T, tables, small_pair, "small", "simt", 2e-5, 2e-3)
+
+
+def test_uni_pair_fp32_engine(T, tables, uni_pair):
+    run_pair(T, tables, uni_pair, "uni", "simt", 2e-5, 2e-3)
+
+
+def test_small_pair_tensor_core_engine(T, tables, small_pair):
+    run_pair(T, tables, small_pair, "small", "tcgen05", 1e-2, 3e-2)
+
+
+def test_uni_pair_tensor_core_engine(T, tables, uni_pair):
+    run_pair(T, tables, uni_pair, "uni", "tcgen05", 1e-2, 3e-2)
+
+
+@pytest.mark.parametrize("engine,tol", [("simt", 1e-4), ("tcgen05", 1e-2)])
+def test_cfg1_full_width(T, tables, cfg1_seeded, engine, tol):
+    T.set_engine(engine)
+    meta = tables["cfg1"]
+    lpl_e, lpl_c = O.trainer_layer_lists(meta["C"], meta["L"])
+    fe, cl = build_modules(T, lpl_e, lpl_c, meta["n_class"], meta["seed"])
+    x, y = O.synthetic_batch(meta["B"], meta["C"], meta["L"], meta["n_class"], 0)
+    feat = fe(x.cuda())
+    logits, pooled = cl(feat)
+    loss = torch.nn.functional.cross_entropy(logits, y.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    assert T.ops.read_watchdog() == 0
+    assert rel_err(logits.detach().cpu(), cfg1_seeded["logits"]) < tol
+    assert rel_err(feat.detach().cpu()[0], cfg1_seeded["feat_b0"]) < tol
+    assert abs(float(loss) - meta["loss"]) < 10 * tol
+    ref = cfg1_seeded["logits"]
+    top2 = np.sort(ref, axis=1)
+    decided = (top2[:, -1] - top2[:, -2]) > 4 * tol * np.abs(ref).max()
+    assert np.array_equal(np.argmax(logits.detach().cpu().numpy(), axis=1)[decided], np.array(meta["argmax"])[decided])
+    gw = fe.net_1.net.net[0].conv1d.weight.grad.cpu().numpy()
+    gref = cfg1_seeded["grad"]["fe.net_1.net.net.0.conv1d.weight"] * O.build_mask(lpl_e[0])
+    assert rel_err(gw, gref) < (5e-3 if engine == "simt" else 5e-2)      # F7: intrinsically noisy end to end
+    T.set_engine("tcgen05")
+
+
+def test_autograd_semantics_of_the_reference_trainer(T):
+    """retain_graph + second backward, autograd.grad on a sub-loss over return_last_layer().parameters()
+    (train_and_test.py:678-690,741), and the eval-mode forward with gradient (train_and_test.py:583-586)."""
+    T.set_engine("simt")
+    lpl_e, lpl_c = O.trainer_layer_lists(2, 64)
+    lpl_e = [[(i, max(o // 8, 1), k) for (i, o, k) in layer] for layer in lpl_e]     # narrow: fast
+    # re-chain the channel counts after narrowing
+    fixed, cin = [], 2
+    for li, layer in enumerate(lpl_e):
+        fixed.append([(cin, o, k) for (_, o, k) in layer])
+        cin = sum(o for (_, o, _) in layer)
+    lpl_e = fixed
+    from feature_level_style_transfer_for_tsc_b200.OS_CNN.OS_CNN import OS_CNN, OS_CNN_res, layer_parameter_list_input_change
+    torch.manual_seed(0)
+    fe = OS_CNN_res(lpl_e).cuda()
+    cf = O.feature_channels(lpl_e)
+    cl = OS_CNN(layer_parameter_list_input_change(lpl_e, cf), 3).cuda()
+    x = torch.randn(5, 2, 64, device="cuda")
+    y = torch.randint(0, 3, (5,), device="cuda")
+    feat = fe(x)
+    logits, _ = cl(feat)
+    cl.eval()
+    logits_e, _ = cl(feat)              # eval BN, autograd on
+    cl.train()
+    l1 = torch.nn.functional.cross_entropy(logits, y)
+    l2 = torch.nn.functional.cross_entropy(logits_e, y)
+    shared = list(fe.return_last_layer().parameters())
+    assert len(shared) == 12
+    g1 = torch.autograd.grad(l1, shared, retain_graph=True)
+    (l1 + l2).backward(retain_graph=True)
+    first = [p.grad.clone() for p in shared]
+    (l1 + l2).backward()
+    for p, a in zip(shared, first):
+        assert torch.allclose(p.grad, 2 * a, rtol=1e-5, atol=1e-7)         # second traversal re-adds the same grads
+    # oracle check of the eval-branch + train-branch sum
+    sd_fe = O.clone_state({k: v.cpu() for k, v in fe.state_dict().items()}, torch.float64, True)
+    assert all(torch.isfinite(g).all() for g in g1)
+    T.set_engine("tcgen05")
+
+
+def test_state_dict_roundtrip_and_missing_extension_message(T, tables):
+    from feature_level_style_transfer_for_tsc_b200.OS_CNN.OS_CNN import OS_CNN_res
+    lpl = as_lpl(tables["small"]["lpl_ext"])
+    torch.manual_seed(0)
+    a = OS_CNN_res(lpl)
+    torch.manual_seed(1)
+    b = OS_CNN_res(lpl)
+    b.load_state_dict(a.state_dict())
+    assert "weight_mask" not in "".join(a.state_dict().keys())
+    a, b = a.cuda().eval(), b.cuda().eval()
+    x = torch.randn(2, 3, 40, device="cuda")
+    T.set_engine("simt")
+    assert torch.equal(a(x), b(x))
+    T.set_engine("tcgen05")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        a(x.cpu())
