@@ -17,8 +17,8 @@ from . import _lib as L
 _ENGINE_NAMES = {"simt": L.ENGINE_SIMT, "fp32": L.ENGINE_SIMT, "tcgen05": L.ENGINE_TCGEN05, "bf16": L.ENGINE_TCGEN05}
 # engine per kernel family.  'conv' (forward + dgrad) decides the operand dtype of the whole OS stack:
 # tcgen05 -> bf16 operands (<= 1e-2), simt -> fp32 operands (<= 1e-5).
-_TC_READY = ("conv",)          # families whose tcgen05 kernel exists (the others stay on the SIMT engine)
-_ENGINES = {"conv": L.ENGINE_TCGEN05, "wgrad": L.ENGINE_SIMT, "gram": L.ENGINE_SIMT}
+_TC_READY = ("conv", "wgrad")          # families whose tcgen05 kernel exists (the others stay on the SIMT engine)
+_ENGINES = {"conv": L.ENGINE_TCGEN05, "wgrad": L.ENGINE_TCGEN05, "gram": L.ENGINE_SIMT}
 
 
 def set_engine(name: str, family: Optional[str] = None) -> None:
