@@ -42,8 +42,9 @@ class StackSpec:
     layers: List[LayerSpec]
     shortcut: Optional[LayerSpec]     # 1x1 conv + BN branch added before the final ReLU
     final_relu: bool                   # relu(shortcut + block) of Res_OS_layer
-    engine: int                        # conv (forward + dgrad) engine; fixes the operand dtype
+    engine: int                        # conv (forward + dgrad) engine
     wgrad_engine: int
+    op_dtype: int                      # operand dtype of the stack (bf16 for the tensor-core engine)
 
 
 class _Saved:
@@ -55,7 +56,7 @@ class OSStackFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, spec: StackSpec, x: torch.Tensor, *params: torch.Tensor):
         eng = spec.engine
-        dt = ops.op_dtype(eng)
+        dt = spec.op_dtype
         ops._req(x, name="input")
         B, C, Ln = x.shape
         if C != spec.layers[0].geom.cin:
@@ -111,7 +112,7 @@ class OSStackFunction(torch.autograd.Function):
         spec, sv = ctx.spec, ctx.sv
         params = ctx.saved_tensors
         eng = spec.engine
-        dt = ops.op_dtype(eng)
+        dt = spec.op_dtype
         nl = len(spec.layers)
         dout = dout.contiguous().float()
         dz = ops.ncl_to_c8(dout, L.TSC_F32)

@@ -14,37 +14,43 @@ import torch
 
 from . import _lib as L
 
-_ENGINE_NAMES = {"simt": L.ENGINE_SIMT, "fp32": L.ENGINE_SIMT, "tcgen05": L.ENGINE_TCGEN05, "bf16": L.ENGINE_TCGEN05}
-# engine per kernel family.  'conv' (forward + dgrad) decides the operand dtype of the whole OS stack:
-# tcgen05 -> bf16 operands (<= 1e-2), simt -> fp32 operands (<= 1e-5).
-_TC_READY = ("conv", "wgrad")          # families whose tcgen05 kernel exists (the others stay on the SIMT engine)
-_ENGINES = {"conv": L.ENGINE_TCGEN05, "wgrad": L.ENGINE_TCGEN05, "gram": L.ENGINE_SIMT}
+# Engine per kernel family plus the operand dtype of the OS stack.
+#   "tcgen05"   : conv / wgrad / gram on the tensor cores, bf16 operands, fp32 accumulation   (<= 1e-2)
+#   "simt"      : fp32 CUDA-core kernels, fp32 operands                                        (<= 1e-5)
+#   "simt_bf16" : the CUDA-core kernels fed the SAME bf16 operands as the tensor-core engine -- not a
+#                 product mode: it is the bit-faithful checker of the tcgen05 kernels used by tests.
+_TC_READY = ("conv", "wgrad")          # families whose tcgen05 kernel exists (others stay on SIMT)
+_CFG = {"conv": L.ENGINE_TCGEN05, "wgrad": L.ENGINE_TCGEN05, "gram": L.ENGINE_SIMT, "op_dtype": L.TSC_BF16,
+        "name": "tcgen05"}
 
 
-def set_engine(name: str, family: Optional[str] = None) -> None:
-    """'tcgen05' (bf16/tf32 operands on the tensor cores, <=1e-2) or 'simt' (fp32 CUDA cores, <=1e-5).
-    family: None (all), 'conv', 'wgrad' or 'gram'."""
-    e = _ENGINE_NAMES[name]
-    for fam in ([family] if family else list(_ENGINES)):
-        if fam not in _ENGINES:
-            raise KeyError(fam)
-        if e == L.ENGINE_TCGEN05 and family is None and fam not in _TC_READY:
-            continue
-        _ENGINES[fam] = e
-    if _ENGINES["conv"] == L.ENGINE_SIMT and _ENGINES["wgrad"] == L.ENGINE_TCGEN05:
-        raise ValueError("the tcgen05 wgrad needs bf16 operands, i.e. the tcgen05 conv engine")
+def set_engine(name: str) -> None:
+    if name in ("tcgen05", "bf16"):
+        for fam in ("conv", "wgrad", "gram"):
+            _CFG[fam] = L.ENGINE_TCGEN05 if fam in _TC_READY else L.ENGINE_SIMT
+        _CFG["op_dtype"], _CFG["name"] = L.TSC_BF16, "tcgen05"
+    elif name in ("simt", "fp32"):
+        for fam in ("conv", "wgrad", "gram"):
+            _CFG[fam] = L.ENGINE_SIMT
+        _CFG["op_dtype"], _CFG["name"] = L.TSC_F32, "simt"
+    elif name == "simt_bf16":
+        for fam in ("conv", "wgrad", "gram"):
+            _CFG[fam] = L.ENGINE_SIMT
+        _CFG["op_dtype"], _CFG["name"] = L.TSC_BF16, "simt_bf16"
+    else:
+        raise KeyError(name)
 
 
 def get_engine(family: str = "conv") -> int:
-    return _ENGINES[family]
+    return _CFG[family]
 
 
-def engine_name(engine: Optional[int] = None) -> str:
-    return "tcgen05" if (engine if engine is not None else _ENGINES["conv"]) == L.ENGINE_TCGEN05 else "simt"
+def engine_name() -> str:
+    return _CFG["name"]
 
 
-def op_dtype(engine: int) -> int:
-    return L.TSC_BF16 if engine == L.ENGINE_TCGEN05 else L.TSC_F32
+def op_dtype() -> int:
+    return _CFG["op_dtype"]
 
 
 def torch_dtype(dt: int):
