@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- OS-CNN + feature-level style-transfer training throughput (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port), rank 0 only
+
+Workload (N = 1): BASELINE.json configs[1] = "cfg2": target and source batches of B=128 series, C=9, L=128,
+6 classes; one step = 2 extractors + DimensionUnification + AdaIN + Gram loss + 2 classifiers + CE, backward,
+RMSprop.  For N > 1 every rank runs the same per-GPU batch on its own shard (weak scaling) and the
+flat gradient bucket is all-reduced over NCCL.  `value` = series/s of the whole job with inputs resident in HBM,
+`e2e` = the same with host->device copies of the step's inputs and a device->host read of the loss inside the
+timed region.  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "OS-CNN+style-transfer train samples/sec"
+UNIT = "samples/s"
+CFG = dict(name="cfg2", B=128, C=9, L=128, K=6)          # per domain, per GPU
+STYLE_WEIGHT = 1.0
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d["bf16_tflops_sustained"], source="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=(max(mx) if mx else None), reasons=reasons,
+                    samples=len(self.rows))
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the step on the host cores
+# ----------------------------------------------------------------------------------------------------
+def cpu_step_rate(steps: int, warmup: int):
+    import torch
+    from oracle import os_cnn as O
+    from oracle import step as OS
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ms = OS.ModelSet(CFG["C"], CFG["L"], CFG["K"], CFG["C"], CFG["L"], CFG["K"], seed=0)
+    xt, yt = O.synthetic_batch(CFG["B"], CFG["C"], CFG["L"], CFG["K"], 0)
+    xs, ys = O.synthetic_batch(CFG["B"], CFG["C"], CFG["L"], CFG["K"], 1)
+    for _ in range(warmup):
+        OS.train_step(ms, xt, yt, xs, ys, STYLE_WEIGHT)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        OS.train_step(ms, xt, yt, xs, ys, STYLE_WEIGHT)
+    dt = (time.perf_counter() - t0) / steps
+    return 2 * CFG["B"] / dt, dt, cores, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 20))
+    value, dt, cores, threads = cpu_step_rate(steps, max(1, min(args.warmup, 2)))
+    sample = f"{steps} full cfg2 steps (B=128 per domain) of the oracle port on {threads} torch CPU threads"
+    line = dict(metric=METRIC, value=value, unit=UNIT, impl="reference", n_gpus=args.gpus, steps=steps,
+                warmup=max(1, min(args.warmup, 2)), ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload="cfg2: OS-CNN + AdaIN/Gram style transfer, B=128 per domain, C=9, L=128, 6 classes",
+                            series_per_step=2 * CFG["B"]),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=threads, kind="port", sample=sample),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+# this repo's arm
+# ----------------------------------------------------------------------------------------------------
+class KernelProfile:
+    """Times every C-ABI call family with CUDA events on the launching stream (instrumented pass, run after
+    the timed region; never part of a reported step time)."""
+    LAUNCHES = dict(ncl_to_c8=1, c8_to_ncl=1, pack_weights=1, osconv=1, oswgrad=2, bn_stats=2, bn_eval_coeffs=1,
+                    bn_apply=1, bn_bwd_reduce=2, bn_bwd_apply=1, adain_fwd=1, adain_bwd=1, gram_loss_fwd=2,
+                    gram_loss_bwd=1, rowstats=1)
+
+    def __init__(self, ops, torch):
+        self.ops, self.torch, self.records, self.orig, self.count = ops, torch, [], {}, 0
+        self.timing = False
+
+    def _meta(self, name, args):
+        L = self.ops.L
+        if name == "osconv":
+            engine, direction, g, x8 = args[0], args[1], args[2], args[3]
+            B, _, Ln, _ = x8.shape
+            return dict(flops=2.0 * B * Ln * g.live_macs_per_position(), tc=engine == L.ENGINE_TCGEN05)
+        if name == "oswgrad":
+            engine, g, dy8, x8 = args[0], args[1], args[2], args[3]
+            B, _, Ln, _ = x8.shape
+            return dict(flops=2.0 * B * Ln * g.live_macs_per_position(), tc=engine == L.ENGINE_TCGEN05)
+        if name == "adain_fwd":
+            return dict(bytes=3.0 * args[0].numel() * 4)
+        if name == "adain_bwd":
+            return dict(bytes=5.0 * args[0].numel() * 4)
+        if name == "gram_loss_fwd":
+            B, C, Ln = args[1].shape
+            return dict(flops=2.0 * 2 * B * C * C * Ln, tc=args[0] == L.ENGINE_TCGEN05)
+        if name == "gram_loss_bwd":
+            B, C, Ln = args[2].shape
+            return dict(flops=2.0 * 2 * B * C * C * Ln, tc=args[0] == L.ENGINE_TCGEN05)
+        if name in ("bn_apply", "bn_stats", "bn_bwd_reduce", "bn_bwd_apply"):
+            y8 = args[0]
+            n = y8.numel() * 4.0
+            mult = dict(bn_stats=1.0, bn_apply=1.75, bn_bwd_reduce=2.0, bn_bwd_apply=2.5)[name]
+            return dict(bytes=n * mult)
+        return {}
+
+    def install(self):
+        for name in self.LAUNCHES:
+            fn = getattr(self.ops, name)
+            self.orig[name] = fn
+
+            def wrapped(*a, __fn=fn, __name=name, **k):
+                self.count += self.LAUNCHES[__name]
+                if __name == "pack_weights" and len(a) > 4 and a[4]:
+                    self.count += 1
+                if not self.timing:
+                    return __fn(*a, **k)
+                e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r = __fn(*a, **k)
+                e1.record()
+                self.records.append((__name, e0, e1, self._meta(__name, a)))
+                return r
+            setattr(self.ops, name, wrapped)
+
+    def uninstall(self):
+        for name, fn in self.orig.items():
+            setattr(self.ops, name, fn)
+
+    def table(self, steps):
+        agg = {}
+        for name, e0, e1, meta in self.records:
+            key = name + ("[tc]" if meta.get("tc") else "")
+            d = agg.setdefault(key, dict(ms=0.0, n=0, flops=0.0, bytes=0.0))
+            d["ms"] += e0.elapsed_time(e1)
+            d["n"] += 1
+            d["flops"] += meta.get("flops", 0.0)
+            d["bytes"] += meta.get("bytes", 0.0)
+        for d in agg.values():
+            d["ms_per_step"] = d["ms"] / steps
+            d["launches_per_step"] = d["n"] / steps
+            d["tflops"] = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["flops"] else None
+            d["gbs"] = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["bytes"] else None
+        return agg
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import feature_level_style_transfer_for_tsc_b200 as T
+    from feature_level_style_transfer_for_tsc_b200 import ops
+    from feature_level_style_transfer_for_tsc_b200.train_step import StyleTransferModelSet, Trainer
+    from oracle import os_cnn as O                      # synthetic input generator only (SURVEY 8d definition)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the tsc_b200 kernels have no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    T._lib.load()
+    T.set_engine(args.engine)
+
+    torch.manual_seed(0)
+    model = StyleTransferModelSet(CFG["C"], CFG["L"], CFG["K"], CFG["C"], CFG["L"], CFG["K"]).to(dev)
+    trainer = Trainer(model, STYLE_WEIGHT)
+    trainer.broadcast_parameters(0)
+    B = CFG["B"]
+    xt_h, yt_h = O.synthetic_batch(B, CFG["C"], CFG["L"], CFG["K"], 2 * rank)
+    xs_h, ys_h = O.synthetic_batch(B, CFG["C"], CFG["L"], CFG["K"], 2 * rank + 1)
+    host = [t.pin_memory() for t in (xt_h, yt_h, xs_h, ys_h)]
+    dev_in = [t.to(dev) for t in host]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host)
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)      # 256 MiB > 126 MB L2
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    prof = KernelProfile(ops, torch)
+    prof.install()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nsteps, e2e):
+        evs = []
+        for _ in range(nsteps):
+            flush.zero_()                                           # L2 flush, outside the timed events
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if e2e:
+                ins = [h.to(dev, non_blocking=True) for h in host]
+                loss = trainer.step(*ins)
+                loss_host.copy_(loss, non_blocking=True)
+            else:
+                trainer.step(*dev_in)
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs) * 1e-3
+
+    for _ in range(max(args.warmup, 3)):
+        trainer.step(*dev_in)
+    barrier()
+    n0 = prof.count
+    with ClockSampler(local_rank) as clocks:
+        t_dev = timed(args.steps, False)
+    launches = (prof.count - n0) // args.steps
+    barrier()
+    t_e2e = timed(args.steps, True)
+    barrier()
+    if world > 1:
+        tt = torch.tensor([t_dev, t_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e = float(tt[0]), float(tt[1])
+    series = 2 * B * world * args.steps
+
+    # instrumented pass (per-kernel-family device time; not part of any reported step time)
+    prof.timing = True
+    psteps = 3
+    for _ in range(psteps):
+        flush.zero_()
+        trainer.step(*dev_in)
+    torch.cuda.synchronize()
+    table = prof.table(psteps)
+    prof.uninstall()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = load_peaks()
+    kern = {k: dict(ms_per_step=round(v["ms_per_step"], 4), launches=v["launches_per_step"],
+                    tflops=(round(v["tflops"], 2) if v["tflops"] else None),
+                    gbs=(round(v["gbs"], 1) if v["gbs"] else None)) for k, v in sorted(table.items(), key=lambda kv: -kv[1]["ms"])}
+    dom = max(table.items(), key=lambda kv: kv[1]["ms"])[0]
+    d = table[dom]
+    if d["flops"]:
+        roof = dict(kernel=dom, bound="tensor", achieved=d["tflops"], peak=peaks["bf16_sustained"], unit="TFLOP/s",
+                    frac=d["tflops"] / peaks["bf16_sustained"], traffic=None,
+                    peak_source=peaks["source"] + " bf16 sustained (kernel timed inside a long step)")
+    else:
+        roof = dict(kernel=dom, bound="hbm", achieved=d["gbs"], peak=peaks["hbm"], unit="GB/s",
+                    frac=(d["gbs"] or 0.0) / peaks["hbm"], traffic=None, peak_source=peaks["source"] + " HBM copy")
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, dt, cores, threads = cpu_step_rate(3, 1)
+        cpu = dict(value=v, unit=UNIT, cores=threads, kind="port",
+                   sample=f"3 full cfg2 steps (B=128 per domain) of the oracle port, {dt * 1e3:.0f} ms/step, {cores} host cores")
+    line = dict(metric=METRIC, value=series / t_dev, unit=UNIT, n_gpus=world, steps=args.steps,
+                warmup=max(args.warmup, 3), ms_per_step=t_dev / args.steps * 1e3, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="bf16" if args.engine == "tcgen05" else "f32", data="synthetic",
+                config=dict(workload="cfg2: OS-CNN + AdaIN/Gram style transfer, B=128 per domain per GPU, C=9, L=128, 6 classes",
+                            series_per_step_per_gpu=2 * B, engine=args.engine, parallelism=f"dp{world}",
+                            l2="flushed between timed steps (256 MiB write, outside the per-step events)"),
+                e2e=dict(value=series / t_e2e, unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=4,
+                         ms_per_step=t_e2e / args.steps * 1e3),
+                gpu_launches=int(launches), clocks=clocks.summary(), roofline=roof, kernels=kern)
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--engine", default="tcgen05", choices=["tcgen05", "simt"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
