@@ -120,7 +120,7 @@ def run_reference(args):
 class KernelProfile:
     """Times every C-ABI call family with CUDA events on the launching stream (instrumented pass, run after
     the timed region; never part of a reported step time)."""
-    LAUNCHES = dict(ncl_to_c8=1, c8_to_ncl=1, pack_weights=1, osconv=1, oswgrad=2, bn_stats=2, bn_eval_coeffs=1,
+    LAUNCHES = dict(ncl_to_c8=1, c8_to_ncl=1, pack_weights=1, pack_weights_pair=1, rmsprop_step=1, osconv=1, oswgrad=2, bn_stats=2, bn_eval_coeffs=1,
                     bn_apply=1, bn_bwd_reduce=2, bn_bwd_apply=1, adain_fwd=1, adain_bwd=1, gram_loss_fwd=2,
                     gram_loss_bwd=1, rowstats=1)
 
@@ -218,7 +218,7 @@ def run_ours(args):
 
     torch.manual_seed(0)
     model = StyleTransferModelSet(CFG["C"], CFG["L"], CFG["K"], CFG["C"], CFG["L"], CFG["K"]).to(dev)
-    trainer = Trainer(model, STYLE_WEIGHT)
+    trainer = Trainer(model, STYLE_WEIGHT, use_graph=not args.no_graph)
     trainer.broadcast_parameters(0)
     B = CFG["B"]
     xt_h, yt_h = O.synthetic_batch(B, CFG["C"], CFG["L"], CFG["K"], 2 * rank)
@@ -231,6 +231,12 @@ def run_ours(args):
 
     prof = KernelProfile(ops, torch)
     prof.install()
+    # one eager step to count this repo's kernel launches per step (the same launches the CUDA graph replays)
+    trainer.use_graph = False
+    n0 = prof.count
+    trainer.step(*dev_in)
+    launches = prof.count - n0
+    trainer.use_graph = not args.no_graph
 
     def barrier():
         if world > 1:
@@ -257,10 +263,8 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         trainer.step(*dev_in)
     barrier()
-    n0 = prof.count
     with ClockSampler(local_rank) as clocks:
         t_dev = timed(args.steps, False)
-    launches = (prof.count - n0) // args.steps
     barrier()
     t_e2e = timed(args.steps, True)
     barrier()
@@ -272,6 +276,7 @@ def run_ours(args):
 
     # instrumented pass (per-kernel-family device time; not part of any reported step time)
     prof.timing = True
+    trainer.use_graph = False
     psteps = 3
     for _ in range(psteps):
         flush.zero_()
@@ -307,6 +312,7 @@ def run_ours(args):
                 vs_baseline=None, dtype="bf16" if args.engine == "tcgen05" else "f32", data="synthetic",
                 config=dict(workload="cfg2: OS-CNN + AdaIN/Gram style transfer, B=128 per domain per GPU, C=9, L=128, 6 classes",
                             series_per_step_per_gpu=2 * B, engine=args.engine, parallelism=f"dp{world}",
+                            cuda_graph=not args.no_graph,
                             l2="flushed between timed steps (256 MiB write, outside the per-step events)"),
                 e2e=dict(value=series / t_e2e, unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=4,
                          ms_per_step=t_e2e / args.steps * 1e3),
@@ -326,6 +332,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--engine", default="tcgen05", choices=["tcgen05", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

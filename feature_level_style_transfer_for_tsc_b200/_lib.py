@@ -44,6 +44,9 @@ SIGNATURES = {
     "tsc_c8_to_ncl": (_i, [_p, _p, _i, _i, _i, _p]),
     "tsc_packed_weight_bytes": (_sz, [_i, _i, _i, _i, _i, _ip]),
     "tsc_pack_weights": (_i, [_i, _i, _p, _p, _i, _i, _i, _ip, _i, _p]),
+    "tsc_pack_weights_pair": (_i, [_i, _p, _p, _p, _i, _i, _i, _ip, _i, _p]),
+    "tsc_rmsprop_step": (_i, [_p, _p, _p, ctypes.c_longlong, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_float),
+                         _i, _f, _f, _f, _p]),
     "tsc_osconv": (_i, [_i, _i, _p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _ip, _p]),
     "tsc_oswgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "tsc_oswgrad": (_i, [_i, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _ip, _p]),

@@ -68,20 +68,33 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_partial_kernel(const floa
 }
 
 // ---- pass 2: merge splits per channel, produce coefficients and update the running statistics -----
-__global__ void bn_stats_finalize_kernel(const float* __restrict__ ws, const float* __restrict__ gamma,
+// One warp per channel: lanes take the splits round-robin and Chan-merge through shuffles.
+__global__ void __launch_bounds__(128) bn_stats_finalize_kernel(const float* __restrict__ ws, const float* __restrict__ gamma,
                                          const float* __restrict__ beta, float* __restrict__ mean_o,
                                          float* __restrict__ invstd_o, float* __restrict__ scale_o,
                                          float* __restrict__ shift_o, float* running_mean, float* running_var,
                                          float momentum, float eps, int C, int Cp, int S) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (c >= Cp) return;
-    if (c >= C) { mean_o[c] = 0.f; invstd_o[c] = 0.f; scale_o[c] = 0.f; shift_o[c] = 0.f; return; }
+    if (c >= C) {
+        if (lane == 0) { mean_o[c] = 0.f; invstd_o[c] = 0.f; scale_o[c] = 0.f; shift_o[c] = 0.f; }
+        return;
+    }
     const int ch = c >> 3, j = c & 7;
     float n = 0.f, m = 0.f, q = 0.f;
-    for (int s = 0; s < S; ++s) {
+    for (int s = lane; s < S; s += 32) {
         const float* p = ws + (((long long)ch * S + s) * 8 + j) * 3;
         welford_merge(n, m, q, p[0], p[1], p[2]);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float nb = __shfl_xor_sync(0xffffffffu, n, o);
+        const float mb = __shfl_xor_sync(0xffffffffu, m, o);
+        const float qb = __shfl_xor_sync(0xffffffffu, q, o);
+        welford_merge(n, m, q, nb, mb, qb);
+    }
+    if (lane != 0) return;
     const float var_b = q / n;
     const float invstd = 1.f / sqrtf(var_b + eps);
     mean_o[c] = m;
@@ -214,17 +227,19 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(
     }
 }
 
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ ws, float* __restrict__ s1, float* __restrict__ s2,
-                                       int Cp, int S) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) bn_bwd_finalize_kernel(const float* __restrict__ ws, float* __restrict__ s1,
+                                                              float* __restrict__ s2, int Cp, int S) {
+    const int c = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (c >= Cp) return;
     const int ch = c >> 3, j = c & 7;
     float a = 0.f, b = 0.f;
-    for (int s = 0; s < S; ++s) {
+    for (int s = lane; s < S; s += 32) {
         const float* p = ws + (((long long)ch * S + s) * 8 + j) * 2;
         a += p[0]; b += p[1];
     }
-    s1[c] = a; s2[c] = b;
+    a = warp_sum(a); b = warp_sum(b);
+    if (lane == 0) { s1[c] = a; s2[c] = b; }
 }
 
 // ---- backward pass 2: dy = gamma*invstd*(d - S1/N - yhat*S2/N)  (train)  |  gamma*invstd*d (eval) ---
@@ -291,7 +306,7 @@ int tsc_bn_stats(const float* y, const float* gamma, const float* beta, float* w
     cudaStream_t cs = (cudaStream_t)stream;
     bn_stats_partial_kernel<<<dim3(Cpc, S), BN_THREADS, 0, cs>>>(y, ws, B, Cpc, L, S);
     TSC_LAUNCH_CHECK();
-    bn_stats_finalize_kernel<<<cdiv(Cp, 128), 128, 0, cs>>>(ws, gamma, beta, mean, invstd, scale, shift, running_mean,
+    bn_stats_finalize_kernel<<<cdiv(Cp, 4), 128, 0, cs>>>(ws, gamma, beta, mean, invstd, scale, shift, running_mean,
                                                            running_var, momentum, eps, C, Cp, S);
     TSC_LAUNCH_CHECK();
     return 0;
@@ -339,7 +354,7 @@ int tsc_bn_bwd_reduce(const float* dz, const float* y, const float* mean, const 
     bn_bwd_reduce_kernel<<<dim3(Cpc, S), BN_THREADS, 0, cs>>>(dz, y, mean, invstd, ym, scale, shift, ym2, scale2, shift2,
                                                              ws, B, Cpc, L, S);
     TSC_LAUNCH_CHECK();
-    bn_bwd_finalize_kernel<<<cdiv(Cp, 128), 128, 0, cs>>>(ws, s1, s2, Cp, S);
+    bn_bwd_finalize_kernel<<<cdiv(Cp, 4), 128, 0, cs>>>(ws, s1, s2, Cp, S);
     TSC_LAUNCH_CHECK();
     return 0;
 }

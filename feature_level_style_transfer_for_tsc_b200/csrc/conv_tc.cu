@@ -212,8 +212,12 @@ int osconv_tc(int direction, const void* x, int dtype, const void* w, const floa
     CUtensorMap xmap;
     if (make_c8_map(&xmap, x, B, tt.kc, L, p.Rp) != 0) return -1;
     const int smem = SMEM_HDR + p.xs_bytes + ns * p.stage_bytes;
-    cudaError_t e = cudaFuncSetAttribute(osconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    static bool attr_set = false;          // once per process: opt in to the full 227 KB of dynamic shared memory
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(osconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        attr_set = true;
+    }
     osconv_tc_kernel<<<B * p.ltiles, TC_THREADS, smem, cs>>>(xmap, tt, p);
     TSC_LAUNCH_CHECK();
     return 0;

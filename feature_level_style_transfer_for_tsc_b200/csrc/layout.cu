@@ -79,6 +79,49 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
     }
 }
 
+// One launch per layer: forward pack + dgrad pack + in-place zeroing of the masked taps.
+// blockIdx.y in [0, nf): forward taps; [nf, nf+nd): dgrad taps; nf+nd: the zeroing slab.
+// Packing reads only live (co >= s(t)) weights and the zeroing writes only masked ones: no race.
+template <typename T>
+__global__ void __launch_bounds__(256) pack_pair_kernel(float* __restrict__ W, T* __restrict__ pf, T* __restrict__ pd,
+                                                         int Cin, int Cout, int Kmax,
+                                                         const __grid_constant__ TapTable tf,
+                                                         const __grid_constant__ TapTable td,
+                                                         const __grid_constant__ STable st, int nd, int zero_masked) {
+    const int nf = tf.n_order;
+    int y = blockIdx.y;
+    if (y >= nf + nd) {
+        if (!zero_masked) return;
+        const int total = Cout * Cin * Kmax;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+            const int t = i % Kmax;
+            const int co = i / (Kmax * Cin);
+            if (co < st.s[t]) W[i] = 0.f;
+        }
+        return;
+    }
+    const bool fwd = y < nf;
+    const TapTable& tt = fwd ? tf : td;
+    if (!fwd) y -= nf;
+    const int t = tt.order[y];
+    const int n_lo = tt.n_lo[t], kc_lo = tt.kc_lo[t];
+    const int nrows = tt.np - n_lo;
+    const int elems = (tt.kc - kc_lo) * nrows * 8;
+    const int wt = fwd ? t : Kmax - 1 - t;
+    const int s = st.s[wt];
+    T* blob = (fwd ? pf : pd) + (long long)tt.w_off[t] * 8;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < elems; e += gridDim.x * blockDim.x) {
+        const int j = e & 7;
+        const int n = n_lo + (e >> 3) % nrows;
+        const int k = (kc_lo + (e >> 3) / nrows) * 8 + j;
+        const int co = fwd ? n : k;
+        const int ci = fwd ? k : n;
+        float v = 0.f;
+        if (co < Cout && ci < Cin && co >= s) v = W[((long long)co * Cin + ci) * Kmax + wt];
+        blob[e] = from_f32<T>(v);
+    }
+}
+
 __global__ void __launch_bounds__(256) zero_masked_kernel(float* __restrict__ W, int Cin, int Cout, int Kmax,
                                                             const __grid_constant__ STable st) {
     const int total = Cout * Cin * Kmax;
@@ -174,3 +217,28 @@ int tsc_pack_weights(int direction, int dtype, float* W, void* packed, int Cin, 
 }
 
 }  // extern "C"
+
+extern "C" int tsc_pack_weights_pair(int dtype, float* W, void* packed_fwd, void* packed_dgrad, int Cin, int Cout,
+                                     int Kmax, const int* s_of_tap, int zero_masked, tsc_stream_t stream) {
+    using namespace tsc;
+    TSC_REQUIRE(W && packed_fwd, "NULL tensor");
+    TapTable tf, td;
+    if (build_tap_table(TSC_DIR_FWD, Cin, Cout, Kmax, s_of_tap, &tf) != 0) return -1;
+    if (build_tap_table(TSC_DIR_DGRAD, Cin, Cout, Kmax, s_of_tap, &td) != 0) return -1;
+    STable st;
+    fill_stable(&st, s_of_tap, Kmax);
+    const int nd = packed_dgrad ? td.n_order : 0;
+    const int max_elems = max(tf.kc * tf.np, td.kc * td.np) * 8;
+    dim3 grid(cdiv(max_elems, 256 * 4), tf.n_order + nd + (zero_masked ? 1 : 0));
+    cudaStream_t cs = (cudaStream_t)stream;
+    if (dtype == TSC_BF16)
+        pack_pair_kernel<__nv_bfloat16><<<grid, 256, 0, cs>>>(W, (__nv_bfloat16*)packed_fwd, (__nv_bfloat16*)packed_dgrad, Cin,
+                                                            Cout, Kmax, tf, td, st, nd, zero_masked);
+    else if (dtype == TSC_F32)
+        pack_pair_kernel<float><<<grid, 256, 0, cs>>>(W, (float*)packed_fwd, (float*)packed_dgrad, Cin, Cout, Kmax, tf, td,
+                                                    st, nd, zero_masked);
+    else
+        TSC_REQUIRE(false, "bad dtype %d", dtype);
+    TSC_LAUNCH_CHECK();
+    return 0;
+}

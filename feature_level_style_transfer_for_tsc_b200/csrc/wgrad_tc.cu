@@ -213,8 +213,12 @@ int oswgrad_tc(const void* dy, const void* x, int dtype, float* dW, void* worksp
     CUtensorMap dymap, xmap;
     if (make_c8_map(&dymap, dy, B, np / 8, L, WG_LT) != 0) return -1;
     if (make_c8_map(&xmap, x, B, p.kcx, L, p.RX) != 0) return -1;
-    cudaError_t e = cudaFuncSetAttribute(oswgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    static bool attr_set = false;          // once per process: opt in to the full 227 KB of dynamic shared memory
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(oswgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        attr_set = true;
+    }
     oswgrad_tc_kernel<<<dim3(items.n, p.S), WG_THREADS, smem, cs>>>(dymap, xmap, items, p);
     TSC_LAUNCH_CHECK();
     return launch_wgrad_reduce(p.part, dW, p.S, Cin, Cout, Kmax, np, cinp, s_of_tap, cs);

@@ -73,8 +73,8 @@ class OSStackFunction(torch.autograd.Function):
             W, bias, gamma, beta = params[4 * i: 4 * i + 4]
             g = ls.geom
             with torch.no_grad():
-                wf = ops.pack_weights(g, W, L.DIR_FWD, dt, ls.zero_masked)
-                sv.wd.append(ops.pack_weights(g, W, L.DIR_DGRAD, dt, False) if (i > 0 or need_dgrad_first) else None)
+                wf, wd = ops.pack_weights_pair(g, W, dt, ls.zero_masked, i > 0 or need_dgrad_first)
+                sv.wd.append(wd)
             y = ops.osconv(eng, L.DIR_FWD, g, h, wf, bias)
             if ls.training:
                 co = ops.bn_stats(y, g.cout, gamma, beta, ls.running_mean if ls.momentum > 0 else None,
@@ -92,8 +92,7 @@ class OSStackFunction(torch.autograd.Function):
                 sc = spec.shortcut
                 Wr, br, gr, betar = params[4 * nl: 4 * nl + 4]
                 with torch.no_grad():
-                    wfr = ops.pack_weights(sc.geom, Wr, L.DIR_FWD, dt, False)
-                    sv.wd_r = ops.pack_weights(sc.geom, Wr, L.DIR_DGRAD, dt, False) if need_dgrad_first else None
+                    wfr, sv.wd_r = ops.pack_weights_pair(sc.geom, Wr, dt, False, need_dgrad_first)
                 y_r = ops.osconv(eng, L.DIR_FWD, sc.geom, x_op, wfr, br)
                 if sc.training:
                     co_r = ops.bn_stats(y_r, sc.geom.cout, gr, betar, sc.running_mean if sc.momentum > 0 else None,
@@ -118,6 +117,8 @@ class OSStackFunction(torch.autograd.Function):
         dz = ops.ncl_to_c8(dout, L.TSC_F32)
         grads: List[Optional[torch.Tensor]] = [None] * len(params)
         dx_short = None
+        # d(conv bias) behind a train-mode BN is identically zero: one zero buffer serves every layer
+        zero_bias = torch.zeros(max(p.numel() for p in params[1::4]), device=dout.device, dtype=torch.float32)
         # masks of the top of the stack
         last = spec.layers[-1]
         if spec.shortcut is not None:
@@ -128,9 +129,9 @@ class OSStackFunction(torch.autograd.Function):
             s1, s2 = ops.bn_bwd_reduce(dz, sv.y_r, sv.co_r, sc.geom.cout, top_mask1, top_mask2)
             dy_r = ops.bn_bwd_apply(dz, sv.y_r, sv.co_r, gr, s1, s2, sc.training, sc.geom.cout, dt, top_mask1, top_mask2)
             C = sc.geom.cout
-            grads[4 * nl + 2] = s2[:C].clone()
-            grads[4 * nl + 3] = s1[:C].clone()
-            grads[4 * nl + 1] = torch.zeros_like(br) if sc.training else (gr * sv.co_r.invstd[:C] * s1[:C])
+            grads[4 * nl + 2] = s2[:C]
+            grads[4 * nl + 3] = s1[:C]
+            grads[4 * nl + 1] = zero_bias[:C] if sc.training else (gr * sv.co_r.invstd[:C] * s1[:C])
             grads[4 * nl + 0] = ops.oswgrad(spec.wgrad_engine, sc.geom, dy_r, sv.x_ops[0])
             if ctx.x_requires_grad:
                 dx_short = ops.osconv(eng, L.DIR_DGRAD, sc.geom, dy_r, sv.wd_r, None)
@@ -149,10 +150,10 @@ class OSStackFunction(torch.autograd.Function):
             s1, s2 = ops.bn_bwd_reduce(dz, y, co, g.cout, m1, m2)
             dy = ops.bn_bwd_apply(dz, y, co, gamma, s1, s2, ls.training, g.cout, dt, m1, m2)
             C = g.cout
-            grads[4 * i + 2] = s2[:C].clone()
-            grads[4 * i + 3] = s1[:C].clone()
+            grads[4 * i + 2] = s2[:C]
+            grads[4 * i + 3] = s1[:C]
             # d(bias) = sum dY: identically 0 behind a train-mode BN, gamma*invstd*S1 behind an eval-mode BN
-            grads[4 * i + 1] = torch.zeros_like(bias) if ls.training else (gamma * co.invstd[:C] * s1[:C])
+            grads[4 * i + 1] = zero_bias[:C] if ls.training else (gamma * co.invstd[:C] * s1[:C])
             grads[4 * i + 0] = ops.oswgrad(spec.wgrad_engine, g, dy, sv.x_ops[i])
             if i > 0 or ctx.x_requires_grad:
                 dz = ops.osconv(eng, L.DIR_DGRAD, g, dy, sv.wd[i], None)

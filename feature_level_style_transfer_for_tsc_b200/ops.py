@@ -176,6 +176,31 @@ def pack_weights(g: BankGeometry, W: torch.Tensor, direction: int, dt: int, zero
     return packed
 
 
+def pack_weights_pair(g: BankGeometry, W: torch.Tensor, dt: int, zero_masked: bool, want_dgrad: bool):
+    """Forward pack, (optionally) dgrad pack and the in-place masking of W in one launch."""
+    _req(W, name="weight")
+    if tuple(W.shape) != (g.cout, g.cin, g.kmax):
+        raise RuntimeError(f"weight shape {tuple(W.shape)} != {(g.cout, g.cin, g.kmax)}")
+    esz = 2 if dt == L.TSC_BF16 else 4
+    pf = torch.empty(g.packed_bytes(L.DIR_FWD, dt) // esz, device=W.device, dtype=torch_dtype(dt))
+    pd = torch.empty(g.packed_bytes(L.DIR_DGRAD, dt) // esz, device=W.device, dtype=torch_dtype(dt)) if want_dgrad else None
+    L.check(L.load().tsc_pack_weights_pair(dt, _ptr(W), _ptr(pf), _ptr(pd), g.cin, g.cout, g.kmax, g.s_arr,
+                                           1 if zero_masked else 0, _stream()), "tsc_pack_weights_pair")
+    return pf, pd
+
+
+def rmsprop_step(params: torch.Tensor, grads: torch.Tensor, square_avg: torch.Tensor, group_end, group_lr,
+                 alpha: float = 0.99, eps: float = 1e-8, grad_scale: float = 1.0):
+    """Fused RMSprop over flat fp32 buffers (torch.optim.RMSprop defaults; per-group learning rates)."""
+    for t, nm in ((params, "params"), (grads, "grads"), (square_avg, "square_avg")):
+        _req(t, name=nm)
+    n = params.numel()
+    ends = (ctypes.c_longlong * len(group_end))(*[int(e) for e in group_end])
+    lrs = (ctypes.c_float * len(group_lr))(*[float(x) for x in group_lr])
+    L.check(L.load().tsc_rmsprop_step(_ptr(params), _ptr(grads), _ptr(square_avg), n, ends, lrs, len(group_end),
+                                      float(alpha), float(eps), float(grad_scale), _stream()), "tsc_rmsprop_step")
+
+
 def osconv(engine: int, direction: int, g: BankGeometry, x8: torch.Tensor, w_packed: torch.Tensor,
            bias: Optional[torch.Tensor]) -> torch.Tensor:
     dt = L.TSC_BF16 if x8.dtype == torch.bfloat16 else L.TSC_F32

@@ -24,6 +24,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import functional as TF
+from . import ops
 from .OS_CNN.OS_CNN import OS_CNN, OS_CNN_res, layer_parameter_list_input_change
 from .OS_CNN.OS_CNN_Structure_build import generate_layer_parameter_list
 from .widgets import DimensionUnification
@@ -69,50 +70,105 @@ class StyleTransferModelSet(nn.Module):
                     logits_t=logits_t, logits_s=logits_s, tf=tf, ssf=ssf, s2t=s2t)
 
 
-class FlatGradBucket:
-    """All parameter gradients as views into one flat fp32 buffer, so the data-parallel exchange is ONE
-    all-reduce per step.  ``p.grad`` is pre-bound to its slice; autograd accumulates in place."""
+class FlatParameters:
+    """Every trainable parameter, its gradient and its RMSprop state as views into three flat fp32 buffers
+    (group by group), so that the data-parallel exchange is ONE all-reduce and the optimizer ONE kernel launch
+    per step.  ``p.data`` / ``p.grad`` are re-bound to their slices; module code is unaffected."""
 
-    def __init__(self, params: List[torch.nn.Parameter]):
-        self.params = [p for p in params if p.requires_grad]
-        n = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(n, device=self.params[0].device, dtype=torch.float32)
+    def __init__(self, groups):
+        """groups: list of (params, lr)."""
+        params = [p for ps, _ in groups for p in ps if p.requires_grad]
+        dev = params[0].device
+        # 4-element alignment of every tensor keeps the float4 path of the optimizer kernel on group boundaries
+        sizes = [(p.numel() + 3) // 4 * 4 for p in params]
+        n = sum(sizes)
+        self.params = params
+        self.flat_p = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.flat_g = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.flat_v = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.group_end, self.group_lr = [], []
         off = 0
-        for p in self.params:
-            p.grad = self.flat[off: off + p.numel()].view_as(p)
-            off += p.numel()
+        it = iter(sizes)
+        for ps, lr in groups:
+            for p in ps:
+                if not p.requires_grad:
+                    continue
+                sz = next(it)
+                view = self.flat_p[off: off + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+                p.grad = self.flat_g[off: off + p.numel()].view_as(p)
+                off += sz
+            self.group_end.append(off)
+            self.group_lr.append(lr)
 
-    def zero(self):
-        self.flat.zero_()
+    def zero_grad(self):
+        self.flat_g.zero_()
 
-    def all_reduce_mean(self, group=None):
+    def all_reduce_sum(self, group=None) -> int:
+        """Sum the flat gradient bucket over the ranks; returns the world size (the 1/N is applied inside the
+        optimizer kernel)."""
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-            self.flat.mul_(1.0 / dist.get_world_size(group))
+            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=group)
+            return dist.get_world_size(group)
+        return 1
+
+    def rmsprop(self, grad_scale: float = 1.0, alpha: float = 0.99, eps: float = 1e-8):
+        ops.rmsprop_step(self.flat_p, self.flat_g, self.flat_v, self.group_end, self.group_lr, alpha, eps, grad_scale)
 
 
 class Trainer:
-    """forward + backward + (all-reduce) + RMSprop of the cfg2 step."""
+    """forward + backward + (all-reduce) + fused RMSprop of the cfg2 step.
 
-    def __init__(self, model: StyleTransferModelSet, style_weight: float = 1.0, group=None):
+    ``use_graph=True`` captures forward + backward of one step in a CUDA graph (fixed shapes): the step is
+    launch-bound at cfg2 size (about 200 small kernels), and replaying one graph removes the host from the loop."""
+
+    def __init__(self, model: StyleTransferModelSet, style_weight: float = 1.0, group=None, use_graph: bool = False):
         self.model = model
         self.style_weight = style_weight
         self.group = group
-        groups = [dict(params=list(getattr(model, name).parameters()), lr=lr) for name, lr in LEARNING_RATES.items()]
-        self.bucket = FlatGradBucket([p for g in groups for p in g["params"]])
-        self.opt = torch.optim.RMSprop(groups, lr=0.001, foreach=True)
+        self.flat = FlatParameters([(list(getattr(model, name).parameters()), lr) for name, lr in LEARNING_RATES.items()])
+        self.use_graph = use_graph
+        self._graph = None
+        self._static_in = None
+        self._static_loss = None
 
     def broadcast_parameters(self, src: int = 0):
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
-            for t in list(self.model.parameters()) + list(self.model.buffers()):
+            dist.broadcast(self.flat.flat_p, src=src, group=self.group)
+            for t in self.model.buffers():
                 dist.broadcast(t.data, src=src, group=self.group)
 
-    def step(self, xt, yt, xs, ys) -> torch.Tensor:
-        self.bucket.zero()
+    def _fwd_bwd(self, xt, yt, xs, ys):
+        self.flat.zero_grad()
         out = self.model(xt, yt, xs, ys, self.style_weight)
         out["loss"].backward()
-        self.bucket.all_reduce_mean(self.group)
-        self.opt.step()
         return out["loss"].detach()
+
+    def _capture(self, xt, yt, xs, ys):
+        self._static_in = [t.clone() for t in (xt, yt, xs, ys)]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):                          # warm-up on a side stream, as graph capture requires
+                self._fwd_bwd(*self._static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._static_loss = self._fwd_bwd(*self._static_in)
+
+    def step(self, xt, yt, xs, ys) -> torch.Tensor:
+        if self.use_graph:
+            if self._graph is None:
+                self._capture(xt, yt, xs, ys)
+            for dst, src in zip(self._static_in, (xt, yt, xs, ys)):
+                dst.copy_(src, non_blocking=True)
+            self._graph.replay()
+            loss = self._static_loss
+        else:
+            loss = self._fwd_bwd(xt, yt, xs, ys)
+        world = self.flat.all_reduce_sum(self.group)
+        self.flat.rmsprop(grad_scale=1.0 / world)
+        return loss

@@ -37,6 +37,7 @@ extern "C" {
 #define TSC_VERSION 100
 #define TSC_MAX_TAPS 96          /* largest supported Kmax (reference caps it at 89, train_and_test.py:40) */
 #define TSC_MAX_CHANNELS 256     /* largest padded channel count of one OS layer (reference: <= 228) */
+#define TSC_MAX_OPT_GROUPS 16    /* parameter groups of one tsc_rmsprop_step call */
 
 typedef void* tsc_stream_t;      /* cudaStream_t */
 
@@ -67,6 +68,10 @@ int tsc_c8_to_ncl(const float* src_c8, float* dst_ncl, int B, int C, int L, tsc_
 size_t tsc_packed_weight_bytes(int direction, int dtype, int Cin, int Cout, int Kmax, const int* s_of_tap);
 int tsc_pack_weights(int direction, int dtype, float* W, void* packed, int Cin, int Cout, int Kmax,
                      const int* s_of_tap, int zero_masked, tsc_stream_t stream);
+/* Both directions (packed_dgrad may be NULL) and the in-place masking in ONE launch -- what a layer's
+ * forward needs every step, since the optimizer changes W between steps. */
+int tsc_pack_weights_pair(int dtype, float* W, void* packed_fwd, void* packed_dgrad, int Cin, int Cout, int Kmax,
+                          const int* s_of_tap, int zero_masked, tsc_stream_t stream);
 
 /* ---- multi-kernel-size Conv1d as one implicit GEMM: replaces ConstantPad1d + Conv1d
  * (OS_CNN.py:70-71, 163-164) and their cuDNN/oneDNN dgrad -------------------------------------
@@ -130,6 +135,13 @@ int tsc_gram_loss_fwd(int engine, const float* a, const float* s, float* D, floa
 /* da = g * 4/(B C^3 L) * D a ; ds = -g * 4/(B C^3 L) * D s ; g = *dloss (device scalar). */
 int tsc_gram_loss_bwd(int engine, const float* D, const float* a, const float* s, const float* dloss,
                       float* da, float* ds, int B, int C, int L, tsc_stream_t stream);
+
+/* ---- fused multi-tensor RMSprop over flat fp32 buffers: replaces the 5 torch.optim.RMSprop instances of the
+ * path (train_and_test.py:97-101): v = alpha v + (1-alpha) g^2 ; p -= lr g / (sqrt(v)+eps), g = grad_scale*grad.
+ * group_end / group_lr (HOST, ngroups entries): exclusive end offset and learning rate of each parameter group. */
+int tsc_rmsprop_step(float* params, const float* grads, float* square_avg, long long n,
+                     const long long* group_end, const float* group_lr, int ngroups, float alpha, float eps,
+                     float grad_scale, tsc_stream_t stream);
 
 /* ---- debugging aid: the tcgen05 kernels bound every mbarrier wait; a timed-out wait stores a
  * non-zero code here (device word, read back by the caller when it wants to). */
