@@ -149,6 +149,8 @@ class Trainer:
 
     def _capture(self, xt, yt, xs, ys):
         self._static_in = [t.clone() for t in (xt, yt, xs, ys)]
+        # the warm-up passes must leave no trace: BatchNorm running statistics are forward side effects
+        saved = [b.detach().clone() for b in self.model.buffers()]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -158,6 +160,9 @@ class Trainer:
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self._static_loss = self._fwd_bwd(*self._static_in)
+        with torch.no_grad():
+            for b, v in zip(self.model.buffers(), saved):
+                b.copy_(v)
 
     def step(self, xt, yt, xs, ys) -> torch.Tensor:
         if self.use_graph:
