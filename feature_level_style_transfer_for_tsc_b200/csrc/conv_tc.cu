@@ -33,7 +33,8 @@ struct ConvTcParams {
 };
 
 static constexpr int TC_THREADS = 192;
-static constexpr int SMEM_HDR = 256;     // barriers + tmem slot
+static constexpr int SMEM_TAPINFO = 256;  // per-tap issue constants, TSC_MAX_TAPS x 16 B
+static constexpr int SMEM_HDR = 256 + TSC_MAX_TAPS * 16;     // barriers + tmem slot + tap info
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ TapTable tt, const ConvTcParams p) {
@@ -70,52 +71,69 @@ osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             mbar_arrive_expect_tx(x_full, (uint32_t)(kc * p.Rp * 16));
             for (int kcI = 0; kcI < kc; ++kcI)
                 tma_load_4d(xs + (size_t)kcI * p.Rp * 16, &xmap, 0, l0 - tt.pad_left, kcI, b, x_full);
-            int it = 0;
+            uint32_t s = 0, ph = 0;
             for (int oi = 0; oi < tt.n_order; ++oi) {
                 const int t = tt.order[oi];
                 const int nt = np - tt.n_lo[t], kspan = kc - tt.kc_lo[t];
                 const __nv_bfloat16* blob = p.w + (size_t)tt.w_off[t] * 8;
-                for (int g0 = 0; g0 < kspan; g0 += p.KB, ++it) {
-                    const int s = it % p.NS;
-                    const uint32_t ph = (uint32_t)(it / p.NS) & 1u;
+                for (int g0 = 0; g0 < kspan; g0 += p.KB) {
                     mbar_wait(&empty[s], ph ^ 1u, dead, 1);
                     const int nch = min(p.KB, kspan - g0);
                     const uint32_t bytes = (uint32_t)(nch * nt * 16);
                     mbar_arrive_expect_tx(&full[s], bytes);
                     bulk_load(stages + (size_t)s * p.stage_bytes, blob + (size_t)g0 * nt * 8, bytes, &full[s]);
+                    if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
+        // A tcgen05.mma with M = 128 occupies the tensor pipe for N/2 cycles, but one thread cannot issue faster
+        // than one every ~54 cycles (measured, tools/mma_bench2.cu), so the issue loop is kept lean: per-tap
+        // constants are precomputed by the whole warp into shared memory, descriptors advance by adding to
+        // their low word, and the stage ring is tracked without divisions.
+        uint32_t* tapinfo = reinterpret_cast<uint32_t*>(smem + SMEM_TAPINFO);     // [n_order][4]
+        for (int oi = lane; oi < tt.n_order; oi += 32) {
+            const int t = tt.order[oi];
+            const int n_lo = tt.n_lo[t], kc_lo = tt.kc_lo[t];
+            const int nt = np - n_lo;
+            tapinfo[oi * 4 + 0] = (uint32_t)(kc_lo * p.Rp + t);                    // A row offset (16 B units)
+            tapinfo[oi * 4 + 1] = (uint32_t)nt | ((uint32_t)(kc - kc_lo) << 16);    // N, k span (chunks)
+            tapinfo[oi * 4 + 2] = make_idesc_bf16(128, (uint32_t)nt, false, false, false);
+            tapinfo[oi * 4 + 3] = tmem_base + (uint32_t)n_lo;
+        }
+        __syncwarp();
         if (lane == 0) {
             bool dead = false;
             mbar_wait(x_full, 0, dead, 2);
             tc_fence_after();
-            const uint32_t xs_addr = smem_u32(xs), st_addr = smem_u32(stages);
-            const uint32_t a_lbo = (uint32_t)p.Rp * 16;
-            int it = 0;
-            bool first = true;
-            for (int oi = 0; oi < tt.n_order; ++oi) {
-                const int t = tt.order[oi];
-                const int n_lo = tt.n_lo[t], kc_lo = tt.kc_lo[t];
-                const int nt = np - n_lo, kspan = kc - kc_lo;
-                const uint32_t idesc = make_idesc_bf16(128, (uint32_t)nt, false, false, false);
-                const uint32_t d_tmem = tmem_base + (uint32_t)n_lo;
-                for (int g0 = 0; g0 < kspan; g0 += p.KB, ++it) {
-                    const int s = it % p.NS;
-                    const uint32_t ph = (uint32_t)(it / p.NS) & 1u;
+            const uint32_t desc_hi = (128u >> 4) | (1u << 14);                      // SBO = 128 B, descriptor version 1
+            const uint32_t a_base16 = (smem_u32(xs) >> 4) | ((uint32_t)p.Rp << 16);  // LBO = Rp * 16 B
+            const uint32_t st_base16 = smem_u32(stages) >> 4;
+            const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4;
+            const uint32_t a_step = 2u * (uint32_t)p.Rp;                             // 16 channels = 2 chunks
+            uint32_t s = 0, ph = 0, acc = 0;
+            const int n_order = tt.n_order, KB = p.KB;
+            for (int oi = 0; oi < n_order; ++oi) {
+                const uint4 ti = *reinterpret_cast<const uint4*>(tapinfo + oi * 4);
+                const uint32_t nt = ti.y & 0xffffu;
+                const int kspan = (int)(ti.y >> 16);
+                const uint32_t b_step = 2u * nt;
+                uint32_t a_lo = a_base16 + ti.x;
+                for (int g0 = 0; g0 < kspan; g0 += KB) {
                     mbar_wait(&full[s], ph, dead, 3);
                     tc_fence_after();
-                    const int nch = min(p.KB, kspan - g0);
-                    for (int k2 = 0; k2 < nch; k2 += 2) {
-                        const uint32_t a_addr = xs_addr + (uint32_t)(((kc_lo + g0 + k2) * p.Rp + t) * 16);
-                        const uint32_t b_addr = st_addr + (uint32_t)(s * p.stage_bytes + k2 * nt * 16);
-                        umma_bf16(d_tmem, make_smem_desc(a_addr, a_lbo, 128), make_smem_desc(b_addr, (uint32_t)nt * 16, 128),
-                                  idesc, !first);
-                        first = false;
+                    const int nsteps = min(KB, kspan - g0) >> 1;
+                    uint32_t b_lo = (st_base16 + s * stage16) | (nt << 16);          // LBO = nt * 16 B
+#pragma unroll 5
+                    for (int k = 0; k < nsteps; ++k) {
+                        umma_bf16(ti.w, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, ti.z, acc);
+                        acc = 1;
+                        a_lo += a_step;
+                        b_lo += b_step;
                     }
                     tc_commit(&empty[s]);      // frees the stage when these MMAs have read it
+                    if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; }
                 }
             }
             tc_commit(acc_full);

@@ -77,9 +77,8 @@ oswgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_consta
         if (lane == 0) {
             bool dead = false;
             const uint32_t bytes = (uint32_t)((dy_chunks * WG_LT + p.kcx * p.RX) * 16);
-            for (int tile = tile0, it = 0; tile < tile1; ++tile, ++it) {
-                const int s = it % WG_STAGES;
-                const uint32_t ph = (uint32_t)(it / WG_STAGES) & 1u;
+            uint32_t s = 0, ph = 0;
+            for (int tile = tile0; tile < tile1; ++tile) {
                 const int b = tile / p.ltiles, l0 = (tile % p.ltiles) * WG_LT;
                 mbar_wait(&empty[s], ph ^ 1u, dead, 5);
                 uint8_t* st = stages + (size_t)s * p.stage_bytes;
@@ -88,29 +87,38 @@ oswgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_consta
                     tma_load_4d(st + (size_t)c * WG_LT * 16, &dymap, 0, l0, item.m0 / 8 + c, b, &full[s]);
                 for (int c = 0; c < p.kcx; ++c)
                     tma_load_4d(st + dy_bytes + (size_t)c * p.RX * 16, &xmap, 0, l0 + item.t0 - p.pad_left, c, b, &full[s]);
+                if (++s == WG_STAGES) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
+            // lean issue loop (one thread issues at most one MMA per ~54 cycles): descriptors advance by adds
             bool dead = false;
             const uint32_t idesc = make_idesc_bf16(128, (uint32_t)cinp, true, true, false);
-            const uint32_t st_addr = smem_u32(stages);
-            for (int tile = tile0, it = 0; tile < tile1; ++tile, ++it) {
-                const int s = it % WG_STAGES;
-                const uint32_t ph = (uint32_t)(it / WG_STAGES) & 1u;
+            const uint32_t st16 = smem_u32(stages) >> 4, stage16 = (uint32_t)p.stage_bytes >> 4;
+            // MN-major, SWIZZLE_NONE: LBO = 128 B between 8-position groups, SBO = chunk stride
+            const uint32_t a_hi = ((uint32_t)(WG_LT * 16) >> 4) | (1u << 14);
+            const uint32_t b_hi = ((uint32_t)(p.RX * 16) >> 4) | (1u << 14);
+            const uint32_t lbo = (128u >> 4) << 16;
+            uint32_t s = 0, ph = 0, acc = 0;
+            const int nt = item.nt;
+            for (int tile = tile0; tile < tile1; ++tile) {
                 mbar_wait(&full[s], ph, dead, 6);
                 tc_fence_after();
-                const uint32_t a_base = st_addr + (uint32_t)(s * p.stage_bytes);
-                const uint32_t b_base = a_base + (uint32_t)dy_bytes;
-                for (int tl = 0; tl < item.nt; ++tl) {
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(tl * cinp);
+                const uint32_t a0 = (st16 + s * stage16) | lbo;
+                const uint32_t b0 = (st16 + s * stage16 + ((uint32_t)dy_bytes >> 4)) | lbo;
+                uint32_t d_tmem = tmem_base;
+                for (int tl = 0; tl < nt; ++tl) {
+#pragma unroll
                     for (int k16 = 0; k16 < WG_LT / 16; ++k16) {
-                        const uint64_t a_desc = make_smem_desc(a_base + (uint32_t)(k16 * 256), 128, (uint32_t)WG_LT * 16);
-                        const uint64_t b_desc = make_smem_desc(b_base + (uint32_t)((tl + k16 * 16) * 16), 128, (uint32_t)p.RX * 16);
-                        umma_bf16(d_tmem, a_desc, b_desc, idesc, it > 0 || k16 > 0);
+                        umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | (a0 + (uint32_t)(k16 * 16)),
+                                  ((uint64_t)b_hi << 32) | (b0 + (uint32_t)(tl + k16 * 16)), idesc, acc | (uint32_t)(k16 > 0));
                     }
+                    d_tmem += (uint32_t)cinp;
                 }
+                acc = 1;
                 tc_commit(&empty[s]);
+                if (++s == WG_STAGES) { s = 0; ph ^= 1u; }
             }
             tc_commit(acc_full);
         }
