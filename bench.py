@@ -279,7 +279,10 @@ def run_ours(args):
     trainer.use_graph = False
     psteps = 3
     for _ in range(psteps):
-        flush.zero_()
+        # keep the GPU busy (~12 ms of memsets) while the host enqueues the whole eager step, so that every event
+        # pair brackets device time only -- without this the host's launch latency sits between the events
+        for _ in range(260):
+            flush.zero_()
         trainer.step(*dev_in)
     torch.cuda.synchronize()
     table = prof.table(psteps)

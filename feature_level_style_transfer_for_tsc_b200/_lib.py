@@ -63,6 +63,7 @@ SIGNATURES = {
     "tsc_gram_loss_fwd": (_i, [_i, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "tsc_gram_loss_bwd": (_i, [_i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "tsc_debug_read_and_clear_watchdog": (_i, [_ip]),
+    "tsc_debug_set_timeline": (_i, [_p]),
 }
 
 

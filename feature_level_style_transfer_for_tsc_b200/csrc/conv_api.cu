@@ -15,6 +15,7 @@ int wgrad_tc_splits(int B, int L, int Cin, int Cout, int Kmax);
 int read_clear_watchdog_conv(int* code);
 int read_clear_watchdog_wgrad(int* code);
 int read_clear_watchdog_gram(int* code);
+void set_conv_timeline(long long* dev);
 }  // namespace tsc
 
 extern "C" {
@@ -52,6 +53,8 @@ int tsc_oswgrad(int engine, const void* dy, const void* x, int dtype, float* dW,
         return oswgrad_tc(dy, x, dtype, dW, workspace, B, L, Cin, Cout, Kmax, s_of_tap, (cudaStream_t)stream);
     TSC_REQUIRE(false, "bad engine %d", engine);
 }
+
+int tsc_debug_set_timeline(void* dev_buf) { tsc::set_conv_timeline((long long*)dev_buf); return 0; }
 
 int tsc_debug_read_and_clear_watchdog(int* host_code) {
     using namespace tsc;

@@ -30,7 +30,10 @@ struct ConvTcParams {
     int stage_bytes;
     int xs_bytes;
     int tmem_cols;
+    long long* tl;     // optional phase timeline of CTA 0 (tsc_debug_set_timeline), NULL in production
 };
+
+#define TL(i) do { if (p.tl && blockIdx.x == 0) p.tl[i] = clock64(); } while (0)
 
 static constexpr int TC_THREADS = 192;
 static constexpr int SMEM_TAPINFO = 256;  // per-tap issue constants, TSC_MAX_TAPS x 16 B
@@ -52,6 +55,7 @@ osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     const int np = tt.np, kc = tt.kc;
 
     if (warp == 0 && lane == 0) {
+        TL(0);
         tma_prefetch_desc(&xmap);
         for (int i = 0; i < p.NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(x_full, 1);
@@ -68,6 +72,7 @@ osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         // ===== copy producer =====
         if (lane == 0) {
             bool dead = false;
+            TL(1);
             mbar_arrive_expect_tx(x_full, (uint32_t)(kc * p.Rp * 16));
             for (int kcI = 0; kcI < kc; ++kcI)
                 tma_load_4d(xs + (size_t)kcI * p.Rp * 16, &xmap, 0, l0 - tt.pad_left, kcI, b, x_full);
@@ -107,6 +112,7 @@ osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             bool dead = false;
             mbar_wait(x_full, 0, dead, 2);
             tc_fence_after();
+            TL(2);
             const uint32_t desc_hi = (128u >> 4) | (1u << 14);                      // SBO = 128 B, descriptor version 1
             const uint32_t a_base16 = (smem_u32(xs) >> 4) | ((uint32_t)p.Rp << 16);  // LBO = Rp * 16 B
             const uint32_t st_base16 = smem_u32(stages) >> 4;
@@ -123,6 +129,7 @@ osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                 for (int g0 = 0; g0 < kspan; g0 += KB) {
                     mbar_wait(&full[s], ph, dead, 3);
                     tc_fence_after();
+                    if (oi == 0 && g0 == 0) TL(3);
                     const int nsteps = min(KB, kspan - g0) >> 1;
                     uint32_t b_lo = (st_base16 + s * stage16) | (nt << 16);          // LBO = nt * 16 B
 #pragma unroll 5
@@ -137,12 +144,14 @@ osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                 }
             }
             tc_commit(acc_full);
+            TL(4);
         }
     } else {
         // ===== epilogue: TMEM -> registers -> (+bias) -> c8 fp32 =====
         bool dead = false;
         mbar_wait(acc_full, 0, dead, 4);
         tc_fence_after();
+        if (warp == 2 && lane == 0) TL(5);
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;
         const int l = l0 + row;
@@ -164,10 +173,12 @@ osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                 *reinterpret_cast<float4*>(d1 + 4) = make_float4(v[12], v[13], v[14], v[15]);
             }
         }
+        if (warp == 2 && lane == 0) TL(6);
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (warp == 1 && lane == 0) TL(7);
 }
 
 EncodeTiledFn get_encode_tiled() {
@@ -200,8 +211,11 @@ int make_c8_map(CUtensorMap* map, const void* base, int B, int kc, int L, int bo
 }
 
 static constexpr int SMEM_CAP = 227 * 1024;
+static long long* g_timeline = nullptr;     // debug only: device buffer of >= 8 clock64 samples
 
 }  // namespace tc
+
+void set_conv_timeline(long long* dev) { tc::g_timeline = dev; }
 
 int osconv_tc(int direction, const void* x, int dtype, const void* w, const float* bias, float* y, int B, int L, int Cin,
               int Cout, int Kmax, const int* s_of_tap, cudaStream_t cs) {
@@ -226,6 +240,7 @@ int osconv_tc(int direction, const void* x, int dtype, const void* w, const floa
     if (ns > 8) ns = 8;
     TSC_REQUIRE(ns >= 2, "shape needs %d B of shared memory for the activation tile: unsupported", p.xs_bytes);
     p.NS = ns;
+    p.tl = g_timeline;
     p.tmem_cols = tt.np <= 32 ? 32 : tt.np <= 64 ? 64 : tt.np <= 128 ? 128 : 256;
     CUtensorMap xmap;
     if (make_c8_map(&xmap, x, B, tt.kc, L, p.Rp) != 0) return -1;

@@ -146,6 +146,10 @@ int tsc_rmsprop_step(float* params, const float* grads, float* square_avg, long 
 /* ---- debugging aid: the tcgen05 kernels bound every mbarrier wait; a timed-out wait stores a
  * non-zero code here (device word, read back by the caller when it wants to). */
 int tsc_debug_read_and_clear_watchdog(int* host_code);
+/* profiling aid: when dev_buf != NULL (device memory, >= 8 x int64), CTA 0 of every following tcgen05 conv launch
+ * stores clock64() at its phase boundaries there (entry, setup, tile loaded, first weights, MMAs issued,
+ * accumulator ready, epilogue done, exit).  NULL switches it off (the default). */
+int tsc_debug_set_timeline(void* dev_buf);
 
 #ifdef __cplusplus
 }
