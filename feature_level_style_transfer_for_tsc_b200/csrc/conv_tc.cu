@@ -34,6 +34,7 @@ struct ConvTcParams {
 };
 
 #define TL(i) do { if (p.tl && blockIdx.x == 0) p.tl[i] = clock64(); } while (0)
+#define TLS(n, k) do { if (p.tl && blockIdx.x == 0 && (n) < 48) p.tl[8 + 8 * (n) + (k)] = clock64(); } while (0)
 
 static constexpr int TC_THREADS = 192;
 static constexpr int SMEM_TAPINFO = 256;  // per-tap issue constants, TSC_MAX_TAPS x 16 B
@@ -77,16 +78,21 @@ osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             for (int kcI = 0; kcI < kc; ++kcI)
                 tma_load_4d(xs + (size_t)kcI * p.Rp * 16, &xmap, 0, l0 - tt.pad_left, kcI, b, x_full);
             uint32_t s = 0, ph = 0;
+            int sn = 0;
             for (int oi = 0; oi < tt.n_order; ++oi) {
                 const int t = tt.order[oi];
                 const int nt = np - tt.n_lo[t], kspan = kc - tt.kc_lo[t];
                 const __nv_bfloat16* blob = p.w + (size_t)tt.w_off[t] * 8;
                 for (int g0 = 0; g0 < kspan; g0 += p.KB) {
+                    TLS(sn, 4);
                     mbar_wait(&empty[s], ph ^ 1u, dead, 1);
+                    TLS(sn, 5);
                     const int nch = min(p.KB, kspan - g0);
                     const uint32_t bytes = (uint32_t)(nch * nt * 16);
                     mbar_arrive_expect_tx(&full[s], bytes);
                     bulk_load(stages + (size_t)s * p.stage_bytes, blob + (size_t)g0 * nt * 8, bytes, &full[s]);
+                    TLS(sn, 6);
+                    ++sn;
                     if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; }
                 }
             }
@@ -119,6 +125,7 @@ osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4;
             const uint32_t a_step = 2u * (uint32_t)p.Rp;                             // 16 channels = 2 chunks
             uint32_t s = 0, ph = 0, acc = 0;
+            int sn = 0;
             const int n_order = tt.n_order, KB = p.KB;
             for (int oi = 0; oi < n_order; ++oi) {
                 const uint4 ti = *reinterpret_cast<const uint4*>(tapinfo + oi * 4);
@@ -127,8 +134,10 @@ osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                 const uint32_t b_step = 2u * nt;
                 uint32_t a_lo = a_base16 + ti.x;
                 for (int g0 = 0; g0 < kspan; g0 += KB) {
+                    TLS(sn, 0);
                     mbar_wait(&full[s], ph, dead, 3);
                     tc_fence_after();
+                    TLS(sn, 1);
                     if (oi == 0 && g0 == 0) TL(3);
                     const int nsteps = min(KB, kspan - g0) >> 1;
                     uint32_t b_lo = (st_base16 + s * stage16) | (nt << 16);          // LBO = nt * 16 B
@@ -139,7 +148,10 @@ osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                         a_lo += a_step;
                         b_lo += b_step;
                     }
+                    TLS(sn, 2);
                     tc_commit(&empty[s]);      // frees the stage when these MMAs have read it
+                    TLS(sn, 3);
+                    ++sn;
                     if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; }
                 }
             }

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--B", type=int, default=128)
     ap.add_argument("--layer", type=int, default=1, help="index into the extractor's layer list (or 3.. = classifier)")
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--stages", action="store_true", help="print the per-stage timeline of CTA 0")
     a = ap.parse_args()
     ext, cls, cf = trainer_layer_lists(a.C, a.L)
     layers = ext + cls
@@ -37,7 +38,7 @@ def main():
     flops = 2.0 * a.B * a.L * g.live_macs_per_position()
     flush = torch.empty(64 * 1024 * 1024, device=dev)
     res = {}
-    tl = torch.zeros(8, device=dev, dtype=torch.int64)
+    tl = torch.zeros(8 + 48 * 8, device=dev, dtype=torch.int64)
     names = ["entry", "setup", "x tile", "first W", "MMAs issued", "acc ready", "epilogue", "exit"]
     for name, fn in (("fwd", lambda: ops.osconv(L.ENGINE_TCGEN05, L.DIR_FWD, g, x8, wf, bias)),
                      ("dgrad", lambda: ops.osconv(L.ENGINE_TCGEN05, L.DIR_DGRAD, g, dy8, wd, None))):
@@ -47,6 +48,14 @@ def main():
         L.load().tsc_debug_set_timeline(None)
         t = tl.cpu().tolist()
         print(f"timeline[{name}] CTA0 cycles since entry: " + ", ".join(f"{n}={v - t[0]}" for n, v in zip(names, t)))
+        if a.stages:
+            print("  stage: mma[wait-begin, wait-end, issued, committed]  producer[wait-begin, wait-end, copy issued]")
+            for i in range(48):
+                r = t[8 + 8 * i: 8 + 8 * i + 7]
+                if r[0] == 0:
+                    break
+                print(f"  {i:3d}: " + " ".join(f"{v - t[0]:7d}" for v in r[:4]) + "   |" + " ".join(f"{v - t[0]:7d}" for v in r[4:7]))
+        tl.zero_()
     for name, fn in (("fwd", lambda: ops.osconv(L.ENGINE_TCGEN05, L.DIR_FWD, g, x8, wf, bias)),
                      ("dgrad", lambda: ops.osconv(L.ENGINE_TCGEN05, L.DIR_DGRAD, g, dy8, wd, None)),
                      ("wgrad", lambda: ops.oswgrad(L.ENGINE_TCGEN05, g, dy8, x8))):
