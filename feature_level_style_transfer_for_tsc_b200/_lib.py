@@ -34,6 +34,16 @@ _lib = None
 _p, _i, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
 _ip = ctypes.POINTER(ctypes.c_int)
 
+
+class ConvEpilogue(ctypes.Structure):
+    """tsc_conv_epilogue of include/tsc_b200.h (device pointers; all nullable)."""
+    _fields_ = [("stat_partial", ctypes.c_void_p), ("mask_y", ctypes.c_void_p), ("mask_scale", ctypes.c_void_p),
+                ("mask_shift", ctypes.c_void_p), ("mask_mean", ctypes.c_void_p), ("mask_invstd", ctypes.c_void_p),
+                ("red_partial", ctypes.c_void_p)]
+
+
+_ep = ctypes.POINTER(ConvEpilogue)
+
 # name -> (restype, argtypes); must list every symbol declared in include/tsc_b200.h
 SIGNATURES = {
     "tsc_version": (_i, []),
@@ -47,7 +57,9 @@ SIGNATURES = {
     "tsc_pack_weights_pair": (_i, [_i, _p, _p, _p, _i, _i, _i, _ip, _i, _p]),
     "tsc_rmsprop_step": (_i, [_p, _p, _p, ctypes.c_longlong, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_float),
                          _i, _f, _f, _f, _p]),
-    "tsc_osconv": (_i, [_i, _i, _p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _ip, _p]),
+    "tsc_osconv_plan_bytes": (_sz, [_i, _i, _i, _i, _ip]),
+    "tsc_osconv_plan_build": (_i, [_i, _i, _i, _i, _ip, _p]),
+    "tsc_osconv": (_i, [_i, _i, _p, _i, _p, _p, _p, _p, _ep, _i, _i, _i, _i, _i, _ip, _p]),
     "tsc_oswgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "tsc_oswgrad": (_i, [_i, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _ip, _p]),
     "tsc_bn_workspace_bytes": (_sz, [_i, _i, _i]),

@@ -4,8 +4,10 @@
 namespace tsc {
 int osconv_simt(int direction, const void* x, int dtype, const void* w, const float* bias, float* y, int B, int L, int Cin,
                 int Cout, int Kmax, const int* s_of_tap, cudaStream_t cs);
-int osconv_tc(int direction, const void* x, int dtype, const void* w, const float* bias, float* y, int B, int L, int Cin,
-              int Cout, int Kmax, const int* s_of_tap, cudaStream_t cs);
+int osconv_tc(int direction, const void* x, int dtype, const void* w, const void* plan, const float* bias, float* y,
+              const tsc_conv_epilogue* epi, int B, int L, int Cin, int Cout, int Kmax, const int* s_of_tap, cudaStream_t cs);
+size_t osconv_plan_bytes(int direction, int Cin, int Cout, int Kmax, const int* s_of_tap);
+int osconv_plan_build(int direction, int Cin, int Cout, int Kmax, const int* s_of_tap, void* host_plan);
 int oswgrad_simt(const void* dy, const void* x, int dtype, float* dW, void* workspace, int B, int L, int Cin, int Cout,
                  int Kmax, const int* s_of_tap, cudaStream_t cs);
 int oswgrad_tc(const void* dy, const void* x, int dtype, float* dW, void* workspace, int B, int L, int Cin, int Cout,
@@ -20,16 +22,31 @@ void set_conv_timeline(long long* dev);
 
 extern "C" {
 
-int tsc_osconv(int engine, int direction, const void* x, int dtype, const void* w, const float* bias, float* y, int B,
-               int L, int Cin, int Cout, int Kmax, const int* s_of_tap, tsc_stream_t stream) {
+size_t tsc_osconv_plan_bytes(int direction, int Cin, int Cout, int Kmax, const int* s_of_tap) {
+    return tsc::osconv_plan_bytes(direction, Cin, Cout, Kmax, s_of_tap);
+}
+
+int tsc_osconv_plan_build(int direction, int Cin, int Cout, int Kmax, const int* s_of_tap, void* host_plan) {
+    using namespace tsc;
+    TSC_REQUIRE(host_plan && s_of_tap, "NULL argument");
+    return osconv_plan_build(direction, Cin, Cout, Kmax, s_of_tap, host_plan);
+}
+
+int tsc_osconv(int engine, int direction, const void* x, int dtype, const void* w, const void* plan, const float* bias,
+               float* y, const tsc_conv_epilogue* epilogue, int B, int L, int Cin, int Cout, int Kmax,
+               const int* s_of_tap, tsc_stream_t stream) {
     using namespace tsc;
     TSC_REQUIRE(x && w && y, "NULL tensor");
     TSC_REQUIRE(B > 0 && L > 0, "bad shape B=%d L=%d", B, L);
     TSC_REQUIRE(dtype == TSC_F32 || dtype == TSC_BF16, "bad dtype %d", dtype);
-    if (engine == TSC_ENGINE_SIMT)
+    if (engine == TSC_ENGINE_SIMT) {
+        TSC_REQUIRE(!epilogue || (!epilogue->stat_partial && !epilogue->red_partial),
+                    "fused epilogues exist on the tcgen05 engine only");
         return osconv_simt(direction, x, dtype, w, bias, y, B, L, Cin, Cout, Kmax, s_of_tap, (cudaStream_t)stream);
+    }
     if (engine == TSC_ENGINE_TCGEN05)
-        return osconv_tc(direction, x, dtype, w, bias, y, B, L, Cin, Cout, Kmax, s_of_tap, (cudaStream_t)stream);
+        return osconv_tc(direction, x, dtype, w, plan, bias, y, epilogue, B, L, Cin, Cout, Kmax, s_of_tap,
+                         (cudaStream_t)stream);
     TSC_REQUIRE(false, "bad engine %d", engine);
 }
 

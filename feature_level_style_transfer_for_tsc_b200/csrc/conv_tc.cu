@@ -4,56 +4,131 @@
 //   output channels (<= 256) -> MMA N   (the whole channel axis is one accumulator tile in TMEM)
 //   (tap, input channel)     -> MMA K   (16 channels per instruction)
 //
-// * The activation tile with its halo, [kc][128 + Kmax - 1 rows][8 ch] bf16, is staged ONCE per CTA by
-//   TMA from the c8 tensor (4-D tensor map, out-of-bounds rows zero-filled = ConstantPad1d,
+// * The activation tile with its halo, [kc][128 + Kmax - 1 rows][8 ch] bf16, is staged ONCE per CTA by one
+//   TMA load from the c8 tensor (4-D tensor map, out-of-bounds rows zero-filled = ConstantPad1d,
 //   OS_CNN.py:59,70).  In the SWIZZLE_NONE canonical layout a convolution tap is just "+ t rows" on the
 //   A-operand descriptor's start address, so all Kmax taps reuse the same shared-memory tile.
 // * The packed kernel bank streams through a ring of shared-memory stages with 1-D bulk copies; only
 //   live (channel, tap) pairs exist in HBM, and each tap issues MMAs over its live channel suffix only
 //   (N = np - n_lo[t], written at TMEM column n_lo[t]) -- the 43 %-dense bank costs 43 % of the FLOPs.
+// * The whole issue sequence is a precomputed PLAN (tsc_osconv_plan_build, host, once per bank geometry):
+//   one 16 B entry per MMA (A offset, B offset + leading-dimension field, instruction descriptor, TMEM
+//   column, stage flags) and one 8 B entry per weight stage.  A stage spans several taps (up to 32 KB), so the
+//   issuing thread pays one mbarrier wait and one commit per ~10-40 MMAs and otherwise only adds two
+//   integers per instruction (measured before the plan: ~745 cycles per tap of which <= 120 were tensor work,
+//   profiles/r1_conv_timeline.md).
 // * Warp roles: warp 0 = copy producer, warp 1 = MMA issuer (one elected thread) + TMEM owner,
-//   warps 2-5 = epilogue (TMEM -> registers -> +bias -> coalesced c8 fp32 stores).
-// Replaces ConstantPad1d + Conv1d (+ cuDNN dgrad), OS_CNN/OS_CNN.py:70-71; arithmetic SURVEY A1.
+//   warps 2-5 = epilogue: tcgen05.ld (32 columns at a time) -> +bias (staged in shared memory) -> coalesced
+//   c8 fp32 stores; optionally the per-CTA BatchNorm partial statistics (forward) or the ReLU mask of the
+//   layer below plus the partial sums of its BatchNorm backward (dgrad), reduced over the 32 rows of a warp
+//   with a transposing butterfly (31 shuffles per 32 columns).
+// Replaces ConstantPad1d + Conv1d (+ cuDNN dgrad), OS_CNN/OS_CNN.py:70-71; arithmetic SURVEY A1/A2.
 #include "tc_common.cuh"
+#include <string.h>
+#include <vector>
 
 namespace tsc {
 namespace tc {
 
+static constexpr int TC_THREADS = 192;
+static constexpr int PLAN_STAGE_BYTES = 32 * 1024;
+static constexpr int STAGE_SLOT_BYTES = PLAN_STAGE_BYTES + 512;   // + a zero block: the B operand of padding MMAs
+static constexpr int MMA_GROUP = 4;                               // MMAs issued per elect block
+static constexpr uint32_t PF_FIRST = 1u << 16, PF_LAST = 1u << 17;
+static constexpr int SMEM_HDR = 256;                       // barriers + tmem slot
+
 struct ConvTcParams {
     const __nv_bfloat16* w;
+    const uint8_t* plan;
     const float* bias;
     float* y;
+    // fused epilogues (all nullable)
+    float* stat_partial;       // FWD : [n_cta][np] float2 (mean, M2) over the CTA's valid rows
+    const float* mask_y;       // DGRAD: pre-BN output of the layer below, c8 fp32 [B][np/8][L][8]
+    const float* mask_scale;   //        z = scale*y + shift; d = dz * [z > 0]   (NULL = no ReLU)
+    const float* mask_shift;
+    const float* mask_mean;    //        yhat = (y - mean) * invstd
+    const float* mask_invstd;
+    float* red_partial;        // DGRAD: [n_cta][np] float2 (S1, S2) partial sums over the CTA's valid rows
     int nbias, B, L, ltiles;
+    int np;
     int Rp;            // halo rows in shared memory (multiple of 8)
-    int KB;            // input-channel chunks per weight stage (even)
+    int kc;
+    int pad_left;
     int NS;            // weight stages
-    int stage_bytes;
-    int xs_bytes;
+    int plan_bytes;
+    int n_stages, n_mma;
+    int off_bias, off_wstat, off_plan, off_xs, off_stages;
     int tmem_cols;
     long long* tl;     // optional phase timeline of CTA 0 (tsc_debug_set_timeline), NULL in production
 };
 
 #define TL(i) do { if (p.tl && blockIdx.x == 0) p.tl[i] = clock64(); } while (0)
-#define TLS(n, k) do { if (p.tl && blockIdx.x == 0 && (n) < 48) p.tl[8 + 8 * (n) + (k)] = clock64(); } while (0)
 
-static constexpr int TC_THREADS = 192;
-static constexpr int SMEM_TAPINFO = 256;  // per-tap issue constants, TSC_MAX_TAPS x 16 B
-static constexpr int SMEM_HDR = 256 + TSC_MAX_TAPS * 16;     // barriers + tmem slot + tap info
+// 32 lanes x 32 bit, 32 consecutive columns
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+// Column sums over the 32 lanes of a warp for 32 columns held one per register: a transposing butterfly.
+// On return lane j holds the sum over all lanes of v[j] (31 shuffles instead of 160).
+__device__ __forceinline__ float warp_colsum32(float* v, int lane) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int j = 0; j < o; ++j) {
+            const float send = up ? v[j] : v[j + o];
+            const float keep = up ? v[j + o] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    return v[0];
+}
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ TapTable tt, const ConvTcParams p) {
+osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const ConvTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);            // [8]
     uint64_t* empty = full + 8;                                    // [8]
     uint64_t* x_full = empty + 8;
     uint64_t* acc_full = x_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
-    uint8_t* xs = smem + SMEM_HDR;
-    uint8_t* stages = xs + p.xs_bytes;
+    uint64_t* plan_full = acc_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(plan_full + 1);
+    float* bias_s = reinterpret_cast<float*>(smem + p.off_bias);
+    float2* wstat = reinterpret_cast<float2*>(smem + p.off_wstat);  // [4][np]
+    const uint8_t* plan_s = smem + p.off_plan;
+    uint8_t* xs = smem + p.off_xs;
+    uint8_t* stages = smem + p.off_stages;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x / p.ltiles, l0 = (blockIdx.x % p.ltiles) * 128;
-    const int np = tt.np, kc = tt.kc;
+    const int np = p.np;
 
     if (warp == 0 && lane == 0) {
         TL(0);
@@ -61,128 +136,222 @@ osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         for (int i = 0; i < p.NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(x_full, 1);
         mbar_init(acc_full, 1);
+        mbar_init(plan_full, 1);
         fence_barrier_init();
+        mbar_arrive_expect_tx(plan_full, (uint32_t)p.plan_bytes);
+        bulk_load(smem + p.off_plan, p.plan, (uint32_t)p.plan_bytes, plan_full);
+        mbar_arrive_expect_tx(x_full, (uint32_t)(p.kc * p.Rp * 16));
+        tma_load_4d(xs, &xmap, 0, l0 - p.pad_left, 0, b, x_full);
     }
     if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    if (warp >= 2) {
+        // zero block at the end of every stage slot (read by the padding MMAs that round a stage up to MMA_GROUP)
+        for (int i = threadIdx.x - 64; i < p.NS * 32; i += 128)
+            *reinterpret_cast<uint4*>(stages + (size_t)(i >> 5) * STAGE_SLOT_BYTES + PLAN_STAGE_BYTES + (i & 31) * 16) =
+                make_uint4(0u, 0u, 0u, 0u);
+        fence_proxy_async();
+        // per-channel epilogue constants -> shared memory: [0] bias | mask scale, [1] mask shift, [2] mean, [3] invstd
+        for (int c = threadIdx.x - 64; c < np; c += 128) {
+            if (p.red_partial) {
+                bias_s[c] = p.mask_scale ? __ldg(p.mask_scale + c) : 0.f;        // no ReLU below: z = 0*y + 1 > 0
+                bias_s[np + c] = p.mask_scale ? __ldg(p.mask_shift + c) : 1.f;
+                bias_s[2 * np + c] = __ldg(p.mask_mean + c);
+                bias_s[3 * np + c] = __ldg(p.mask_invstd + c);
+            } else {
+                bias_s[c] = (p.bias && c < p.nbias) ? __ldg(p.bias + c) : 0.f;
+            }
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===== copy producer =====
+        // ===== copy producer: one bulk copy per plan stage =====
         if (lane == 0) {
             bool dead = false;
             TL(1);
-            mbar_arrive_expect_tx(x_full, (uint32_t)(kc * p.Rp * 16));
-            for (int kcI = 0; kcI < kc; ++kcI)
-                tma_load_4d(xs + (size_t)kcI * p.Rp * 16, &xmap, 0, l0 - tt.pad_left, kcI, b, x_full);
+            mbar_wait(plan_full, 0, dead, 8);
+            const uint2* st = reinterpret_cast<const uint2*>(plan_s + 16);
             uint32_t s = 0, ph = 0;
-            int sn = 0;
-            for (int oi = 0; oi < tt.n_order; ++oi) {
-                const int t = tt.order[oi];
-                const int nt = np - tt.n_lo[t], kspan = kc - tt.kc_lo[t];
-                const __nv_bfloat16* blob = p.w + (size_t)tt.w_off[t] * 8;
-                for (int g0 = 0; g0 < kspan; g0 += p.KB) {
-                    TLS(sn, 4);
-                    mbar_wait(&empty[s], ph ^ 1u, dead, 1);
-                    TLS(sn, 5);
-                    const int nch = min(p.KB, kspan - g0);
-                    const uint32_t bytes = (uint32_t)(nch * nt * 16);
-                    mbar_arrive_expect_tx(&full[s], bytes);
-                    bulk_load(stages + (size_t)s * p.stage_bytes, blob + (size_t)g0 * nt * 8, bytes, &full[s]);
-                    TLS(sn, 6);
-                    ++sn;
-                    if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; }
-                }
+            const int n_stages = p.n_stages;
+            for (int i = 0; i < n_stages; ++i) {
+                const uint2 e = st[i];                        // {source offset in 16 B units, bytes}
+                mbar_wait(&empty[s], ph ^ 1u, dead, 1);
+                mbar_arrive_expect_tx(&full[s], e.y);
+                bulk_load(stages + (size_t)s * STAGE_SLOT_BYTES, reinterpret_cast<const uint8_t*>(p.w) + (size_t)e.x * 16,
+                          e.y, &full[s]);
+                if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        // A tcgen05.mma with M = 128 occupies the tensor pipe for N/2 cycles, but one thread cannot issue faster
-        // than one every ~54 cycles (measured, tools/mma_bench2.cu), so the issue loop is kept lean: per-tap
-        // constants are precomputed by the whole warp into shared memory, descriptors advance by adding to
-        // their low word, and the stage ring is tracked without divisions.
-        uint32_t* tapinfo = reinterpret_cast<uint32_t*>(smem + SMEM_TAPINFO);     // [n_order][4]
-        for (int oi = lane; oi < tt.n_order; oi += 32) {
-            const int t = tt.order[oi];
-            const int n_lo = tt.n_lo[t], kc_lo = tt.kc_lo[t];
-            const int nt = np - n_lo;
-            tapinfo[oi * 4 + 0] = (uint32_t)(kc_lo * p.Rp + t);                    // A row offset (16 B units)
-            tapinfo[oi * 4 + 1] = (uint32_t)nt | ((uint32_t)(kc - kc_lo) << 16);    // N, k span (chunks)
-            tapinfo[oi * 4 + 2] = make_idesc_bf16(128, (uint32_t)nt, false, false, false);
-            tapinfo[oi * 4 + 3] = tmem_base + (uint32_t)n_lo;
+        // ===== MMA issuer: the whole warp walks the plan in lock-step (uniform control flow, entries prefetched one
+        // iteration ahead); one elected lane issues.  Measured (tools/mma_bench3.cu): 73 cycles per MMA against 105-145
+        // for a lane-0-only branch, whose UTCHMMA ptxas wraps in a per-thread ELECT loop. =====
+        bool dead = false;
+        mbar_wait(plan_full, 0, dead, 9);
+        mbar_wait(x_full, 0, dead, 2);
+        __syncwarp();             // lanes leave the polling loops at different times: reconverge before every elect
+        tc_fence_after();
+        if (lane == 0) TL(2);
+        const uint4* mm = reinterpret_cast<const uint4*>(plan_s + 16 + ((p.n_stages * 8 + 15) & ~15));
+        const uint32_t desc_hi = (128u >> 4) | (1u << 14);                        // SBO = 128 B, descriptor version 1
+        const uint32_t a_base16 = (smem_u32(xs) >> 4) | ((uint32_t)p.Rp << 16);    // LBO = Rp * 16 B
+        const uint32_t st_base16 = smem_u32(stages) >> 4;
+        const uint32_t stage16 = (uint32_t)STAGE_SLOT_BYTES >> 4;
+        uint32_t s = 0, ph = 0, b_base16 = st_base16, acc = 0;
+        const int n_grp = p.n_mma / MMA_GROUP;
+        uint4 e0 = mm[0], e1 = mm[1], e2 = mm[2], e3 = mm[3];
+        for (int g = 0; g < n_grp; ++g) {
+            const uint4* nx = mm + (size_t)min(g + 1, n_grp - 1) * MMA_GROUP;
+            const uint4 f0 = nx[0], f1 = nx[1], f2 = nx[2], f3 = nx[3];
+            if (e0.w & PF_FIRST) {
+                mbar_wait(&full[s], ph, dead, 3);
+                __syncwarp();     // lanes leave the polling loop at different times: reconverge before the elect
+                tc_fence_after();
+                if (g == 0 && lane == 0) TL(3);
+            }
+            const bool last = (e3.w & PF_LAST) != 0;
+            if (elect_one()) {
+                umma_bf16(tmem_base + (e0.w & 0xffffu), ((uint64_t)desc_hi << 32) | (a_base16 + e0.x),
+                          ((uint64_t)desc_hi << 32) | (b_base16 + e0.y), e0.z, acc);
+                umma_bf16(tmem_base + (e1.w & 0xffffu), ((uint64_t)desc_hi << 32) | (a_base16 + e1.x),
+                          ((uint64_t)desc_hi << 32) | (b_base16 + e1.y), e1.z, 1u);
+                umma_bf16(tmem_base + (e2.w & 0xffffu), ((uint64_t)desc_hi << 32) | (a_base16 + e2.x),
+                          ((uint64_t)desc_hi << 32) | (b_base16 + e2.y), e2.z, 1u);
+                umma_bf16(tmem_base + (e3.w & 0xffffu), ((uint64_t)desc_hi << 32) | (a_base16 + e3.x),
+                          ((uint64_t)desc_hi << 32) | (b_base16 + e3.y), e3.z, 1u);
+                if (last) tc_commit(&empty[s]);      // frees the stage when these MMAs have read it
+            }
+            acc = 1;
+            if (last) {
+                if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; }
+                b_base16 = st_base16 + s * stage16;
+            }
+            e0 = f0; e1 = f1; e2 = f2; e3 = f3;
         }
         __syncwarp();
-        if (lane == 0) {
-            bool dead = false;
-            mbar_wait(x_full, 0, dead, 2);
-            tc_fence_after();
-            TL(2);
-            const uint32_t desc_hi = (128u >> 4) | (1u << 14);                      // SBO = 128 B, descriptor version 1
-            const uint32_t a_base16 = (smem_u32(xs) >> 4) | ((uint32_t)p.Rp << 16);  // LBO = Rp * 16 B
-            const uint32_t st_base16 = smem_u32(stages) >> 4;
-            const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4;
-            const uint32_t a_step = 2u * (uint32_t)p.Rp;                             // 16 channels = 2 chunks
-            uint32_t s = 0, ph = 0, acc = 0;
-            int sn = 0;
-            const int n_order = tt.n_order, KB = p.KB;
-            for (int oi = 0; oi < n_order; ++oi) {
-                const uint4 ti = *reinterpret_cast<const uint4*>(tapinfo + oi * 4);
-                const uint32_t nt = ti.y & 0xffffu;
-                const int kspan = (int)(ti.y >> 16);
-                const uint32_t b_step = 2u * nt;
-                uint32_t a_lo = a_base16 + ti.x;
-                for (int g0 = 0; g0 < kspan; g0 += KB) {
-                    TLS(sn, 0);
-                    mbar_wait(&full[s], ph, dead, 3);
-                    tc_fence_after();
-                    TLS(sn, 1);
-                    if (oi == 0 && g0 == 0) TL(3);
-                    const int nsteps = min(KB, kspan - g0) >> 1;
-                    uint32_t b_lo = (st_base16 + s * stage16) | (nt << 16);          // LBO = nt * 16 B
-#pragma unroll 5
-                    for (int k = 0; k < nsteps; ++k) {
-                        umma_bf16(ti.w, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, ti.z, acc);
-                        acc = 1;
-                        a_lo += a_step;
-                        b_lo += b_step;
-                    }
-                    TLS(sn, 2);
-                    tc_commit(&empty[s]);      // frees the stage when these MMAs have read it
-                    TLS(sn, 3);
-                    ++sn;
-                    if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; }
-                }
-            }
-            tc_commit(acc_full);
-            TL(4);
-        }
+        if (elect_one()) tc_commit(acc_full);
+        if (lane == 0) TL(4);
     } else {
-        // ===== epilogue: TMEM -> registers -> (+bias) -> c8 fp32 =====
+        // ===== epilogue: TMEM -> registers -> (+bias | mask) -> c8 fp32 (+ per-CTA partial reductions) =====
         bool dead = false;
-        mbar_wait(acc_full, 0, dead, 4);
-        tc_fence_after();
-        if (warp == 2 && lane == 0) TL(5);
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;
         const int l = l0 + row;
+        const bool valid = l < p.L;
         const int npc = np / 8;
-        for (int c0 = 0; c0 < np; c0 += 16) {
-            float v[16];
-            tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            if (p.bias) {
+        const size_t row_off = ((size_t)b * npc * p.L + (size_t)(valid ? l : 0)) * 8;
+        const size_t chunk_stride = (size_t)p.L * 8;
+        float* ybase = p.y + row_off;
+        const bool do_stat = p.stat_partial != nullptr;
+        const bool do_red = p.red_partial != nullptr;
+        const float* mbase = do_red ? p.mask_y + row_off : nullptr;
+        // one thread polls the accumulator barrier; the other 127 sleep in a named barrier instead of spinning on
+        // mbarrier.try_wait next to the MMA issuer
+        if (threadIdx.x == 64) mbar_wait(acc_full, 0, dead, 4);
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        tc_fence_after();
+        if (warp == 2 && lane == 0) TL(5);
+        for (int c0 = 0; c0 < np; c0 += 32) {
+            float v[32];
+            const bool wide = c0 + 32 <= np;          // np is a multiple of 16: the tail chunk is 16 wide
+            if (wide) {
+                tmem_ld_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            } else {
+                tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    if (c0 + i < p.nbias) v[i] += __ldg(p.bias + c0 + i);
+                for (int i = 16; i < 32; ++i) v[i] = 0.f;
             }
-            if (l < p.L) {
-                float* d0 = p.y + (((size_t)b * npc + (c0 >> 3)) * p.L + l) * 8;
-                float* d1 = d0 + (size_t)p.L * 8;
-                *reinterpret_cast<float4*>(d0) = make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<float4*>(d0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                *reinterpret_cast<float4*>(d1) = make_float4(v[8], v[9], v[10], v[11]);
-                *reinterpret_cast<float4*>(d1 + 4) = make_float4(v[12], v[13], v[14], v[15]);
+            const int ng = wide ? 4 : 2;              // 8-channel groups in this chunk
+            if (!do_red) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    if (i < ng * 8) {
+                        const float4 bb = *reinterpret_cast<const float4*>(bias_s + c0 + i);
+                        v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
+                    }
+                }
+            }
+            float yh[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) yh[i] = 0.f;
+            if (do_red) {
+                // d = dz * [scale*y + shift > 0]; yhat = (y - mean) * invstd of the layer below
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    if (g < ng) {
+                        float yv[8];
+                        if (valid) {
+                            const float* src = mbase + (size_t)((c0 >> 3) + g) * chunk_stride;
+                            const float4 a0 = __ldg(reinterpret_cast<const float4*>(src));
+                            const float4 a1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+                            yv[0] = a0.x; yv[1] = a0.y; yv[2] = a0.z; yv[3] = a0.w; yv[4] = a1.x; yv[5] = a1.y; yv[6] = a1.z; yv[7] = a1.w;
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) yv[j] = 0.f;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int c = c0 + g * 8 + j;
+                            const float z = fmaf(yv[j], bias_s[c], bias_s[np + c]);
+                            if (!(z > 0.f)) v[g * 8 + j] = 0.f;
+                            yh[g * 8 + j] = (yv[j] - bias_s[2 * np + c]) * bias_s[3 * np + c];
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) yh[g * 8 + j] = 0.f;
+                    }
+                }
+            }
+            if (valid) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    if (g < ng) {
+                        float* d0 = ybase + (size_t)((c0 >> 3) + g) * chunk_stride;
+                        *reinterpret_cast<float4*>(d0) = make_float4(v[g * 8], v[g * 8 + 1], v[g * 8 + 2], v[g * 8 + 3]);
+                        *reinterpret_cast<float4*>(d0 + 4) = make_float4(v[g * 8 + 4], v[g * 8 + 5], v[g * 8 + 6], v[g * 8 + 7]);
+                    }
+                }
+            }
+            if (do_stat || do_red) {
+                float s1[32], s2[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float x = valid ? v[i] : 0.f;
+                    s1[i] = x;
+                    s2[i] = do_red ? x * yh[i] : x * x;
+                }
+                const float a = warp_colsum32(s1, lane);
+                const float c = warp_colsum32(s2, lane);
+                if (c0 + lane < np) wstat[q * np + c0 + lane] = make_float2(a, c);
+            }
+        }
+        if (do_stat || do_red) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");             // the four epilogue warps
+            const int rows_cta = min(128, p.L - l0);
+            for (int c = threadIdx.x - 64; c < np; c += 128) {
+                if (do_red) {
+                    float a = 0.f, d = 0.f;
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) { const float2 t = wstat[w * np + c]; a += t.x; d += t.y; }
+                    reinterpret_cast<float2*>(p.red_partial)[(size_t)blockIdx.x * np + c] = make_float2(a, d);
+                } else {
+                    // per-warp (n, sum, sumsq) -> (mean, M2), then Chan merges of the four warps
+                    float n = 0.f, mean = 0.f, m2 = 0.f;
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        const int nw = max(0, min(32, rows_cta - w * 32));
+                        if (nw > 0) {
+                            const float2 t = wstat[w * np + c];
+                            const float mw = t.x / (float)nw;
+                            const float qw = fmaxf(t.y - t.x * mw, 0.f);
+                            welford_merge(n, mean, m2, (float)nw, mw, qw);
+                        }
+                    }
+                    reinterpret_cast<float2*>(p.stat_partial)[(size_t)blockIdx.x * np + c] = make_float2(mean, m2);
+                }
             }
         }
         if (warp == 2 && lane == 0) TL(6);
@@ -205,15 +374,16 @@ EncodeTiledFn get_encode_tiled() {
     return fn;
 }
 
-// c8 bf16 tensor [B][kc][L][8] as a 4-D tensor map with a (8, rows, 1, 1) box, no swizzle, zero OOB fill.
-int make_c8_map(CUtensorMap* map, const void* base, int B, int kc, int L, int box_rows) {
+// c8 bf16 tensor [B][kc][L][8] as a 4-D tensor map with a (8, rows, chunks, 1) box, no swizzle, zero OOB fill.
+int make_c8_map(CUtensorMap* map, const void* base, int B, int kc, int L, int box_rows, int box_chunks) {
     EncodeTiledFn enc = get_encode_tiled();
     TSC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
     TSC_REQUIRE(((uintptr_t)base & 15) == 0, "c8 tensor must be 16-byte aligned");
     TSC_REQUIRE(box_rows >= 1 && box_rows <= 256, "TMA box rows %d outside [1,256]", box_rows);
+    TSC_REQUIRE(box_chunks >= 1 && box_chunks <= 256, "TMA box chunks %d outside [1,256]", box_chunks);
     cuuint64_t dims[4] = {8, (cuuint64_t)L, (cuuint64_t)kc, (cuuint64_t)B};
     cuuint64_t strides[3] = {16, (cuuint64_t)L * 16, (cuuint64_t)kc * L * 16};
-    cuuint32_t box[4] = {8, (cuuint32_t)box_rows, 1, 1};
+    cuuint32_t box[4] = {8, (cuuint32_t)box_rows, (cuuint32_t)box_chunks, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -225,45 +395,147 @@ int make_c8_map(CUtensorMap* map, const void* base, int B, int kc, int L, int bo
 static constexpr int SMEM_CAP = 227 * 1024;
 static long long* g_timeline = nullptr;     // debug only: device buffer of >= 8 clock64 samples
 
+static inline int conv_rp(int Kmax) { return (128 + Kmax - 1 + 7) & ~7; }
+
+// ---- the plan: header (16 B) | stage table (8 B each, padded to 16) | MMA table (16 B each) ----------
+struct PlanHost {
+    std::vector<uint2> stages;
+    std::vector<uint4> mmas;
+};
+
+// A stage ends: pad its MMA list to a multiple of MMA_GROUP with instructions that add zero (N = 16, B = the zero
+// block behind the stage slot, A = the tile base) and flag the last one.
+static void close_stage(PlanHost* ph, uint32_t src16, uint32_t bytes) {
+    ph->stages.push_back(make_uint2(src16, bytes));
+    while (ph->mmas.size() % MMA_GROUP != 0) {
+        uint4 e;
+        e.x = 0;
+        e.y = ((uint32_t)PLAN_STAGE_BYTES >> 4) | (16u << 16);     // LBO = 16 rows * 16 B
+        e.z = (1u << 4) | (1u << 7) | (1u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+        e.w = 0;
+        ph->mmas.push_back(e);
+    }
+    ph->mmas.back().w |= PF_LAST;
+}
+
+static int build_plan(int direction, int Cin, int Cout, int Kmax, const int* s_of_tap, PlanHost* ph) {
+    TapTable tt;
+    if (build_tap_table(direction, Cin, Cout, Kmax, s_of_tap, &tt) != 0) return -1;
+    const int Rp = conv_rp(Kmax);
+    uint32_t stage_src16 = 0, stage_bytes = 0;
+    bool open = false;
+    for (int oi = 0; oi < tt.n_order; ++oi) {
+        const int t = tt.order[oi];
+        const int n_lo = tt.n_lo[t], kc_lo = tt.kc_lo[t];
+        const int nt = tt.np - n_lo, kspan = tt.kc - kc_lo;
+        // = make_idesc_bf16(128, nt, K-major, K-major): F32 accumulate, BF16 x BF16
+        const uint32_t idesc_host = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nt >> 3) << 17) | ((128u >> 4) << 24);
+        for (int kp = 0; kp < kspan / 2; ++kp) {
+            const uint32_t unit_bytes = (uint32_t)(2 * nt * 16);
+            const uint32_t unit_src16 = (uint32_t)tt.w_off[t] + (uint32_t)(2 * kp * nt);
+            if (open && stage_bytes + unit_bytes > (uint32_t)PLAN_STAGE_BYTES) {
+                close_stage(ph, stage_src16, stage_bytes);
+                open = false;
+            }
+            uint32_t flags = 0;
+            if (!open) { stage_src16 = unit_src16; stage_bytes = 0; open = true; flags |= PF_FIRST; }
+            uint4 e;
+            e.x = (uint32_t)((kc_lo + 2 * kp) * Rp + t);               // A start, 16 B units from the tile base
+            e.y = (stage_bytes >> 4) | ((uint32_t)nt << 16);           // B start within the stage | LBO = nt * 16 B
+            e.z = idesc_host;
+            e.w = (uint32_t)n_lo | flags;
+            ph->mmas.push_back(e);
+            stage_bytes += unit_bytes;
+        }
+    }
+    TSC_REQUIRE(open && !ph->mmas.empty(), "kernel bank has no live tap");
+    close_stage(ph, stage_src16, stage_bytes);
+    return 0;
+}
+
+static inline size_t plan_bytes_of(const PlanHost& ph) {
+    return 16 + ((ph.stages.size() * 8 + 15) & ~(size_t)15) + ph.mmas.size() * 16;
+}
+
 }  // namespace tc
 
 void set_conv_timeline(long long* dev) { tc::g_timeline = dev; }
 
-int osconv_tc(int direction, const void* x, int dtype, const void* w, const float* bias, float* y, int B, int L, int Cin,
-              int Cout, int Kmax, const int* s_of_tap, cudaStream_t cs) {
+size_t osconv_plan_bytes(int direction, int Cin, int Cout, int Kmax, const int* s_of_tap) {
+    tc::PlanHost ph;
+    if (tc::build_plan(direction, Cin, Cout, Kmax, s_of_tap, &ph) != 0) return 0;
+    return tc::plan_bytes_of(ph);
+}
+
+int osconv_plan_build(int direction, int Cin, int Cout, int Kmax, const int* s_of_tap, void* host_plan) {
+    tc::PlanHost ph;
+    if (tc::build_plan(direction, Cin, Cout, Kmax, s_of_tap, &ph) != 0) return -1;
+    uint8_t* o = (uint8_t*)host_plan;
+    memset(o, 0, tc::plan_bytes_of(ph));
+    int hdr[4] = {(int)ph.mmas.size(), (int)ph.stages.size(), tc::PLAN_STAGE_BYTES, 0x504c414e};
+    memcpy(o, hdr, 16);
+    memcpy(o + 16, ph.stages.data(), ph.stages.size() * 8);
+    memcpy(o + 16 + ((ph.stages.size() * 8 + 15) & ~(size_t)15), ph.mmas.data(), ph.mmas.size() * 16);
+    return 0;
+}
+
+int osconv_tc(int direction, const void* x, int dtype, const void* w, const void* plan, const float* bias, float* y,
+              const tsc_conv_epilogue* epi, int B, int L, int Cin, int Cout, int Kmax, const int* s_of_tap, cudaStream_t cs) {
     using namespace tc;
     TSC_REQUIRE(dtype == TSC_BF16, "the tcgen05 engine takes bf16 operands");
-    TapTable tt;
-    if (build_tap_table(direction, Cin, Cout, Kmax, s_of_tap, &tt) != 0) return -1;
+    TSC_REQUIRE(plan != nullptr, "the tcgen05 engine needs the device copy of tsc_osconv_plan_build()'s plan");
+    // geometry only (the schedule itself was built once by osconv_plan_build and lives on the device)
+    PlanHost ph;
+    if (build_plan(direction, Cin, Cout, Kmax, s_of_tap, &ph) != 0) return -1;
+    const bool fwd = direction == TSC_DIR_FWD;
     ConvTcParams p;
+    memset(&p, 0, sizeof(p));
     p.w = (const __nv_bfloat16*)w;
-    p.bias = direction == TSC_DIR_FWD ? bias : nullptr;
-    p.nbias = direction == TSC_DIR_FWD ? Cout : 0;
+    p.plan = (const uint8_t*)plan;
+    p.bias = fwd ? bias : nullptr;
+    p.nbias = fwd ? Cout : 0;
     p.y = y;
+    if (epi) {
+        if (fwd) {
+            p.stat_partial = epi->stat_partial;
+        } else if (epi->red_partial) {
+            TSC_REQUIRE(epi->mask_y && epi->mask_mean && epi->mask_invstd, "dgrad reduction needs mask_y, mask_mean, mask_invstd");
+            TSC_REQUIRE(!epi->mask_scale || epi->mask_shift, "mask_scale needs mask_shift");
+            p.mask_y = epi->mask_y; p.mask_scale = epi->mask_scale; p.mask_shift = epi->mask_shift;
+            p.mask_mean = epi->mask_mean; p.mask_invstd = epi->mask_invstd; p.red_partial = epi->red_partial;
+        }
+    }
     p.B = B; p.L = L; p.ltiles = cdiv(L, 128);
-    p.Rp = (128 + Kmax - 1 + 7) & ~7;
-    p.xs_bytes = tt.kc * p.Rp * 16;
-    int kb = (40 * 1024 / (tt.np * 16)) & ~1;
-    if (kb > tt.kc) kb = tt.kc;
-    if (kb < 2) kb = 2;
-    p.KB = kb;
-    p.stage_bytes = kb * tt.np * 16;
-    int ns = (SMEM_CAP - SMEM_HDR - p.xs_bytes) / p.stage_bytes;
+    p.np = fwd ? pad16(Cout) : pad16(Cin);
+    p.kc = fwd ? pad16(Cin) / 8 : pad16(Cout) / 8;
+    p.pad_left = fwd ? (Kmax - 1) / 2 : Kmax / 2;
+    p.Rp = conv_rp(Kmax);
+    p.n_stages = (int)ph.stages.size();
+    p.n_mma = (int)ph.mmas.size();
+    p.plan_bytes = (int)plan_bytes_of(ph);
+    p.off_bias = SMEM_HDR;
+    p.off_wstat = p.off_bias + 4 * p.np * 4;
+    p.off_plan = (p.off_wstat + 4 * p.np * 8 + 15) & ~15;
+    p.off_xs = (p.off_plan + p.plan_bytes + 127) & ~127;
+    p.off_stages = (p.off_xs + p.kc * p.Rp * 16 + 127) & ~127;
+    int ns = (SMEM_CAP - p.off_stages) / STAGE_SLOT_BYTES;
     if (ns > 8) ns = 8;
-    TSC_REQUIRE(ns >= 2, "shape needs %d B of shared memory for the activation tile: unsupported", p.xs_bytes);
+    if (ns > p.n_stages) ns = p.n_stages;
+    TSC_REQUIRE(ns >= 1 && (ns >= 2 || p.n_stages == 1), "shape needs %d B of shared memory before the weight stages: unsupported",
+                p.off_stages);
     p.NS = ns;
     p.tl = g_timeline;
-    p.tmem_cols = tt.np <= 32 ? 32 : tt.np <= 64 ? 64 : tt.np <= 128 ? 128 : 256;
+    p.tmem_cols = p.np <= 32 ? 32 : p.np <= 64 ? 64 : p.np <= 128 ? 128 : 256;
     CUtensorMap xmap;
-    if (make_c8_map(&xmap, x, B, tt.kc, L, p.Rp) != 0) return -1;
-    const int smem = SMEM_HDR + p.xs_bytes + ns * p.stage_bytes;
+    if (make_c8_map(&xmap, x, B, p.kc, L, p.Rp, p.kc) != 0) return -1;
+    const int smem = p.off_stages + ns * STAGE_SLOT_BYTES;
     static bool attr_set = false;          // once per process: opt in to the full 227 KB of dynamic shared memory
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(osconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         attr_set = true;
     }
-    osconv_tc_kernel<<<B * p.ltiles, TC_THREADS, smem, cs>>>(xmap, tt, p);
+    osconv_tc_kernel<<<B * p.ltiles, TC_THREADS, smem, cs>>>(xmap, p);
     TSC_LAUNCH_CHECK();
     return 0;
 }

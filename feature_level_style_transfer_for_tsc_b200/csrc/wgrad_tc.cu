@@ -158,7 +158,7 @@ oswgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_consta
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-int make_c8_map(CUtensorMap* map, const void* base, int B, int kc, int L, int box_rows);   // conv_tc.cu
+int make_c8_map(CUtensorMap* map, const void* base, int B, int kc, int L, int box_rows, int box_chunks);   // conv_tc.cu
 
 }  // namespace tc
 
@@ -219,8 +219,8 @@ int oswgrad_tc(const void* dy, const void* x, int dtype, float* dW, void* worksp
     const int smem = WG_HDR + WG_STAGES * p.stage_bytes;
     TSC_REQUIRE(smem <= 227 * 1024, "wgrad shape needs %d B of shared memory: unsupported", smem);
     CUtensorMap dymap, xmap;
-    if (make_c8_map(&dymap, dy, B, np / 8, L, WG_LT) != 0) return -1;
-    if (make_c8_map(&xmap, x, B, p.kcx, L, p.RX) != 0) return -1;
+    if (make_c8_map(&dymap, dy, B, np / 8, L, WG_LT, 1) != 0) return -1;
+    if (make_c8_map(&xmap, x, B, p.kcx, L, p.RX, 1) != 0) return -1;
     static bool attr_set = false;          // once per process: opt in to the full 227 KB of dynamic shared memory
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(oswgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

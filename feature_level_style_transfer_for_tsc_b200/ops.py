@@ -100,6 +100,7 @@ class BankGeometry:
         self.s_arr = L.int_array(self.s_of_tap)
         self.pad_l, self.pad_r = (self.kmax - 1) // 2, self.kmax // 2
         self._packed_bytes = {}
+        self._plans = {}
 
     def packed_bytes(self, direction: int, dt: int) -> int:
         key = (direction, dt)
@@ -109,6 +110,20 @@ class BankGeometry:
                 raise RuntimeError("tsc_packed_weight_bytes failed: " + L.load().tsc_last_error().decode())
             self._packed_bytes[key] = int(n)
         return self._packed_bytes[key]
+
+    def plan(self, direction: int, device) -> torch.Tensor:
+        """Device copy of the tcgen05 issue schedule of this bank (built once per geometry, direction and device)."""
+        key = (direction, str(device))
+        if key not in self._plans:
+            lib = L.load()
+            n = int(lib.tsc_osconv_plan_bytes(direction, self.cin, self.cout, self.kmax, self.s_arr))
+            if n == 0:
+                raise RuntimeError("tsc_osconv_plan_bytes failed: " + lib.tsc_last_error().decode())
+            host = torch.empty(n, dtype=torch.uint8)
+            L.check(lib.tsc_osconv_plan_build(direction, self.cin, self.cout, self.kmax, self.s_arr,
+                                              ctypes.c_void_p(host.data_ptr())), "tsc_osconv_plan_build")
+            self._plans[key] = host.to(device)
+        return self._plans[key]
 
     def live_macs_per_position(self) -> int:
         return self.cin * sum(h - l for l, h in zip(self.lo, self.hi))
@@ -201,8 +216,15 @@ def rmsprop_step(params: torch.Tensor, grads: torch.Tensor, square_avg: torch.Te
                                       float(alpha), float(eps), float(grad_scale), _stream()), "tsc_rmsprop_step")
 
 
+def n_conv_ctas(B: int, Ln: int) -> int:
+    """CTAs (= rows of the fused-epilogue partial buffers) of one tcgen05 conv launch."""
+    return B * ((Ln + 127) // 128)
+
+
 def osconv(engine: int, direction: int, g: BankGeometry, x8: torch.Tensor, w_packed: torch.Tensor,
-           bias: Optional[torch.Tensor]) -> torch.Tensor:
+           bias: Optional[torch.Tensor], stat_partial: Optional[torch.Tensor] = None, mask=None,
+           red_partial: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """mask = (y_c8, scale|None, shift|None, mean, invstd) of the layer below (dgrad with red_partial only)."""
     dt = L.TSC_BF16 if x8.dtype == torch.bfloat16 else L.TSC_F32
     _req(x8, torch_dtype(dt), "x_c8")
     _req(w_packed, torch_dtype(dt), "w_packed")
@@ -214,7 +236,20 @@ def osconv(engine: int, direction: int, g: BankGeometry, x8: torch.Tensor, w_pac
     if bias is not None:
         _req(bias, name="bias")
     y = torch.empty((B, cout_side // 8, Ln, 8), device=x8.device, dtype=torch.float32)
-    L.check(L.load().tsc_osconv(engine, direction, _ptr(x8), dt, _ptr(w_packed), _ptr(bias), _ptr(y), B, Ln,
+    plan = g.plan(direction, x8.device) if engine == L.ENGINE_TCGEN05 else None
+    epi = None
+    if stat_partial is not None or red_partial is not None:
+        epi = L.ConvEpilogue()
+        if stat_partial is not None:
+            epi.stat_partial = stat_partial.data_ptr()
+        if red_partial is not None:
+            my, msc, msh, mmean, minv = mask
+            epi.mask_y, epi.mask_mean, epi.mask_invstd = my.data_ptr(), mmean.data_ptr(), minv.data_ptr()
+            if msc is not None:
+                epi.mask_scale, epi.mask_shift = msc.data_ptr(), msh.data_ptr()
+            epi.red_partial = red_partial.data_ptr()
+    L.check(L.load().tsc_osconv(engine, direction, _ptr(x8), dt, _ptr(w_packed), _ptr(plan), _ptr(bias), _ptr(y),
+                                ctypes.byref(epi) if epi is not None else None, B, Ln,
                                 g.cin, g.cout, g.kmax, g.s_arr, _stream()), "tsc_osconv")
     return y
 

@@ -77,9 +77,35 @@ int tsc_pack_weights_pair(int dtype, float* W, void* packed_fwd, void* packed_dg
  * (OS_CNN.py:70-71, 163-164) and their cuDNN/oneDNN dgrad -------------------------------------
  * FWD  : x = X  [B, Cin, L] c8(dtype), y = Y  [B, Cout, L] c8 fp32, bias[Cout] or NULL.
  * DGRAD: x = dY [B, Cout, L] c8(dtype), y = dX [B, Cin, L] c8 fp32, bias ignored.
- * Zero padding (pad_left=(Kmax-1)/2, pad_right=Kmax/2, OS_CNN.py:59) is implicit. */
-int tsc_osconv(int engine, int direction, const void* x_c8, int dtype, const void* w_packed, const float* bias,
-               float* y_c8, int B, int L, int Cin, int Cout, int Kmax, const int* s_of_tap, tsc_stream_t stream);
+ * Zero padding (pad_left=(Kmax-1)/2, pad_right=Kmax/2, OS_CNN.py:59) is implicit.
+ *
+ * plan (tcgen05 engine only, NULL for SIMT): the issue schedule of the bank -- one entry per tensor-core
+ * instruction and per weight stage.  It depends on the bank geometry only: build it ONCE on the host with
+ * tsc_osconv_plan_build into a HOST buffer of tsc_osconv_plan_bytes bytes, copy it to device memory (16 B
+ * aligned) and pass that device pointer to every call.
+ *
+ * epilogue (tcgen05 engine only, may be NULL): reductions fused into the accumulator read-out, each written as
+ * one float2 per (CTA, padded channel), n_cta = B * ceil(L/128), CTA i covering rows [128*(i % ceil(L/128)), +128)
+ * of sample i / ceil(L/128):
+ *   FWD   stat_partial [n_cta][Cout_p][2] = (mean, M2) of y over the CTA's valid rows  -> BatchNorm statistics
+ *         (tsc_bn_apply_fused merges them; replaces a separate pass over y).
+ *   DGRAD red_partial  [n_cta][Cin_p][2]  = (S1, S2): the layer below is z = act(BN(mask_y)); the written dX is
+ *         already d = dX * [mask_scale*mask_y + mask_shift > 0] (mask_scale NULL = no ReLU), and S1 = sum d,
+ *         S2 = sum d * (mask_y - mask_mean) * mask_invstd over the CTA's rows -> tsc_bn_bwd_apply_fused. */
+typedef struct tsc_conv_epilogue {
+    float* stat_partial;
+    const float* mask_y;
+    const float* mask_scale;
+    const float* mask_shift;
+    const float* mask_mean;
+    const float* mask_invstd;
+    float* red_partial;
+} tsc_conv_epilogue;
+size_t tsc_osconv_plan_bytes(int direction, int Cin, int Cout, int Kmax, const int* s_of_tap);
+int tsc_osconv_plan_build(int direction, int Cin, int Cout, int Kmax, const int* s_of_tap, void* host_plan);
+int tsc_osconv(int engine, int direction, const void* x_c8, int dtype, const void* w_packed, const void* plan,
+               const float* bias, float* y_c8, const tsc_conv_epilogue* epilogue, int B, int L, int Cin, int Cout,
+               int Kmax, const int* s_of_tap, tsc_stream_t stream);
 
 /* ---- weight gradient on live taps only (masked taps get exact zeros) ---------------
  * dW[co,ci,t] = sum_{b,l} dY[b,co,l] * X[b,ci,l+t-pad_left];  dy/x c8(dtype); dW [Cout,Cin,Kmax] fp32.

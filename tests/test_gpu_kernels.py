@@ -129,6 +129,61 @@ def test_conv_tcgen05_matches_simt_on_bf16_operands(T, name):
         assert rel_err(c8_to_ncl_ref(y_tc.cpu(), cout), ref) < TOL_BF16
 
 
+@pytest.mark.parametrize("name", ["small7", "mid13", "cfg2_l1", "cfg2_l2", "cfg4_l1"])
+def test_conv_tcgen05_fused_epilogues(T, name):
+    """Forward: per-CTA (mean, M2) partials of y merge to the batch statistics.  Dgrad: the written gradient is
+    already masked by the ReLU of the layer below and the per-CTA (S1, S2) partials sum to the BatchNorm-backward
+    reductions, both against fp64 torch on the kernel's own fp32 output."""
+    ops, L = T.ops, T._lib
+    if not L.load().tsc_device_supports_tcgen05():
+        pytest.skip("device has no tcgen05")
+    layer, g, x, w, b, dy = make_case(name, seed=3)
+    geom = ops.bank_geometry(layer)
+    B, Ln = x.shape[0], x.shape[2]
+    ncta, ltiles = ops.n_conv_ctas(B, Ln), (Ln + 127) // 128
+    wd = w.clone().cuda()
+    # forward statistics
+    wp = ops.pack_weights(geom, wd, L.DIR_FWD, L.TSC_BF16, True)
+    part = torch.full((ncta, geom.cout_p, 2), float("nan"), device="cuda")
+    y8 = ops.osconv(L.ENGINE_TCGEN05, L.DIR_FWD, geom, ops.ncl_to_c8(x.cuda(), L.TSC_BF16), wp, b.cuda(), stat_partial=part)
+    torch.cuda.synchronize()
+    assert ops.read_watchdog() == 0
+    y = c8_to_ncl_ref(y8.cpu(), geom.cout).double()                       # [B, C, L]
+    part = part.cpu().double()
+    n_rows = torch.tensor([min(128, Ln - (i % ltiles) * 128) for i in range(ncta)], dtype=torch.float64)
+    mean_i, m2_i = part[:, :geom.cout, 0], part[:, :geom.cout, 1]
+    N = float(B * Ln)
+    mean = (mean_i * n_rows[:, None]).sum(0) / N
+    m2 = m2_i.sum(0) + (n_rows[:, None] * (mean_i - mean) ** 2).sum(0)
+    assert rel_err(mean, y.mean(dim=(0, 2))) < 1e-5
+    assert rel_err(m2 / N, y.var(dim=(0, 2), unbiased=False)) < 1e-4
+    # dgrad with the mask / reductions of a layer below that has geom.cin channels
+    gen = torch.Generator().manual_seed(11)
+    cin, cp = geom.cin, geom.cin_p
+    y_below = torch.randn(B, cin, Ln, generator=gen)
+    scale, shift = torch.randn(cin, generator=gen), torch.randn(cin, generator=gen) * 0.3
+    mean_b, invstd_b = torch.randn(cin, generator=gen) * 0.1, torch.rand(cin, generator=gen) + 0.5
+    pad = lambda v: F.pad(v, (0, cp - cin)).cuda()
+    wpd = ops.pack_weights(geom, wd, L.DIR_DGRAD, L.TSC_BF16, False)
+    dy8 = ops.ncl_to_c8(dy.cuda(), L.TSC_BF16)
+    plain = ops.osconv(L.ENGINE_TCGEN05, L.DIR_DGRAD, geom, dy8, wpd, None)
+    for relu in (True, False):
+        red = torch.full((ncta, cp, 2), float("nan"), device="cuda")
+        mask = (ops.ncl_to_c8(y_below.cuda(), L.TSC_F32), pad(scale) if relu else None, pad(shift) if relu else None,
+                pad(mean_b), pad(invstd_b))
+        d8 = ops.osconv(L.ENGINE_TCGEN05, L.DIR_DGRAD, geom, dy8, wpd, None, mask=mask, red_partial=red)
+        torch.cuda.synchronize()
+        assert ops.read_watchdog() == 0
+        dz = c8_to_ncl_ref(plain.cpu(), cin).double()
+        z = scale[None, :, None].double() * y_below.double() + shift[None, :, None].double()
+        d_ref = dz * (z > 0) if relu else dz
+        assert rel_err(c8_to_ncl_ref(d8.cpu(), cin), d_ref) < 1e-6
+        yhat = (y_below.double() - mean_b[None, :, None].double()) * invstd_b[None, :, None].double()
+        red = red.cpu().double().sum(0)
+        assert rel_err(red[:cin, 0], d_ref.sum(dim=(0, 2))) < 1e-4
+        assert rel_err(red[:cin, 1], (d_ref * yhat).sum(dim=(0, 2))) < 1e-4
+
+
 @pytest.mark.parametrize("name", list(BANKS))
 def test_wgrad_tcgen05(T, name):
     ops, L = T.ops, T._lib

@@ -48,13 +48,6 @@ def main():
         L.load().tsc_debug_set_timeline(None)
         t = tl.cpu().tolist()
         print(f"timeline[{name}] CTA0 cycles since entry: " + ", ".join(f"{n}={v - t[0]}" for n, v in zip(names, t)))
-        if a.stages:
-            print("  stage: mma[wait-begin, wait-end, issued, committed]  producer[wait-begin, wait-end, copy issued]")
-            for i in range(48):
-                r = t[8 + 8 * i: 8 + 8 * i + 7]
-                if r[0] == 0:
-                    break
-                print(f"  {i:3d}: " + " ".join(f"{v - t[0]:7d}" for v in r[:4]) + "   |" + " ".join(f"{v - t[0]:7d}" for v in r[4:7]))
         tl.zero_()
     for name, fn in (("fwd", lambda: ops.osconv(L.ENGINE_TCGEN05, L.DIR_FWD, g, x8, wf, bias)),
                      ("dgrad", lambda: ops.osconv(L.ENGINE_TCGEN05, L.DIR_DGRAD, g, dy8, wd, None)),
