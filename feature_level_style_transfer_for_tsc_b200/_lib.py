@@ -61,7 +61,7 @@ SIGNATURES = {
     "tsc_osconv_plan_build": (_i, [_i, _i, _i, _i, _ip, _p]),
     "tsc_osconv": (_i, [_i, _i, _p, _i, _p, _p, _p, _p, _ep, _i, _i, _i, _i, _i, _ip, _p]),
     "tsc_oswgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
-    "tsc_oswgrad": (_i, [_i, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _ip, _p]),
+    "tsc_oswgrad": (_i, [_i, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _ip, _p]),
     "tsc_bn_workspace_bytes": (_sz, [_i, _i, _i]),
     "tsc_bn_stats": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _f, _f, _i, _i, _i, _p]),
     "tsc_bn_eval_coeffs": (_i, [_p, _p, _p, _p, _f, _p, _p, _p, _p, _i, _p]),

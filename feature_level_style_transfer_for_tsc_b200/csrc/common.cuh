@@ -59,7 +59,7 @@ static inline void fill_stable(STable* st, const int* s_of_tap, int Kmax) {
 
 // Ordered reduction of wgrad partials [S][Kmax][np][kcp] -> dW [Cout][Cin][Kmax] (layout.cu).
 int launch_wgrad_reduce(const float* part, float* dW, int S, int Cin, int Cout, int Kmax, int np, int kcp,
-                        const int* s_of_tap, cudaStream_t stream);
+                        const int* s_of_tap, int accumulate, cudaStream_t stream);
 
 // ---- dtype helpers ----------------------------------------------------------------------------
 __device__ __forceinline__ float to_f32(float v) { return v; }

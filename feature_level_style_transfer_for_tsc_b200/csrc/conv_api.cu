@@ -8,16 +8,18 @@ int osconv_tc(int direction, const void* x, int dtype, const void* w, const void
               const tsc_conv_epilogue* epi, int B, int L, int Cin, int Cout, int Kmax, const int* s_of_tap, cudaStream_t cs);
 size_t osconv_plan_bytes(int direction, int Cin, int Cout, int Kmax, const int* s_of_tap);
 int osconv_plan_build(int direction, int Cin, int Cout, int Kmax, const int* s_of_tap, void* host_plan);
-int oswgrad_simt(const void* dy, const void* x, int dtype, float* dW, void* workspace, int B, int L, int Cin, int Cout,
-                 int Kmax, const int* s_of_tap, cudaStream_t cs);
-int oswgrad_tc(const void* dy, const void* x, int dtype, float* dW, void* workspace, int B, int L, int Cin, int Cout,
-               int Kmax, const int* s_of_tap, cudaStream_t cs);
+int oswgrad_simt(const void* dy, const void* x, int dtype, float* dW, void* workspace, int accumulate, int B, int L, int Cin,
+                 int Cout, int Kmax, const int* s_of_tap, cudaStream_t cs);
+int oswgrad_tc(const void* dy, const void* x, int dtype, float* dW, void* workspace, int accumulate, int B, int L, int Cin,
+               int Cout, int Kmax, const int* s_of_tap, cudaStream_t cs);
+size_t wgrad_tc_workspace_bytes(int B, int L, int Cin, int Cout, int Kmax);
 int wgrad_simt_splits(int B, int L, int Cin, int Cout, int Kmax);
 int wgrad_tc_splits(int B, int L, int Cin, int Cout, int Kmax);
 int read_clear_watchdog_conv(int* code);
 int read_clear_watchdog_wgrad(int* code);
 int read_clear_watchdog_gram(int* code);
 void set_conv_timeline(long long* dev);
+void set_wgrad_timeline(long long* dev);
 }  // namespace tsc
 
 extern "C" {
@@ -52,12 +54,12 @@ int tsc_osconv(int engine, int direction, const void* x, int dtype, const void* 
 
 size_t tsc_oswgrad_workspace_bytes(int engine, int B, int L, int Cin, int Cout, int Kmax) {
     using namespace tsc;
-    const int S = engine == TSC_ENGINE_TCGEN05 ? wgrad_tc_splits(B, L, Cin, Cout, Kmax) : wgrad_simt_splits(B, L, Cin, Cout, Kmax);
-    return (size_t)S * Kmax * pad16(Cout) * pad16(Cin) * sizeof(float);
+    if (engine == TSC_ENGINE_TCGEN05) return wgrad_tc_workspace_bytes(B, L, Cin, Cout, Kmax);
+    return (size_t)wgrad_simt_splits(B, L, Cin, Cout, Kmax) * Kmax * pad16(Cout) * pad16(Cin) * sizeof(float);
 }
 
-int tsc_oswgrad(int engine, const void* dy, const void* x, int dtype, float* dW, void* workspace, int B, int L, int Cin,
-                int Cout, int Kmax, const int* s_of_tap, tsc_stream_t stream) {
+int tsc_oswgrad(int engine, const void* dy, const void* x, int dtype, float* dW, void* workspace, int accumulate, int B,
+                int L, int Cin, int Cout, int Kmax, const int* s_of_tap, tsc_stream_t stream) {
     using namespace tsc;
     TSC_REQUIRE(dy && x && dW && workspace, "NULL tensor");
     TSC_REQUIRE(B > 0 && L > 0, "bad shape B=%d L=%d", B, L);
@@ -65,13 +67,17 @@ int tsc_oswgrad(int engine, const void* dy, const void* x, int dtype, float* dW,
     TSC_REQUIRE(Kmax >= 1 && Kmax <= TSC_MAX_TAPS && s_of_tap, "bad kernel bank");
     TSC_REQUIRE(Cin >= 1 && Cin <= TSC_MAX_CHANNELS && Cout >= 1 && Cout <= TSC_MAX_CHANNELS, "bad channel counts");
     if (engine == TSC_ENGINE_SIMT)
-        return oswgrad_simt(dy, x, dtype, dW, workspace, B, L, Cin, Cout, Kmax, s_of_tap, (cudaStream_t)stream);
+        return oswgrad_simt(dy, x, dtype, dW, workspace, accumulate, B, L, Cin, Cout, Kmax, s_of_tap, (cudaStream_t)stream);
     if (engine == TSC_ENGINE_TCGEN05)
-        return oswgrad_tc(dy, x, dtype, dW, workspace, B, L, Cin, Cout, Kmax, s_of_tap, (cudaStream_t)stream);
+        return oswgrad_tc(dy, x, dtype, dW, workspace, accumulate, B, L, Cin, Cout, Kmax, s_of_tap, (cudaStream_t)stream);
     TSC_REQUIRE(false, "bad engine %d", engine);
 }
 
-int tsc_debug_set_timeline(void* dev_buf) { tsc::set_conv_timeline((long long*)dev_buf); return 0; }
+int tsc_debug_set_timeline(void* dev_buf) {
+    tsc::set_conv_timeline((long long*)dev_buf);
+    tsc::set_wgrad_timeline((long long*)dev_buf);
+    return 0;
+}
 
 int tsc_debug_read_and_clear_watchdog(int* host_code) {
     using namespace tsc;

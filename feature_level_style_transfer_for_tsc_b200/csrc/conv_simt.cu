@@ -203,8 +203,8 @@ int osconv_simt(int direction, const void* x, int dtype, const void* w, const fl
     return 0;
 }
 
-int oswgrad_simt(const void* dy, const void* x, int dtype, float* dW, void* workspace, int B, int L, int Cin, int Cout,
-                 int Kmax, const int* s_of_tap, cudaStream_t cs) {
+int oswgrad_simt(const void* dy, const void* x, int dtype, float* dW, void* workspace, int accumulate, int B, int L, int Cin,
+                 int Cout, int Kmax, const int* s_of_tap, cudaStream_t cs) {
     const int np = pad16(Cout), kc_x = pad16(Cin) / 8;
     const int S = wgrad_simt_splits(B, L, Cin, Cout, Kmax);
     STable st;
@@ -217,7 +217,7 @@ int oswgrad_simt(const void* dy, const void* x, int dtype, float* dW, void* work
     else
         oswgrad_simt_kernel<float><<<grid, 256, 0, cs>>>((const float*)dy, (const float*)x, part, B, L, kc_x, np, Kmax, pad_left, S, st);
     TSC_LAUNCH_CHECK();
-    return launch_wgrad_reduce(part, dW, S, Cin, Cout, Kmax, np, kc_x * 8, s_of_tap, cs);
+    return launch_wgrad_reduce(part, dW, S, Cin, Cout, Kmax, np, kc_x * 8, s_of_tap, accumulate, cs);
 }
 
 }  // namespace tsc

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256) zero_masked_kernel(float* __restrict__ W,
 
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dW,
                                                              int S, int Cin, int Cout, int Kmax, int np, int kcp,
-                                                             const __grid_constant__ STable st) {
+                                                             const __grid_constant__ STable st, int accumulate) {
     const int total = Cout * Cin * Kmax;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int t = i % Kmax;
@@ -146,16 +146,16 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
             const float* p = part + ((long long)t * np + co) * kcp + ci;
             for (int s = 0; s < S; ++s) acc += p[s * stride];
         }
-        dW[i] = acc;
+        dW[i] = accumulate ? dW[i] + acc : acc;
     }
 }
 
 int launch_wgrad_reduce(const float* part, float* dW, int S, int Cin, int Cout, int Kmax, int np, int kcp,
-                        const int* s_of_tap, cudaStream_t stream) {
+                        const int* s_of_tap, int accumulate, cudaStream_t stream) {
     STable st;
     for (int t = 0; t < TSC_MAX_TAPS; ++t) st.s[t] = t < Kmax ? s_of_tap[t] : 0x7fffffff;
     wgrad_reduce_kernel<<<grid_for((long long)Cout * Cin * Kmax), 256, 0, stream>>>(part, dW, S, Cin, Cout, Kmax,
-                                                                                    np, kcp, st);
+                                                                                    np, kcp, st, accumulate);
     TSC_LAUNCH_CHECK();
     return 0;
 }

@@ -74,6 +74,38 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
                  : "memory");
 }
 
+// ---- LDGSTS (cp.async) staging of c8 tiles ---------------------------------------------------------
+// A c8 row is 16 B and consecutive positions are contiguous, so a warp's 32 copies cover 512 contiguous bytes; one
+// producer warpgroup stages a tile an order of magnitude faster than a TMA box whose inner extent is a single
+// 16 B row (measured: the TMA unit retires ~1 such row per cycle -- profiles/r1_conv_timeline.md).
+__device__ __forceinline__ void cp_async16_zfill(uint32_t smem_dst, const void* gsrc, bool valid) {
+    const uint32_t n = valid ? 16u : 0u;       // src-size 0: the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(n) : "memory");
+}
+// the calling thread's earlier cp.async copies arrive on the mbarrier when they have landed (does not add to the
+// barrier's expected count: initialise it with the number of producer threads)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Stage rows [l_start, l_start + R) of chunks [chunk0, chunk0 + nchunk) of sample b of a c8 bf16 tensor
+// [B][C8][L][8] into smem [nchunk][R][8]; rows outside [0, L) and chunks outside [0, C8) are zero-filled
+// (ConstantPad1d / channel padding).  R >= nthreads is required (one chunk wrap per step at most).
+__device__ __forceinline__ void stage_c8_tile(uint8_t* smem_dst, const __nv_bfloat16* base, int b, int C8, int L, int chunk0,
+                                              int nchunk, int l_start, int R, int tid, int nthreads) {
+    const uint32_t dst0 = smem_u32(smem_dst);
+    int c = 0, r = tid;
+    while (r >= R) { r -= R; ++c; }
+    const int total = nchunk * R;
+    for (int i = tid; i < total; i += nthreads) {
+        const int l = l_start + r, ch = chunk0 + c;
+        const bool valid = l >= 0 && l < L && ch >= 0 && ch < C8;
+        const __nv_bfloat16* src = base + (((size_t)b * C8 + (valid ? ch : 0)) * L + (valid ? l : 0)) * 8;
+        cp_async16_zfill(dst0 + (uint32_t)i * 16u, src, valid);
+        r += nthreads;
+        while (r >= R) { r -= R; ++c; }
+    }
+}
+
 // ---- TMEM -----------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)

@@ -12,15 +12,21 @@
 // (b, l) position tiles, accumulates in TMEM over all of them, and writes its partial dW once.
 // Out tiles are anchored at the END of the channel axis: by nestedness of the kernel bank the outer
 // taps are live only on a channel suffix, so they need the last tile only (masked taps cost nothing).
-// Partials [split][tap][co][ci] are reduced in order by wgrad_reduce_kernel (deterministic, no atomics),
-// which also writes the exact zeros of the masked taps.
+//
+// Warp roles: warps 1-2 = MMA issuers (taps alternate between them: with N = Cin_p <= 128 one issuing thread is the
+// limiter, ~73 cycles per instruction against N/2 cycles of tensor work -- tools/mma_bench2.cu), warps 3-6 = tile
+// producers during the main loop (LDGSTS with zero fill: a c8 row is 16 B, and a TMA box of 16 B rows retires
+// about one row per cycle, slower than 128 threads issuing coalesced 16 B copies), then the epilogue.
+// Partials are CTA-private blocks [split][item][tap][ci][128 rows] (row-fastest, so every store instruction of a
+// warp writes 128 contiguous bytes); wgrad_tc_reduce_kernel adds the splits in a fixed order (deterministic, no
+// float atomics), writes the exact zeros of the masked taps and can accumulate into dW (flat gradient bucket).
 // Replaces cuDNN/oneDNN wgrad of OS_CNN/OS_CNN.py:71.
 #include "tc_common.cuh"
 
 namespace tsc {
 namespace tc {
 
-static constexpr int WG_THREADS = 192;
+static constexpr int WG_THREADS = 224;
 static constexpr int WG_LT = 128;          // positions per stage
 static constexpr int WG_MAX_ITEMS = 192;
 static constexpr int WG_HDR = 256;
@@ -28,26 +34,32 @@ static constexpr int WG_STAGES = 2;
 
 struct WgItem { short m0, t0, nt, pad; };
 struct WgItems { int n; WgItem it[WG_MAX_ITEMS]; };
+// tile (0: channels below m_split, 1: the rest) x tap -> work item (or -1: masked tap, gradient is zero)
+struct WgLookup { short item_of[2][TSC_MAX_TAPS]; };
 
 struct WgParams {
-    float* part;        // [S][taps][np][kcp]
+    float* part;        // [S][items][NT][cinp][128]
+    const __nv_bfloat16* dy;   // c8 [B][np/8][L][8]
+    const __nv_bfloat16* x;    // c8 [B][kcx][L][8]
     int B, L, ltiles;
     int taps, pad_left;
     int np;             // padded out channels
     int kcx;            // in-channel chunks
     int RX;             // X rows per chunk in shared memory
     int S;              // position splits
+    int NT;             // accumulators (taps) per item
     int stage_bytes;
-    int m_split;        // channels below m_split belong to tile 0 (MT == 2), 0 when MT == 1
+    long long* tl;      // optional phase timeline of CTA (0,0) (tsc_debug_set_timeline), NULL in production
 };
 
+#define WTL(i) do { if (p.tl && blockIdx.x == 0 && blockIdx.y == 0) p.tl[i] = clock64(); } while (0)
+
 __global__ void __launch_bounds__(WG_THREADS, 1)
-oswgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant__ CUtensorMap xmap,
-                  const __grid_constant__ WgItems items, const WgParams p) {
+oswgrad_tc_kernel(const __grid_constant__ WgItems items, const WgParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);        // [2]
-    uint64_t* empty = full + WG_STAGES;                        // [2]
-    uint64_t* acc_full = empty + WG_STAGES;
+    uint64_t* empty = full + WG_STAGES;                        // [2], two arrivals each (one per issuer warp)
+    uint64_t* acc_full = empty + WG_STAGES;                    // two arrivals
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
     uint8_t* stages = smem + WG_HDR;
 
@@ -57,14 +69,12 @@ oswgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_consta
     const int cinp = p.kcx * 8;
     const long long ntile = (long long)p.B * p.ltiles;
     const int tile0 = (int)(ntile * sp / p.S), tile1 = (int)(ntile * (sp + 1) / p.S);
-    const int dy_chunks = min(16, p.np / 8 - item.m0 / 8);
     const int dy_bytes = 16 * WG_LT * 16;                       // the A tile always spans 16 chunks of smem
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&dymap);
-        tma_prefetch_desc(&xmap);
-        for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        mbar_init(acc_full, 1);
+        WTL(0);
+        for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], 2); }
+        mbar_init(acc_full, 2);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -74,101 +84,167 @@ oswgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_consta
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            bool dead = false;
-            const uint32_t bytes = (uint32_t)((dy_chunks * WG_LT + p.kcx * p.RX) * 16);
-            uint32_t s = 0, ph = 0;
-            for (int tile = tile0; tile < tile1; ++tile) {
-                const int b = tile / p.ltiles, l0 = (tile % p.ltiles) * WG_LT;
-                mbar_wait(&empty[s], ph ^ 1u, dead, 5);
-                uint8_t* st = stages + (size_t)s * p.stage_bytes;
-                mbar_arrive_expect_tx(&full[s], bytes);
-                for (int c = 0; c < dy_chunks; ++c)
-                    tma_load_4d(st + (size_t)c * WG_LT * 16, &dymap, 0, l0, item.m0 / 8 + c, b, &full[s]);
-                for (int c = 0; c < p.kcx; ++c)
-                    tma_load_4d(st + dy_bytes + (size_t)c * p.RX * 16, &xmap, 0, l0 + item.t0 - p.pad_left, c, b, &full[s]);
-                if (++s == WG_STAGES) { s = 0; ph ^= 1u; }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            // lean issue loop (one thread issues at most one MMA per ~54 cycles): descriptors advance by adds
-            bool dead = false;
-            const uint32_t idesc = make_idesc_bf16(128, (uint32_t)cinp, true, true, false);
-            const uint32_t st16 = smem_u32(stages) >> 4, stage16 = (uint32_t)p.stage_bytes >> 4;
-            // MN-major, SWIZZLE_NONE: LBO = 128 B between 8-position groups, SBO = chunk stride
-            const uint32_t a_hi = ((uint32_t)(WG_LT * 16) >> 4) | (1u << 14);
-            const uint32_t b_hi = ((uint32_t)(p.RX * 16) >> 4) | (1u << 14);
-            const uint32_t lbo = (128u >> 4) << 16;
-            uint32_t s = 0, ph = 0, acc = 0;
-            const int nt = item.nt;
-            for (int tile = tile0; tile < tile1; ++tile) {
-                mbar_wait(&full[s], ph, dead, 6);
-                tc_fence_after();
-                const uint32_t a0 = (st16 + s * stage16) | lbo;
-                const uint32_t b0 = (st16 + s * stage16 + ((uint32_t)dy_bytes >> 4)) | lbo;
-                uint32_t d_tmem = tmem_base;
-                for (int tl = 0; tl < nt; ++tl) {
+        // (idle: the tiles are staged by the four epilogue warps)
+    } else if (warp <= 2) {
+        // Each issuer warp walks the tiles in lock-step (uniform control flow) and one elected lane issues the 8 MMAs
+        // of a (tile, tap) per elect block: a lane-0-only branch makes ptxas wrap every UTCHMMA in a per-thread ELECT
+        // loop (tools/mma_bench3.cu).  Warp 1 takes the even taps of the item, warp 2 the odd ones.
+        bool dead = false;
+        const int wi = warp - 1;
+        const uint32_t idesc = make_idesc_bf16(128, (uint32_t)cinp, true, true, false);
+        const uint32_t st16 = smem_u32(stages) >> 4, stage16 = (uint32_t)p.stage_bytes >> 4;
+        // MN-major, SWIZZLE_NONE: LBO = 128 B between 8-position groups, SBO = chunk stride
+        const uint32_t a_hi = ((uint32_t)(WG_LT * 16) >> 4) | (1u << 14);
+        const uint32_t b_hi = ((uint32_t)(p.RX * 16) >> 4) | (1u << 14);
+        const uint32_t lbo = (128u >> 4) << 16;
+        uint32_t s = 0, ph = 0, acc = 0;
+        const int nt = item.nt;
+        for (int tile = tile0; tile < tile1; ++tile) {
+            mbar_wait(&full[s], ph, dead, 6);
+            __syncwarp();             // lanes leave the polling loop at different times: reconverge before the elect
+            fence_proxy_async();      // the tile was written by cp.async (generic proxy), the MMA reads it through the async proxy
+            tc_fence_after();
+            if (wi == 0 && lane == 0 && p.tl && blockIdx.x == 0 && blockIdx.y == 0 && tile - tile0 < 24)
+                p.tl[8 + tile - tile0] = clock64();
+            const uint32_t a0 = (st16 + s * stage16) | lbo;
+            const uint32_t b0 = (st16 + s * stage16 + ((uint32_t)dy_bytes >> 4)) | lbo;
+            for (int tl = wi; tl < nt; tl += 2) {
+                const uint32_t d_tmem = tmem_base + (uint32_t)(tl * cinp);
+                if (elect_one()) {
 #pragma unroll
                     for (int k16 = 0; k16 < WG_LT / 16; ++k16) {
                         umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | (a0 + (uint32_t)(k16 * 16)),
                                   ((uint64_t)b_hi << 32) | (b0 + (uint32_t)(tl + k16 * 16)), idesc, acc | (uint32_t)(k16 > 0));
                     }
-                    d_tmem += (uint32_t)cinp;
                 }
-                acc = 1;
-                tc_commit(&empty[s]);
-                if (++s == WG_STAGES) { s = 0; ph ^= 1u; }
             }
-            tc_commit(acc_full);
+            __syncwarp();
+            if (elect_one()) tc_commit(&empty[s]);      // this warp's MMAs on the stage are done reading it
+            acc = 1;
+            if (++s == WG_STAGES) { s = 0; ph ^= 1u; }
         }
+        __syncwarp();
+        if (elect_one()) tc_commit(acc_full);
+        if (wi == 0 && lane == 0) WTL(4);
     } else {
         bool dead = false;
-        mbar_wait(acc_full, 0, dead, 7);
-        tc_fence_after();
-        const int q = warp & 3;
-        const int co = item.m0 + q * 32 + lane;
-        // tile 0 of a two-tile layer owns co < m_split, the last tile owns the rest
-        const bool mine = co < p.np && (item.m0 == 0 ? (p.m_split == 0 || co < p.m_split) : co >= p.m_split);
-        const int kcp = cinp;
-        if (tile1 > tile0) {
-            for (int tl = 0; tl < item.nt; ++tl) {
-                const int t = item.t0 + tl;
-                float* dst = p.part + (((size_t)sp * p.taps + t) * p.np + co) * kcp;
-                for (int c0 = 0; c0 < cinp; c0 += 16) {
-                    float v[16];
-                    tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tl * cinp + c0), v);
-                    if (mine) {
-#pragma unroll
-                        for (int i = 0; i < 16; i += 4)
-                            *reinterpret_cast<float4*>(dst + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                    }
-                }
-            }
-        } else if (mine) {
-            // this split had no position tile: its partial is zero
-            for (int tl = 0; tl < item.nt; ++tl) {
-                float* dst = p.part + (((size_t)sp * p.taps + item.t0 + tl) * p.np + co) * kcp;
-                for (int c = 0; c < cinp; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        {
+            // ===== producer phase: the four epilogue warps stage (dY tile, X tile + halo) with LDGSTS, zero-filling the
+            // rows outside the series (ConstantPad1d) and the chunks past the channel axis =====
+            const int ptid = threadIdx.x - 96;
+            uint32_t s = 0, ph = 0;
+            for (int tile = tile0; tile < tile1; ++tile) {
+                const int b = tile / p.ltiles, l0 = (tile % p.ltiles) * WG_LT;
+                mbar_wait(&empty[s], ph ^ 1u, dead, 5);
+                uint8_t* st = stages + (size_t)s * p.stage_bytes;
+                stage_c8_tile(st, p.dy, b, p.np / 8, p.L, item.m0 / 8, 16, l0, WG_LT, ptid, 128);
+                stage_c8_tile(st + dy_bytes, p.x, b, p.kcx, p.L, 0, p.kcx, l0 + item.t0 - p.pad_left, p.RX, ptid, 128);
+                cp_async_arrive_noinc(&full[s]);
+                if (++s == WG_STAGES) { s = 0; ph ^= 1u; }
             }
         }
+        if (threadIdx.x == 96) mbar_wait(acc_full, 0, dead, 7);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        tc_fence_after();
+        if (threadIdx.x == 96) WTL(5);
+        const int q = warp & 3;                        // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;
+        // CTA-private block [tap][ci][128 rows]: the 32 lanes of a warp store 128 contiguous bytes per instruction
+        float* dst = p.part + (((size_t)sp * items.n + blockIdx.x) * p.NT) * (size_t)cinp * 128 + row;
+        const bool any = tile1 > tile0;                // a split without a position tile contributes zeros
+        for (int tl = 0; tl < item.nt; ++tl) {
+            for (int c0 = 0; c0 < cinp; c0 += 16) {
+                float v[16];
+                if (any) {
+                    tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tl * cinp + c0), v);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                }
+                float* d = dst + ((size_t)tl * cinp + c0) * 128;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) d[(size_t)i * 128] = v[i];
+            }
+        }
+        if (threadIdx.x == 96) WTL(6);
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (warp == 1 && lane == 0) WTL(7);
+}
+
+// dW[co, ci, t] (+)= sum over splits of the partial of the item covering (tile(co), t); 0 on masked taps.
+// One block = 8 consecutive out channels x 8 consecutive taps x 32 in channels; thread = (ci, channel): the 8 threads
+// of a group read 8 consecutive floats of a partial row (one 32 B sector), the 8 taps of a thread are independent
+// loads in flight, and each thread writes its 8 taps contiguously.
+__global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __restrict__ part, float* __restrict__ dW,
+                                                                const __grid_constant__ WgItems items,
+                                                                const __grid_constant__ WgLookup lk,
+                                                                const __grid_constant__ STable st, int S, int NT, int Cin,
+                                                                int Cout, int Kmax, int np, int cinp, int m_split,
+                                                                int accumulate) {
+    const int r = threadIdx.x & 7;
+    const int co = blockIdx.x * 8 + r;
+    const int t_base = blockIdx.y * 8;
+    const int ci = blockIdx.z * 32 + (threadIdx.x >> 3);
+    if (co >= Cout || ci >= Cin) return;
+    const int tile = (m_split > 0 && co >= m_split) ? 1 : 0;
+    const int m0 = tile == 1 ? np - 128 : 0;
+    const int row = co - m0;
+    const size_t split_stride = (size_t)items.n * NT * cinp * 128;
+    const float* src[8];
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int t = t_base + j;
+        src[j] = nullptr;
+        acc[j] = 0.f;
+        if (t < Kmax && co >= st.s[t]) {
+            const int it = lk.item_of[tile][t];
+            if (it >= 0) src[j] = part + (((size_t)it * NT + (t - items.it[it].t0)) * cinp + ci) * 128 + row;
+        }
+    }
+    // four splits x eight taps = 32 independent loads in flight per thread; the sums stay in split order
+    int s = 0;
+    for (; s + 4 <= S; s += 4) {
+        float v[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[u][j] = src[j] ? __ldg(src[j] + (size_t)(s + u) * split_stride) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += v[u][j];
+    }
+    for (; s < S; ++s) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (src[j]) acc[j] += __ldg(src[j] + (size_t)s * split_stride);
+    }
+    float* o = dW + ((size_t)co * Cin + ci) * Kmax + t_base;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (t_base + j < Kmax) o[j] = accumulate ? o[j] + acc[j] : acc[j];
+    }
 }
 
 int make_c8_map(CUtensorMap* map, const void* base, int B, int kc, int L, int box_rows, int box_chunks);   // conv_tc.cu
+static long long* g_wg_timeline = nullptr;
 
 }  // namespace tc
 
-static int wgrad_tc_items(int Cin, int Cout, int Kmax, const int* s_of_tap, tc::WgItems* items, int* m_split) {
+static int wgrad_tc_items(int Cin, int Cout, int Kmax, const int* s_of_tap, tc::WgItems* items, tc::WgLookup* lk,
+                          int* m_split) {
     using namespace tc;
     const int np = pad16(Cout), cinp = pad16(Cin);
     const int NT = 512 / cinp;
     const int MT = np > 128 ? 2 : 1;
     *m_split = MT == 2 ? np - 128 : 0;
     items->n = 0;
+    for (int a = 0; a < 2; ++a)
+        for (int t = 0; t < TSC_MAX_TAPS; ++t) lk->item_of[a][t] = -1;
     for (int mt = 0; mt < MT; ++mt) {
         const int m0 = (MT == 2 && mt == 1) ? np - 128 : 0;
         // taps that need this tile: the last tile serves every live tap, tile 0 (of two) the taps whose
@@ -180,6 +256,7 @@ static int wgrad_tc_items(int Cin, int Cout, int Kmax, const int* s_of_tap, tc::
             int n = 0;
             while (t + n < Kmax && n < NT && s_of_tap[t + n] < limit) ++n;
             TSC_REQUIRE(items->n < WG_MAX_ITEMS, "too many wgrad work items");
+            for (int j = 0; j < n; ++j) lk->item_of[MT == 2 ? mt : 0][t + j] = (short)items->n;
             items->it[items->n++] = WgItem{(short)m0, (short)t, (short)n, 0};
             t += n;
         }
@@ -188,10 +265,14 @@ static int wgrad_tc_items(int Cin, int Cout, int Kmax, const int* s_of_tap, tc::
     return 0;
 }
 
-int wgrad_tc_splits(int B, int L, int Cin, int Cout, int Kmax) {
-    // upper bound on the number of work items without the tap table: 2 tiles x ceil(Kmax / NT)
+// upper bound on the number of work items without the tap table: 2 tiles x ceil(Kmax / NT)
+static int wgrad_tc_max_items(int Cin, int Cout, int Kmax) {
     const int cinp = pad16(Cin), NT = 512 / cinp, MT = pad16(Cout) > 128 ? 2 : 1;
-    const int items = MT * cdiv(Kmax, NT);
+    return MT * cdiv(Kmax, NT);
+}
+
+int wgrad_tc_splits(int B, int L, int Cin, int Cout, int Kmax) {
+    const int items = wgrad_tc_max_items(Cin, Cout, Kmax);
     const int ntile = B * cdiv(L, tc::WG_LT);
     int s = cdiv(148, items);
     if (s > ntile) s = ntile;
@@ -200,13 +281,20 @@ int wgrad_tc_splits(int B, int L, int Cin, int Cout, int Kmax) {
     return s;
 }
 
-int oswgrad_tc(const void* dy, const void* x, int dtype, float* dW, void* workspace, int B, int L, int Cin, int Cout,
-               int Kmax, const int* s_of_tap, cudaStream_t cs) {
+size_t wgrad_tc_workspace_bytes(int B, int L, int Cin, int Cout, int Kmax) {
+    const int cinp = pad16(Cin), NT = 512 / cinp;
+    return (size_t)wgrad_tc_splits(B, L, Cin, Cout, Kmax) * wgrad_tc_max_items(Cin, Cout, Kmax) * NT * cinp * 128 * sizeof(float);
+}
+
+int oswgrad_tc(const void* dy, const void* x, int dtype, float* dW, void* workspace, int accumulate, int B, int L, int Cin,
+               int Cout, int Kmax, const int* s_of_tap, cudaStream_t cs) {
     using namespace tc;
     TSC_REQUIRE(dtype == TSC_BF16, "the tcgen05 engine takes bf16 operands");
     WgItems items;
+    WgLookup lk;
     WgParams p;
-    if (wgrad_tc_items(Cin, Cout, Kmax, s_of_tap, &items, &p.m_split) != 0) return -1;
+    int m_split = 0;
+    if (wgrad_tc_items(Cin, Cout, Kmax, s_of_tap, &items, &lk, &m_split) != 0) return -1;
     const int np = pad16(Cout), cinp = pad16(Cin);
     const int NT = 512 / cinp;
     p.part = (float*)workspace;
@@ -215,22 +303,30 @@ int oswgrad_tc(const void* dy, const void* x, int dtype, float* dW, void* worksp
     p.np = np; p.kcx = cinp / 8;
     p.RX = (WG_LT + NT - 1 + 7) & ~7;
     p.S = wgrad_tc_splits(B, L, Cin, Cout, Kmax);
+    p.NT = NT;
+    p.tl = g_wg_timeline;
     p.stage_bytes = 16 * WG_LT * 16 + p.kcx * p.RX * 16;
     const int smem = WG_HDR + WG_STAGES * p.stage_bytes;
     TSC_REQUIRE(smem <= 227 * 1024, "wgrad shape needs %d B of shared memory: unsupported", smem);
-    CUtensorMap dymap, xmap;
-    if (make_c8_map(&dymap, dy, B, np / 8, L, WG_LT, 1) != 0) return -1;
-    if (make_c8_map(&xmap, x, B, p.kcx, L, p.RX, 1) != 0) return -1;
+    p.dy = (const __nv_bfloat16*)dy;
+    p.x = (const __nv_bfloat16*)x;
     static bool attr_set = false;          // once per process: opt in to the full 227 KB of dynamic shared memory
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(oswgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         attr_set = true;
     }
-    oswgrad_tc_kernel<<<dim3(items.n, p.S), WG_THREADS, smem, cs>>>(dymap, xmap, items, p);
+    oswgrad_tc_kernel<<<dim3(items.n, p.S), WG_THREADS, smem, cs>>>(items, p);
     TSC_LAUNCH_CHECK();
-    return launch_wgrad_reduce(p.part, dW, p.S, Cin, Cout, Kmax, np, cinp, s_of_tap, cs);
+    STable st;
+    fill_stable(&st, s_of_tap, Kmax);
+    wgrad_tc_reduce_kernel<<<dim3(cdiv(Cout, 8), cdiv(Kmax, 8), cdiv(Cin, 32)), 256, 0, cs>>>(p.part, dW, items, lk, st, p.S, NT, Cin, Cout,
+                                                                          Kmax, np, cinp, m_split, accumulate);
+    TSC_LAUNCH_CHECK();
+    return 0;
 }
+
+void set_wgrad_timeline(long long* dev) { tc::g_wg_timeline = dev; }
 
 int read_clear_watchdog_wgrad(int* code) {
     int zero = 0;

@@ -254,7 +254,10 @@ def osconv(engine: int, direction: int, g: BankGeometry, x8: torch.Tensor, w_pac
     return y
 
 
-def oswgrad(engine: int, g: BankGeometry, dy8: torch.Tensor, x8: torch.Tensor) -> torch.Tensor:
+def oswgrad(engine: int, g: BankGeometry, dy8: torch.Tensor, x8: torch.Tensor,
+            out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """dW of the bank; with ``out`` (fp32 [Cout, Cin, Kmax], e.g. a view of the flat gradient bucket) the result is
+    written -- or, with ``accumulate``, added -- in place."""
     dt = L.TSC_BF16 if x8.dtype == torch.bfloat16 else L.TSC_F32
     _req(x8, torch_dtype(dt), "x_c8")
     _req(dy8, torch_dtype(dt), "dy_c8")
@@ -262,9 +265,16 @@ def oswgrad(engine: int, g: BankGeometry, dy8: torch.Tensor, x8: torch.Tensor) -
     lib = L.load()
     ws = torch.empty(int(lib.tsc_oswgrad_workspace_bytes(engine, B, Ln, g.cin, g.cout, g.kmax)) // 4 + 4,
                      device=x8.device, dtype=torch.float32)
-    dW = torch.empty((g.cout, g.cin, g.kmax), device=x8.device, dtype=torch.float32)
-    L.check(lib.tsc_oswgrad(engine, _ptr(dy8), _ptr(x8), dt, _ptr(dW), _ptr(ws), B, Ln, g.cin, g.cout, g.kmax,
-                            g.s_arr, _stream()), "tsc_oswgrad")
+    if out is None:
+        if accumulate:
+            raise RuntimeError("accumulate needs an output tensor")
+        dW = torch.empty((g.cout, g.cin, g.kmax), device=x8.device, dtype=torch.float32)
+    else:
+        dW = _req(out, name="dW")
+        if tuple(dW.shape) != (g.cout, g.cin, g.kmax):
+            raise RuntimeError(f"dW shape {tuple(dW.shape)} != {(g.cout, g.cin, g.kmax)}")
+    L.check(lib.tsc_oswgrad(engine, _ptr(dy8), _ptr(x8), dt, _ptr(dW), _ptr(ws), 1 if accumulate else 0, B, Ln, g.cin,
+                            g.cout, g.kmax, g.s_arr, _stream()), "tsc_oswgrad")
     return dW
 
 

@@ -109,9 +109,11 @@ int tsc_osconv(int engine, int direction, const void* x_c8, int dtype, const voi
 
 /* ---- weight gradient on live taps only (masked taps get exact zeros) ---------------
  * dW[co,ci,t] = sum_{b,l} dY[b,co,l] * X[b,ci,l+t-pad_left];  dy/x c8(dtype); dW [Cout,Cin,Kmax] fp32.
- * Deterministic: partial sums per position split, then an ordered reduction (no float atomics). */
+ * Deterministic: partial sums per position split, then an ordered reduction (no float atomics).
+ * accumulate != 0: dW += result (dW is then typically a slice of the flat gradient bucket that the data-parallel
+ * all-reduce and the optimizer read -- the kernel writes the collective's operand in place). */
 size_t tsc_oswgrad_workspace_bytes(int engine, int B, int L, int Cin, int Cout, int Kmax);
-int tsc_oswgrad(int engine, const void* dy_c8, const void* x_c8, int dtype, float* dW, void* workspace,
+int tsc_oswgrad(int engine, const void* dy_c8, const void* x_c8, int dtype, float* dW, void* workspace, int accumulate,
                 int B, int L, int Cin, int Cout, int Kmax, const int* s_of_tap, tsc_stream_t stream);
 
 /* ---- BatchNorm1d (+ReLU, + shortcut add): replaces OS_CNN.py:72-74, 165, 176-180 --------------

@@ -41,13 +41,17 @@ def main():
     tl = torch.zeros(8 + 48 * 8, device=dev, dtype=torch.int64)
     names = ["entry", "setup", "x tile", "first W", "MMAs issued", "acc ready", "epilogue", "exit"]
     for name, fn in (("fwd", lambda: ops.osconv(L.ENGINE_TCGEN05, L.DIR_FWD, g, x8, wf, bias)),
-                     ("dgrad", lambda: ops.osconv(L.ENGINE_TCGEN05, L.DIR_DGRAD, g, dy8, wd, None))):
+                     ("dgrad", lambda: ops.osconv(L.ENGINE_TCGEN05, L.DIR_DGRAD, g, dy8, wd, None)),
+                     ("wgrad", lambda: ops.oswgrad(L.ENGINE_TCGEN05, g, dy8, x8))):
         fn(); torch.cuda.synchronize()
         L.load().tsc_debug_set_timeline(tl.data_ptr())
         fn(); torch.cuda.synchronize()
         L.load().tsc_debug_set_timeline(None)
         t = tl.cpu().tolist()
         print(f"timeline[{name}] CTA0 cycles since entry: " + ", ".join(f"{n}={v - t[0]}" for n, v in zip(names, t)))
+        if name == "wgrad":
+            it = [v - t[0] for v in t[8:32] if v]
+            print("  wgrad tile-ready times (cycles since entry): " + " ".join(str(v) for v in it))
         tl.zero_()
     for name, fn in (("fwd", lambda: ops.osconv(L.ENGINE_TCGEN05, L.DIR_FWD, g, x8, wf, bias)),
                      ("dgrad", lambda: ops.osconv(L.ENGINE_TCGEN05, L.DIR_DGRAD, g, dy8, wd, None)),
