@@ -120,8 +120,9 @@ def run_reference(args):
 class KernelProfile:
     """Times every C-ABI call family with CUDA events on the launching stream (instrumented pass, run after
     the timed region; never part of a reported step time)."""
-    LAUNCHES = dict(ncl_to_c8=1, c8_to_ncl=1, pack_weights=1, pack_weights_pair=1, rmsprop_step=1, osconv=1, oswgrad=2, bn_stats=2, bn_eval_coeffs=1,
-                    bn_apply=1, bn_bwd_reduce=2, bn_bwd_apply=1, adain_fwd=1, adain_bwd=1, gram_loss_fwd=2,
+    LAUNCHES = dict(ncl_to_c8=1, c8_to_ncl=1, pack_weights=1, pack_weights_pair=1, pack_weights_multi=1, rmsprop_step=1,
+                    osconv=1, oswgrad=2, bn_stats=2, bn_eval_coeffs=1, bn_apply=1, bn_bwd_reduce=2, bn_bwd_apply=1,
+                    bn_apply_fused=1, bn_bwd_top=1, bn_bwd_apply_fused=1, adain_fwd=1, adain_bwd=1, gram_loss_fwd=2,
                     gram_loss_bwd=1, rowstats=1)
 
     def __init__(self, ops, torch):
@@ -153,6 +154,15 @@ class KernelProfile:
             n = y8.numel() * 4.0
             mult = dict(bn_stats=1.0, bn_apply=1.75, bn_bwd_reduce=2.0, bn_bwd_apply=2.5)[name]
             return dict(bytes=n * mult)
+        if name == "bn_apply_fused":          # read y (fp32) [+ second branch], write bf16 c8 or fp32 NCL
+            n = args[0].y8.numel() * 4.0
+            return dict(bytes=n * ((2.0 if args[1] is not None else 1.0) + (1.0 if args[4] == L.OUT_NCL_F32 else 0.5)))
+        if name == "bn_bwd_top":               # read dout, y [+ y2], write d
+            n = args[1].y8.numel() * 4.0
+            return dict(bytes=n * (3.0 + (1.0 if args[2] is not None else 0.0)))
+        if name == "bn_bwd_apply_fused":       # read d, y, write dy (bf16)
+            n = args[0].numel() * 4.0
+            return dict(bytes=n * 2.5)
         return {}
 
     def install(self):

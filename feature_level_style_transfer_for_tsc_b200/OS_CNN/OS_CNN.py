@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ..functional import LayerSpec, StackSpec, os_stack
+from ..functional import LayerSpec, StackSpec, direct_grads, os_stack
 
 
 def calculate_mask_index(kernel_length_now, largest_kernel_lenght):
@@ -80,7 +80,7 @@ def _run_stack(layers, x, shortcut=None, final_relu=False):
         sc_spec = _bn_layer_spec(shortcut.geometry, shortcut.bn, False, zero_masked=False)
         params += _bn_params(shortcut.conv1d, shortcut.bn)
     spec = StackSpec(layers=specs, shortcut=sc_spec, final_relu=final_relu, engine=ops.get_engine("conv"),
-                     wgrad_engine=ops.get_engine("wgrad"), op_dtype=ops.op_dtype())
+                     wgrad_engine=ops.get_engine("wgrad"), op_dtype=ops.op_dtype(), direct_grads=direct_grads())
     if x.dtype != torch.float32:
         raise RuntimeError(f"OS-CNN input must be float32 (the reference casts with .float()), got {x.dtype}")
     return os_stack(spec, x.contiguous(), params)

@@ -43,6 +43,36 @@ class ConvEpilogue(ctypes.Structure):
 
 
 _ep = ctypes.POINTER(ConvEpilogue)
+PACK_MAX_LAYERS = 8
+
+
+class PackLayer(ctypes.Structure):
+    """tsc_pack_layer"""
+    _fields_ = [("W", ctypes.c_void_p), ("packed_fwd", ctypes.c_void_p), ("packed_dgrad", ctypes.c_void_p),
+                ("Cin", ctypes.c_int), ("Cout", ctypes.c_int), ("Kmax", ctypes.c_int), ("zero_masked", ctypes.c_int),
+                ("s_of_tap", ctypes.c_short * 96)]
+
+
+class PackBatch(ctypes.Structure):
+    """tsc_pack_batch"""
+    _fields_ = [("n", ctypes.c_int), ("pad_", ctypes.c_int), ("layer", PackLayer * PACK_MAX_LAYERS)]
+
+
+class BNBranch(ctypes.Structure):
+    """tsc_bn_branch"""
+    _fields_ = [("y_c8", ctypes.c_void_p), ("stat_partial", ctypes.c_void_p), ("gamma", ctypes.c_void_p),
+                ("beta", ctypes.c_void_p), ("running_mean", ctypes.c_void_p), ("running_var", ctypes.c_void_p),
+                ("momentum", ctypes.c_float), ("eps", ctypes.c_float), ("coef", ctypes.c_void_p)]
+
+
+class BNBwdBranch(ctypes.Structure):
+    """tsc_bn_bwd_branch"""
+    _fields_ = [("y_c8", ctypes.c_void_p), ("coef", ctypes.c_void_p), ("gamma", ctypes.c_void_p),
+                ("training", ctypes.c_int), ("red_partial", ctypes.c_void_p), ("dgamma", ctypes.c_void_p),
+                ("dbeta", ctypes.c_void_p), ("dbias", ctypes.c_void_p)]
+
+
+_bp, _bbp = ctypes.POINTER(BNBranch), ctypes.POINTER(BNBwdBranch)
 
 # name -> (restype, argtypes); must list every symbol declared in include/tsc_b200.h
 SIGNATURES = {
@@ -55,6 +85,11 @@ SIGNATURES = {
     "tsc_packed_weight_bytes": (_sz, [_i, _i, _i, _i, _i, _ip]),
     "tsc_pack_weights": (_i, [_i, _i, _p, _p, _i, _i, _i, _ip, _i, _p]),
     "tsc_pack_weights_pair": (_i, [_i, _p, _p, _p, _i, _i, _i, _ip, _i, _p]),
+    "tsc_pack_weights_multi": (_i, [_i, ctypes.POINTER(PackBatch), _p]),
+    "tsc_bn_apply_fused": (_i, [_bp, _bp, _i, _i, _p, _i, _i, _i, _i, _p]),
+    "tsc_bn_fused_splits": (_i, [_i, _i, _i]),
+    "tsc_bn_bwd_top": (_i, [_p, _bbp, _bbp, _i, _p, _i, _i, _i, _p]),
+    "tsc_bn_bwd_apply_fused": (_i, [_p, _bbp, _i, _i, _p, _i, _i, _i, _i, _p]),
     "tsc_rmsprop_step": (_i, [_p, _p, _p, ctypes.c_longlong, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_float),
                          _i, _f, _f, _f, _p]),
     "tsc_osconv_plan_bytes": (_sz, [_i, _i, _i, _i, _ip]),

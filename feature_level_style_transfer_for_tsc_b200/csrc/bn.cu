@@ -383,3 +383,353 @@ int tsc_bn_bwd_apply(const float* dz, const float* y, const float* mean, const f
 }
 
 }  // extern "C"
+
+// =====================================================================================================
+// Fused BatchNorm path of the tcgen05 engine: the statistics arrive as per-CTA partials from the conv
+// epilogue (tsc_osconv stat_partial / red_partial), and the merge runs in the prologue of the apply kernels,
+// so a training-mode layer costs two launches forward (conv, apply) and needs no separate statistics pass.
+// =====================================================================================================
+namespace tsc {
+
+static constexpr int BF_THREADS = 256;
+
+// sum of v over the block, result broadcast to all threads; sh: >= BF_THREADS/32 floats per slot (slots: 8 channels)
+__device__ __forceinline__ void block_sum8(float (&v)[8], float* sh /*[8][8]*/) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = warp_sum(v[j]);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sh[(threadIdx.x >> 5) * 8 + j] = v[j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < BF_THREADS / 32; ++w) a += sh[w * 8 + j];
+        v[j] = a;
+    }
+}
+
+// Coefficients of the 8 channels of chunk `ch` into coef_s[4][8] = (mean, invstd, scale, shift).
+// partial != NULL: merge the per-CTA (mean, M2) pairs (n_i = rows of CTA i) -> batch statistics (training);
+// partial == NULL: running statistics (eval mode).  `writer` blocks also store them to coef[4][Cp] and update the
+// running statistics (momentum, unbiased variance -- torch semantics).
+__device__ __forceinline__ void bn_branch_coeffs(const tsc_bn_branch& br, int ch, int C, int Cp, int n_part, int ltiles, int L,
+                                                 bool writer, float* coef_s, float* sh) {
+    float mean[8], var[8];
+    if (br.stat_partial) {
+        const float2* part = reinterpret_cast<const float2*>(br.stat_partial);
+        float sn = 0.f, sm[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sm[j] = 0.f;
+        for (int i = threadIdx.x; i < n_part; i += BF_THREADS) {
+            const float n = (float)min(128, L - (i % ltiles) * 128);
+            sn += n;
+            const float2* p = part + (size_t)i * Cp + ch * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sm[j] = fmaf(n, p[j].x, sm[j]);
+        }
+        float tmp[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tmp[j] = sm[j];
+        block_sum8(tmp, sh);
+        float nn[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) nn[j] = j == 0 ? sn : 0.f;
+        block_sum8(nn, sh);
+        const float N = nn[0];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mean[j] = tmp[j] / N;
+        float q[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) q[j] = 0.f;
+        for (int i = threadIdx.x; i < n_part; i += BF_THREADS) {
+            const float n = (float)min(128, L - (i % ltiles) * 128);
+            const float2* p = part + (size_t)i * Cp + ch * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float d = p[j].x - mean[j];
+                q[j] += p[j].y + n * d * d;
+            }
+        }
+        block_sum8(q, sh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) var[j] = q[j] / N;
+        if (writer && threadIdx.x < 8) {
+            const int j = threadIdx.x, c = ch * 8 + j;
+            if (c < C && br.running_mean && br.momentum > 0.f) {
+                float m = 0.f, v = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { if (k == j) { m = mean[k]; v = q[k]; } }
+                br.running_mean[c] = (1.f - br.momentum) * br.running_mean[c] + br.momentum * m;
+                br.running_var[c] = (1.f - br.momentum) * br.running_var[c] + br.momentum * (v / fmaxf(N - 1.f, 1.f));
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = ch * 8 + j;
+            mean[j] = c < C ? br.running_mean[c] : 0.f;
+            var[j] = c < C ? br.running_var[c] : 1.f;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        const int j = threadIdx.x, c = ch * 8 + j;
+        float m = 0.f, v = 1.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { if (k == j) { m = mean[k]; v = var[k]; } }
+        float invstd = 0.f, sc = 0.f, shf = 0.f;
+        if (c < C) {
+            invstd = 1.f / sqrtf(v + br.eps);
+            sc = br.gamma[c] * invstd;
+            shf = br.beta[c] - m * sc;
+        } else {
+            m = 0.f;
+        }
+        coef_s[0 * 8 + j] = m; coef_s[1 * 8 + j] = invstd; coef_s[2 * 8 + j] = sc; coef_s[3 * 8 + j] = shf;
+        if (writer && br.coef) {
+            br.coef[0 * Cp + c] = m; br.coef[1 * Cp + c] = invstd; br.coef[2 * Cp + c] = sc; br.coef[3 * Cp + c] = shf;
+        }
+    }
+    __syncthreads();
+}
+
+// grid (Cpc, S): block = one 8-channel chunk x one share of the (b, l) rows.
+template <int OUT_KIND>
+__global__ void __launch_bounds__(BF_THREADS) bn_apply_fused_kernel(const tsc_bn_branch a, const tsc_bn_branch b2, int two,
+                                                                     int n_part, int relu, void* __restrict__ out, int B,
+                                                                     int C, int Cpc, int L, int S) {
+    __shared__ float coef_a[32], coef_b[32], sh[64];
+    const int ch = blockIdx.x, sp = blockIdx.y;
+    const int ltiles = (L + 127) / 128;
+    bn_branch_coeffs(a, ch, C, Cpc * 8, n_part, ltiles, L, sp == 0, coef_a, sh);
+    if (two) bn_branch_coeffs(b2, ch, C, Cpc * 8, n_part, ltiles, L, sp == 0, coef_b, sh);
+    float sc[8], sf[8], sc2[8], sf2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sc[j] = coef_a[16 + j]; sf[j] = coef_a[24 + j];
+        sc2[j] = two ? coef_b[16 + j] : 0.f; sf2[j] = two ? coef_b[24 + j] : 0.f;
+    }
+    const long long rows = (long long)B * L;
+    const long long r0 = rows * sp / S, r1 = rows * (sp + 1) / S;
+    for (long long r = r0 + threadIdx.x; r < r1; r += BF_THREADS) {
+        const int bb = (int)(r / L), l = (int)(r % L);
+        const long long i = ((long long)bb * Cpc + ch) * L + l;
+        Row8<float> v, o;
+        v.load(a.y_c8 + i * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o.v[j] = fmaf(v.v[j], sc[j], sf[j]);
+        if (two) {
+            Row8<float> w;
+            w.load(b2.y_c8 + i * 8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o.v[j] += fmaf(w.v[j], sc2[j], sf2[j]);
+        }
+        if (relu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o.v[j] = fmaxf(o.v[j], 0.f);
+        }
+        if (OUT_KIND == TSC_OUT_C8_F32) {
+            o.store(reinterpret_cast<float*>(out) + i * 8);
+        } else if (OUT_KIND == TSC_OUT_C8_BF16) {
+            Row8<__nv_bfloat16> ob;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ob.v[j] = o.v[j];
+            ob.store(reinterpret_cast<__nv_bfloat16*>(out) + i * 8);
+        } else {
+            float* dst = reinterpret_cast<float*>(out);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = ch * 8 + j;
+                if (c < C) dst[((long long)bb * C + c) * L + l] = o.v[j];
+            }
+        }
+    }
+}
+
+// Top of a stack: the incoming gradient is NCL fp32.  d = dout * [z > 0] (z = scale*y + shift [+ second branch]) is
+// written as c8 fp32 and the per-block partial sums (S1, S2) of each branch go to red_partial[S][Cp][2].
+__global__ void __launch_bounds__(BF_THREADS) bn_bwd_top_kernel(const float* __restrict__ dout, const tsc_bn_bwd_branch a,
+                                                                 const tsc_bn_bwd_branch b2, int two, int relu,
+                                                                 float* __restrict__ d_c8, int B, int C, int Cpc, int L,
+                                                                 int S) {
+    __shared__ float sh[64];
+    const int ch = blockIdx.x, sp = blockIdx.y, Cp = Cpc * 8;
+    float mean[8], invstd[8], sc[8], sf[8], mean2[8], invstd2[8], sc2[8], sf2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = ch * 8 + j;
+        mean[j] = a.coef[c]; invstd[j] = a.coef[Cp + c]; sc[j] = a.coef[2 * Cp + c]; sf[j] = a.coef[3 * Cp + c];
+        mean2[j] = two ? b2.coef[c] : 0.f; invstd2[j] = two ? b2.coef[Cp + c] : 0.f;
+        sc2[j] = two ? b2.coef[2 * Cp + c] : 0.f; sf2[j] = two ? b2.coef[3 * Cp + c] : 0.f;
+    }
+    float s1[8], s2[8], s2b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; s2b[j] = 0.f; }
+    const long long rows = (long long)B * L;
+    const long long r0 = rows * sp / S, r1 = rows * (sp + 1) / S;
+    for (long long r = r0 + threadIdx.x; r < r1; r += BF_THREADS) {
+        const int bb = (int)(r / L), l = (int)(r % L);
+        const long long i = ((long long)bb * Cpc + ch) * L + l;
+        Row8<float> y, y2, d;
+        y.load(a.y_c8 + i * 8);
+        if (two) y2.load(b2.y_c8 + i * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = ch * 8 + j;
+            float g = c < C ? __ldg(dout + ((long long)bb * C + c) * L + l) : 0.f;
+            if (relu) {
+                float z = fmaf(y.v[j], sc[j], sf[j]);
+                if (two) z += fmaf(y2.v[j], sc2[j], sf2[j]);
+                if (!(z > 0.f)) g = 0.f;
+            }
+            d.v[j] = g;
+            s1[j] += g;
+            s2[j] = fmaf(g, (y.v[j] - mean[j]) * invstd[j], s2[j]);
+            if (two) s2b[j] = fmaf(g, (y2.v[j] - mean2[j]) * invstd2[j], s2b[j]);
+        }
+        d.store(d_c8 + i * 8);
+    }
+    block_sum8(s1, sh);
+    block_sum8(s2, sh);
+    if (two) block_sum8(s2b, sh);
+    if (threadIdx.x < 8) {
+        const int j = threadIdx.x, c = ch * 8 + j;
+        float v1 = 0.f, v2 = 0.f, v3 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { if (k == j) { v1 = s1[k]; v2 = s2[k]; v3 = s2b[k]; } }
+        reinterpret_cast<float2*>(a.red_partial)[(size_t)sp * Cp + c] = make_float2(v1, v2);
+        if (two) reinterpret_cast<float2*>(b2.red_partial)[(size_t)sp * Cp + c] = make_float2(v1, v3);
+    }
+}
+
+// dy = gamma*invstd*(d - S1/N - yhat*S2/N) (training) | gamma*invstd*d (eval), written as c8 bf16/fp32; (S1, S2) are
+// summed from red_partial[n_part][Cp][2] in the prologue (fixed order).  Split 0 also writes the parameter
+// gradients dgamma = S2, dbeta = S1, dbias = 0 (training) | gamma*invstd*S1 (eval), adding when accumulate != 0.
+template <typename T>
+__global__ void __launch_bounds__(BF_THREADS) bn_bwd_apply_fused_kernel(const float* __restrict__ d_c8, const tsc_bn_bwd_branch a,
+                                                                         int n_part, int accumulate, T* __restrict__ dy,
+                                                                         int B, int C, int Cpc, int L, int S) {
+    __shared__ float sh[64];
+    const int ch = blockIdx.x, sp = blockIdx.y, Cp = Cpc * 8;
+    float s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+    const float2* part = reinterpret_cast<const float2*>(a.red_partial);
+    for (int i = threadIdx.x; i < n_part; i += BF_THREADS) {
+        const float2* p = part + (size_t)i * Cp + ch * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s1[j] += p[j].x; s2[j] += p[j].y; }
+    }
+    block_sum8(s1, sh);
+    block_sum8(s2, sh);
+    float mean[8], invstd[8], g[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = ch * 8 + j;
+        mean[j] = a.coef[c]; invstd[j] = a.coef[Cp + c];
+        g[j] = c < C ? a.gamma[c] * invstd[j] : 0.f;
+    }
+    if (sp == 0 && threadIdx.x < 8) {
+        const int j = threadIdx.x, c = ch * 8 + j;
+        if (c < C) {
+            float v1 = 0.f, v2 = 0.f, gg = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { if (k == j) { v1 = s1[k]; v2 = s2[k]; gg = g[k]; } }
+            const float db = a.training ? 0.f : gg * v1;
+            if (a.dgamma) a.dgamma[c] = accumulate ? a.dgamma[c] + v2 : v2;
+            if (a.dbeta) a.dbeta[c] = accumulate ? a.dbeta[c] + v1 : v1;
+            if (a.dbias) a.dbias[c] = accumulate ? a.dbias[c] + db : db;
+        }
+    }
+    const float inv_n = 1.f / ((float)B * (float)L);
+    const long long rows = (long long)B * L;
+    const long long r0 = rows * sp / S, r1 = rows * (sp + 1) / S;
+    for (long long r = r0 + threadIdx.x; r < r1; r += BF_THREADS) {
+        const int bb = (int)(r / L), l = (int)(r % L);
+        const long long i = ((long long)bb * Cpc + ch) * L + l;
+        Row8<float> d, y;
+        Row8<T> o;
+        d.load(d_c8 + i * 8);
+        if (a.training) y.load(a.y_c8 + i * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float rr;
+            if (a.training) {
+                const float yhat = (y.v[j] - mean[j]) * invstd[j];
+                rr = g[j] * (d.v[j] - s1[j] * inv_n - yhat * s2[j] * inv_n);
+            } else {
+                rr = g[j] * d.v[j];
+            }
+            o.v[j] = rr;
+        }
+        o.store(dy + i * 8);
+    }
+}
+
+}  // namespace tsc
+
+extern "C" {
+
+int tsc_bn_fused_splits(int B, int C, int L) { return tsc::bn_splits(B, tsc::pad16(C) / 8, L); }
+
+int tsc_bn_apply_fused(const tsc_bn_branch* a, const tsc_bn_branch* b, int n_part, int relu, void* out, int out_kind, int B,
+                       int C, int L, tsc_stream_t stream) {
+    using namespace tsc;
+    TSC_REQUIRE(a && a->y_c8 && a->gamma && a->beta && out, "NULL argument");
+    TSC_REQUIRE(a->stat_partial || (a->running_mean && a->running_var), "eval-mode branch needs running statistics");
+    TSC_REQUIRE(!b || (b->y_c8 && b->gamma && b->beta && (b->stat_partial || (b->running_mean && b->running_var))),
+                "second branch incomplete");
+    TSC_REQUIRE(B > 0 && C > 0 && L > 0, "bad shape [%d,%d,%d]", B, C, L);
+    TSC_REQUIRE(n_part == B * cdiv(L, 128), "n_part=%d does not match B*ceil(L/128)=%d", n_part, B * cdiv(L, 128));
+    const int Cpc = pad16(C) / 8, S = bn_splits(B, Cpc, L);
+    const tsc_bn_branch bb = b ? *b : *a;
+    cudaStream_t cs = (cudaStream_t)stream;
+    dim3 grid(Cpc, S);
+    switch (out_kind) {
+        case TSC_OUT_C8_F32: bn_apply_fused_kernel<TSC_OUT_C8_F32><<<grid, BF_THREADS, 0, cs>>>(*a, bb, b != nullptr, n_part, relu, out, B, C, Cpc, L, S); break;
+        case TSC_OUT_C8_BF16: bn_apply_fused_kernel<TSC_OUT_C8_BF16><<<grid, BF_THREADS, 0, cs>>>(*a, bb, b != nullptr, n_part, relu, out, B, C, Cpc, L, S); break;
+        case TSC_OUT_NCL_F32: bn_apply_fused_kernel<TSC_OUT_NCL_F32><<<grid, BF_THREADS, 0, cs>>>(*a, bb, b != nullptr, n_part, relu, out, B, C, Cpc, L, S); break;
+        default: TSC_REQUIRE(false, "bad out_kind %d", out_kind);
+    }
+    TSC_LAUNCH_CHECK();
+    return 0;
+}
+
+int tsc_bn_bwd_top(const float* dout_ncl, const tsc_bn_bwd_branch* a, const tsc_bn_bwd_branch* b, int relu, float* d_c8,
+                   int B, int C, int L, tsc_stream_t stream) {
+    using namespace tsc;
+    TSC_REQUIRE(dout_ncl && a && a->y_c8 && a->coef && a->red_partial && d_c8, "NULL argument");
+    TSC_REQUIRE(!b || (b->y_c8 && b->coef && b->red_partial), "second branch incomplete");
+    TSC_REQUIRE(B > 0 && C > 0 && L > 0, "bad shape [%d,%d,%d]", B, C, L);
+    const int Cpc = pad16(C) / 8, S = bn_splits(B, Cpc, L);
+    const tsc_bn_bwd_branch bb = b ? *b : *a;
+    bn_bwd_top_kernel<<<dim3(Cpc, S), BF_THREADS, 0, (cudaStream_t)stream>>>(dout_ncl, *a, bb, b != nullptr, relu, d_c8, B, C,
+                                                                            Cpc, L, S);
+    TSC_LAUNCH_CHECK();
+    return 0;
+}
+
+int tsc_bn_bwd_apply_fused(const float* d_c8, const tsc_bn_bwd_branch* a, int n_part, int accumulate, void* dy_c8,
+                           int dy_dtype, int B, int C, int L, tsc_stream_t stream) {
+    using namespace tsc;
+    TSC_REQUIRE(d_c8 && a && a->coef && a->red_partial && a->gamma && dy_c8, "NULL argument");
+    TSC_REQUIRE(!a->training || a->y_c8, "training-mode backward needs y");
+    TSC_REQUIRE(B > 0 && C > 0 && L > 0 && n_part > 0, "bad shape [%d,%d,%d] n_part=%d", B, C, L, n_part);
+    const int Cpc = pad16(C) / 8, S = bn_splits(B, Cpc, L);
+    cudaStream_t cs = (cudaStream_t)stream;
+    dim3 grid(Cpc, S);
+    if (dy_dtype == TSC_BF16)
+        bn_bwd_apply_fused_kernel<__nv_bfloat16><<<grid, BF_THREADS, 0, cs>>>(d_c8, *a, n_part, accumulate, (__nv_bfloat16*)dy_c8, B, C, Cpc, L, S);
+    else if (dy_dtype == TSC_F32)
+        bn_bwd_apply_fused_kernel<float><<<grid, BF_THREADS, 0, cs>>>(d_c8, *a, n_part, accumulate, (float*)dy_c8, B, C, Cpc, L, S);
+    else
+        TSC_REQUIRE(false, "bad dtype %d", dy_dtype);
+    TSC_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

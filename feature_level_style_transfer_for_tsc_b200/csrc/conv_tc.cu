@@ -315,17 +315,35 @@ osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const ConvTcParams p)
                     }
                 }
             }
-            if (do_stat || do_red) {
+            if (do_red) {
                 float s1[32], s2[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const float x = valid ? v[i] : 0.f;
                     s1[i] = x;
-                    s2[i] = do_red ? x * yh[i] : x * x;
+                    s2[i] = x * yh[i];
                 }
                 const float a = warp_colsum32(s1, lane);
                 const float c = warp_colsum32(s2, lane);
                 if (c0 + lane < np) wstat[q * np + c0 + lane] = make_float2(a, c);
+            } else if (do_stat) {
+                // two-pass per warp: column means first, then the centred sums of squares (no cancellation even when
+                // |mean| >> std); lane j ends up with (sum, M2) of column c0 + j over this warp's valid rows
+                const int nw = max(0, min(32, min(128, p.L - l0) - q * 32));
+                float s1[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) s1[i] = valid ? v[i] : 0.f;
+                const float a = warp_colsum32(s1, lane);
+                const float mean_l = nw > 0 ? a / (float)nw : 0.f;
+                float s2[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float m = __shfl_sync(0xffffffffu, mean_l, i);
+                    const float dlt = valid ? v[i] - m : 0.f;
+                    s2[i] = dlt * dlt;
+                }
+                const float c = warp_colsum32(s2, lane);
+                if (c0 + lane < np) wstat[q * np + c0 + lane] = make_float2(mean_l, c);
             }
         }
         if (do_stat || do_red) {
@@ -338,16 +356,14 @@ osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const ConvTcParams p)
                     for (int w = 0; w < 4; ++w) { const float2 t = wstat[w * np + c]; a += t.x; d += t.y; }
                     reinterpret_cast<float2*>(p.red_partial)[(size_t)blockIdx.x * np + c] = make_float2(a, d);
                 } else {
-                    // per-warp (n, sum, sumsq) -> (mean, M2), then Chan merges of the four warps
+                    // Chan merges of the four warps' (n, mean, M2)
                     float n = 0.f, mean = 0.f, m2 = 0.f;
 #pragma unroll
                     for (int w = 0; w < 4; ++w) {
                         const int nw = max(0, min(32, rows_cta - w * 32));
                         if (nw > 0) {
                             const float2 t = wstat[w * np + c];
-                            const float mw = t.x / (float)nw;
-                            const float qw = fmaxf(t.y - t.x * mw, 0.f);
-                            welford_merge(n, mean, m2, (float)nw, mw, qw);
+                            welford_merge(n, mean, m2, (float)nw, t.x, t.y);
                         }
                     }
                     reinterpret_cast<float2*>(p.stat_partial)[(size_t)blockIdx.x * np + c] = make_float2(mean, m2);

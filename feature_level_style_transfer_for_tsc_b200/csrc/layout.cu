@@ -242,3 +242,158 @@ extern "C" int tsc_pack_weights_pair(int dtype, float* W, void* packed_fwd, void
     TSC_LAUNCH_CHECK();
     return 0;
 }
+
+// =====================================================================================================
+// Kernel-bank packing for a whole stack of layers in ONE launch (tsc_pack_weights_multi).
+// Block = (layer, chunk of 8 out channels, pair of in-channel chunks = 16 in channels): it reads its
+// [8][16][Kmax] slab of W with coalesced rows, masks W in place, and emits the 16 B rows of both packed
+// layouts: forward blob_t[kc][n][8 ci] and dgrad blob_t'[kc = co chunk][n = ci][8 co].
+// The per-tap geometry (live suffix, blob offsets) is recomputed per block from s(t) exactly as
+// build_tap_table does on the host (stable order by suffix start, widest tap first).
+// =====================================================================================================
+namespace tsc {
+
+struct PackTaps {
+    short n_lo_f[TSC_MAX_TAPS];   // forward: first stored out channel of conv tap t (multiple of 16), -1 = dead
+    short kc_lo_d[TSC_MAX_TAPS];  // dgrad  : first stored out-channel chunk of conv tap t' (even), -1 = dead
+    int off_f[TSC_MAX_TAPS];      // blob offsets in 16 B rows
+    int off_d[TSC_MAX_TAPS];
+};
+
+__device__ void pack_build_taps(const tsc_pack_layer& ly, PackTaps* pt) {
+    const int Kmax = ly.Kmax, Cout = ly.Cout;
+    const int np_f = (ly.Cout + 15) & ~15, kc_f = ((ly.Cin + 15) & ~15) / 8;     // forward: N = out, K = in
+    const int np_d = (ly.Cin + 15) & ~15, kc_d = ((ly.Cout + 15) & ~15) / 8;     // dgrad  : N = in,  K = out
+    const int t = threadIdx.x;
+    if (t < Kmax) {
+        const int sf = ly.s_of_tap[t];
+        pt->n_lo_f[t] = sf >= Cout ? -1 : (short)((sf / 16) * 16);
+        const int sd = ly.s_of_tap[Kmax - 1 - t];
+        pt->kc_lo_d[t] = sd >= Cout ? -1 : (short)((sd / 16) * 2);
+    }
+    __syncthreads();
+    if (t < Kmax) {
+        // forward: the first tap in (n_lo, t) order is widened to n_lo = 0 (it initialises every accumulator column)
+        int first = -1;
+        for (int u = 0; u < Kmax; ++u)
+            if (pt->n_lo_f[u] >= 0 && (first < 0 || pt->n_lo_f[u] < pt->n_lo_f[first])) first = u;
+        int off = 0;
+        const int mine = pt->n_lo_f[t];
+        if (mine >= 0) {
+            const int key = t == first ? -1 : mine;
+            for (int u = 0; u < Kmax; ++u) {
+                const int nu = pt->n_lo_f[u];
+                if (nu < 0 || u == t) continue;
+                const int ku = u == first ? -1 : nu;
+                if (ku < key || (ku == key && u < t)) off += kc_f * (np_f - (u == first ? 0 : nu));
+            }
+        }
+        pt->off_f[t] = off;
+        int offd = 0;
+        const int md = pt->kc_lo_d[t];
+        if (md >= 0) {
+            for (int u = 0; u < Kmax; ++u) {
+                const int ku = pt->kc_lo_d[u];
+                if (ku < 0 || u == t) continue;
+                if (ku < md || (ku == md && u < t)) offd += (kc_d - ku) * np_d;
+            }
+        }
+        pt->off_d[t] = offd;
+    }
+    __syncthreads();
+    if (t < Kmax) {
+        int first = -1;
+        for (int u = 0; u < Kmax; ++u)
+            if (pt->n_lo_f[u] >= 0 && (first < 0 || pt->n_lo_f[u] < pt->n_lo_f[first])) first = u;
+        if (t == first) pt->n_lo_f[t] = 0;
+    }
+    __syncthreads();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) pack_multi_kernel(const __grid_constant__ tsc_pack_batch batch) {
+    extern __shared__ float wsm[];                    // [8][16][Kmax]
+    __shared__ PackTaps pt;
+    const tsc_pack_layer& ly = batch.layer[blockIdx.y];
+    const int Cin = ly.Cin, Cout = ly.Cout, Kmax = ly.Kmax;
+    const int np_f = (Cout + 15) & ~15, cin_p = (Cin + 15) & ~15;
+    const int n_cc = np_f / 8, n_kp = cin_p / 16;
+    if ((int)blockIdx.x >= n_cc * n_kp) return;
+    const int cc = blockIdx.x / n_kp, kp = blockIdx.x % n_kp;
+    const int co0 = cc * 8, ci0 = kp * 16;
+    pack_build_taps(ly, &pt);
+    // ---- load (and mask in place) ----
+    float* W = ly.W;
+    const int slab = 16 * Kmax;
+    for (int e = threadIdx.x; e < 8 * slab; e += 256) {
+        const int r = e / slab, q = e % slab;
+        const int ci = ci0 + q / Kmax, t = q % Kmax, co = co0 + r;
+        float v = 0.f;
+        if (co < Cout && ci < Cin) {
+            float* p = W + ((size_t)co * Cin + ci) * Kmax + t;
+            if (co >= ly.s_of_tap[t]) v = *p;
+            else if (ly.zero_masked) *p = 0.f;
+        }
+        wsm[e] = v;
+    }
+    __syncthreads();
+    T* pf = reinterpret_cast<T*>(ly.packed_fwd);
+    T* pd = reinterpret_cast<T*>(ly.packed_dgrad);
+    const int kc_f = cin_p / 8, np_d = cin_p;
+    // ---- forward rows: (t, k = 0..1 chunk of this pair, r = out channel) -> 8 in channels ----
+    for (int e = threadIdx.x; e < Kmax * 16; e += 256) {
+        const int t = e / 16, k = (e >> 3) & 1, r = e & 7;
+        const int n_lo = pt.n_lo_f[t];
+        const int co = co0 + r;
+        if (n_lo < 0 || co < n_lo) continue;
+        const int nt = np_f - n_lo;
+        Row8<T> row;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) row.v[j] = wsm[(r * 16 + k * 8 + j) * Kmax + t];
+        row.store(pf + ((size_t)pt.off_f[t] + (size_t)(kp * 2 + k) * nt + (co - n_lo)) * 8);
+    }
+    (void)kc_f;
+    // ---- dgrad rows: (t', n = in channel of this pair) -> the 8 out channels of this chunk ----
+    if (pd) {
+        for (int e = threadIdx.x; e < Kmax * 16; e += 256) {
+            const int t = e / 16, q = e & 15;
+            const int kc_lo = pt.kc_lo_d[t];
+            if (kc_lo < 0 || cc < kc_lo) continue;
+            const int wt = Kmax - 1 - t;
+            Row8<T> row;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) row.v[j] = wsm[(j * 16 + q) * Kmax + wt];
+            row.store(pd + ((size_t)pt.off_d[t] + (size_t)(cc - kc_lo) * np_d + (ci0 + q)) * 8);
+        }
+    }
+}
+
+}  // namespace tsc
+
+extern "C" int tsc_pack_weights_multi(int dtype, const tsc_pack_batch* batch, tsc_stream_t stream) {
+    using namespace tsc;
+    TSC_REQUIRE(batch && batch->n >= 1 && batch->n <= TSC_PACK_MAX_LAYERS, "bad layer count");
+    int max_blocks = 0, max_k = 0;
+    for (int i = 0; i < batch->n; ++i) {
+        const tsc_pack_layer& ly = batch->layer[i];
+        TSC_REQUIRE(ly.W && ly.packed_fwd, "layer %d: NULL tensor", i);
+        TSC_REQUIRE(ly.Kmax >= 1 && ly.Kmax <= TSC_MAX_TAPS && ly.Cin >= 1 && ly.Cin <= TSC_MAX_CHANNELS && ly.Cout >= 1 &&
+                        ly.Cout <= TSC_MAX_CHANNELS, "layer %d: bad geometry", i);
+        max_blocks = max(max_blocks, (pad16(ly.Cout) / 8) * (pad16(ly.Cin) / 16));
+        max_k = max(max_k, ly.Kmax);
+    }
+    const int smem = 8 * 16 * max_k * (int)sizeof(float);
+    dim3 grid(max_blocks, batch->n);
+    cudaStream_t cs = (cudaStream_t)stream;
+    if (dtype == TSC_BF16) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(pack_multi_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        pack_multi_kernel<__nv_bfloat16><<<grid, 256, smem, cs>>>(*batch);
+    } else if (dtype == TSC_F32) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(pack_multi_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        pack_multi_kernel<float><<<grid, 256, smem, cs>>>(*batch);
+    } else {
+        TSC_REQUIRE(false, "bad dtype %d", dtype);
+    }
+    TSC_LAUNCH_CHECK();
+    return 0;
+}

@@ -45,11 +45,158 @@ class StackSpec:
     engine: int                        # conv (forward + dgrad) engine
     wgrad_engine: int
     op_dtype: int                      # operand dtype of the stack (bf16 for the tensor-core engine)
+    direct_grads: bool = False         # backward adds parameter gradients straight into the existing .grad buffers
 
 
 class _Saved:
     """Per-call buffers kept for backward (all read-only after forward)."""
-    __slots__ = ("x_ops", "ys", "coeffs", "wd", "y_r", "co_r", "wd_r", "B", "Ln")
+    __slots__ = ("x_ops", "ys", "coeffs", "wd", "y_r", "co_r", "wd_r", "B", "Ln", "fused")
+
+
+_DIRECT_GRADS = False
+FUSED_PATH = True          # debugging switch: False runs the tcgen05 engine through the unfused BatchNorm kernels
+
+
+def set_direct_grads(on: bool) -> None:
+    """When on, the backward of ``os_stack`` adds the gradients of parameters that already own a ``.grad`` buffer
+    (e.g. views of a flat data-parallel bucket) in place inside the kernels and reports ``None`` to autograd for them:
+    the wgrad / BatchNorm-backward kernels write the collective's operand directly and no ``AccumulateGrad`` add
+    kernels run.  Off (the default) keeps plain autograd semantics (``torch.autograd.grad``, hooks)."""
+    global _DIRECT_GRADS
+    _DIRECT_GRADS = bool(on)
+
+
+def direct_grads() -> bool:
+    return _DIRECT_GRADS
+
+
+def _fused_forward(spec: StackSpec, sv: "_Saved", x: torch.Tensor, params, need_dgrad_first: bool):
+    """tcgen05 engine: conv (+ per-CTA BatchNorm statistics in its epilogue) -> fused merge + apply, one pack launch."""
+    eng, dt = spec.engine, spec.op_dtype
+    B, _, Ln = x.shape
+    nl = len(spec.layers)
+    ncta = ops.n_conv_ctas(B, Ln)
+    dev = x.device
+    h = ops.ncl_to_c8(x, dt)
+    jobs = []
+    for i, ls in enumerate(spec.layers):
+        jobs.append((ls.geom, params[4 * i], ls.zero_masked, i > 0 or need_dgrad_first))
+    if spec.shortcut is not None:
+        jobs.append((spec.shortcut.geom, params[4 * nl], False, need_dgrad_first))
+    with torch.no_grad():
+        packs = ops.pack_weights_multi(jobs, dt)
+
+    def branch(ls, y, part, gamma, beta):
+        coef = torch.empty((4, ls.geom.cout_p), device=dev, dtype=torch.float32)
+        track = ls.training and ls.momentum > 0
+        rm = ls.running_mean if (track or not ls.training) else None
+        rv = ls.running_var if (track or not ls.training) else None
+        return ops.BNLayerFwd(y, part, gamma, beta, rm, rv, ls.momentum if ls.training else 0.0, ls.eps, coef)
+
+    out = None
+    for i, ls in enumerate(spec.layers):
+        W, bias, gamma, beta = params[4 * i: 4 * i + 4]
+        g = ls.geom
+        wf, wd = packs[i]
+        sv.wd.append(wd)
+        part = torch.empty((ncta, g.cout_p, 2), device=dev, dtype=torch.float32) if ls.training else None
+        y = ops.osconv(eng, L.DIR_FWD, g, h, wf, bias, stat_partial=part)
+        br = branch(ls, y, part, gamma, beta)
+        sv.x_ops.append(h)
+        sv.ys.append(y)
+        sv.coeffs.append(br.coef)
+        if i < nl - 1:
+            h = ops.bn_apply_fused(br, None, g.cout, ls.relu, L.OUT_C8_BF16)
+        elif spec.shortcut is None:
+            out = ops.bn_apply_fused(br, None, g.cout, ls.relu, L.OUT_NCL_F32)
+        else:
+            sc = spec.shortcut
+            Wr, br_, gr, betar = params[4 * nl: 4 * nl + 4]
+            wfr, sv.wd_r = packs[nl]
+            part_r = torch.empty((ncta, sc.geom.cout_p, 2), device=dev, dtype=torch.float32) if sc.training else None
+            y_r = ops.osconv(eng, L.DIR_FWD, sc.geom, sv.x_ops[0], wfr, br_, stat_partial=part_r)
+            brr = branch(sc, y_r, part_r, gr, betar)
+            sv.y_r, sv.co_r = y_r, brr.coef
+            out = ops.bn_apply_fused(br, brr, g.cout, spec.final_relu, L.OUT_NCL_F32)
+    return out
+
+
+def _fused_backward(spec: StackSpec, sv: "_Saved", params, dout: torch.Tensor, x_requires_grad: bool):
+    eng, dt = spec.engine, spec.op_dtype
+    nl = len(spec.layers)
+    B, Ln = sv.B, sv.Ln
+    dev = dout.device
+    ncta = ops.n_conv_ctas(B, Ln)
+    direct = spec.direct_grads and all(p.grad is not None and p.grad.is_contiguous() for p in params)
+    grads: List[Optional[torch.Tensor]] = [None] * len(params)
+    zero_bias = None
+
+    def param_grad_targets(k, C, training):
+        """(dgamma, dbeta, dbias) buffers for parameter group k (index of W in params)."""
+        nonlocal zero_bias
+        if direct:
+            return params[k + 2].grad, params[k + 3].grad, (None if training else params[k + 1].grad)
+        dg = torch.empty(C, device=dev, dtype=torch.float32)
+        db = torch.empty(C, device=dev, dtype=torch.float32)
+        if training:
+            if zero_bias is None:       # d(conv bias) behind a train-mode BN is identically zero
+                zero_bias = torch.zeros(max(p.numel() for p in params[1::4]), device=dev, dtype=torch.float32)
+            dbias = zero_bias[:C]
+            grads[k + 1] = dbias
+            dbias_buf = None
+        else:
+            dbias_buf = torch.empty(C, device=dev, dtype=torch.float32)
+            grads[k + 1] = dbias_buf
+        grads[k + 2], grads[k + 3] = dg, db
+        return dg, db, dbias_buf
+
+    def wgrad(k, g, dy, x_op):
+        if direct:
+            ops.oswgrad(spec.wgrad_engine, g, dy, x_op, out=params[k].grad, accumulate=True)
+        else:
+            grads[k] = ops.oswgrad(spec.wgrad_engine, g, dy, x_op)
+
+    last = spec.layers[-1]
+    S_top = ops.bn_fused_splits(B, last.geom.cout, Ln)
+    red = torch.empty((S_top, last.geom.cout_p, 2), device=dev, dtype=torch.float32)
+    a_top = ops.BNLayerBwd(sv.ys[-1], sv.coeffs[-1], params[4 * (nl - 1) + 2], last.training, red)
+    dx_short = None
+    if spec.shortcut is not None:
+        sc = spec.shortcut
+        red_r = torch.empty((S_top, sc.geom.cout_p, 2), device=dev, dtype=torch.float32)
+        b_top = ops.BNLayerBwd(sv.y_r, sv.co_r, params[4 * nl + 2], sc.training, red_r)
+        d = ops.bn_bwd_top(dout, a_top, b_top, spec.final_relu)
+        b_top.dgamma, b_top.dbeta, b_top.dbias = param_grad_targets(4 * nl, sc.geom.cout, sc.training)
+        dy_r = ops.bn_bwd_apply_fused(d, b_top, S_top, sc.geom.cout, dt, direct)
+        wgrad(4 * nl, sc.geom, dy_r, sv.x_ops[0])
+        if x_requires_grad:
+            dx_short = ops.osconv(eng, L.DIR_DGRAD, sc.geom, dy_r, sv.wd_r, None)
+    else:
+        d = ops.bn_bwd_top(dout, a_top, None, last.relu)
+    cur, n_part = a_top, S_top
+    dz = None
+    for i in range(nl - 1, -1, -1):
+        ls = spec.layers[i]
+        g = ls.geom
+        cur.dgamma, cur.dbeta, cur.dbias = param_grad_targets(4 * i, g.cout, ls.training)
+        dy = ops.bn_bwd_apply_fused(d, cur, n_part, g.cout, dt, direct)
+        wgrad(4 * i, g, dy, sv.x_ops[i])
+        if i > 0:
+            below = spec.layers[i - 1]
+            co = sv.coeffs[i - 1]
+            red_b = torch.empty((ncta, below.geom.cout_p, 2), device=dev, dtype=torch.float32)
+            mask = (sv.ys[i - 1], co[2] if below.relu else None, co[3] if below.relu else None, co[0], co[1])
+            d = ops.osconv(eng, L.DIR_DGRAD, g, dy, sv.wd[i], None, mask=mask, red_partial=red_b)
+            cur = ops.BNLayerBwd(sv.ys[i - 1], co, params[4 * (i - 1) + 2], below.training, red_b)
+            n_part = ncta
+        elif x_requires_grad:
+            dz = ops.osconv(eng, L.DIR_DGRAD, g, dy, sv.wd[0], None)
+    dx = None
+    if x_requires_grad:
+        if dx_short is not None:
+            dz = dz + dx_short
+        dx = ops.c8_to_ncl(dz, spec.layers[0].geom.cin)
+    return dx, grads
 
 
 class OSStackFunction(torch.autograd.Function):
@@ -64,7 +211,14 @@ class OSStackFunction(torch.autograd.Function):
         sv = _Saved()
         sv.B, sv.Ln = B, Ln
         sv.x_ops, sv.ys, sv.coeffs, sv.wd = [], [], [], []
+        sv.fused = FUSED_PATH and eng == L.ENGINE_TCGEN05 and dt == L.TSC_BF16
         nl = len(spec.layers)
+        if sv.fused:
+            out = _fused_forward(spec, sv, x, params, x.requires_grad)
+            ctx.spec, ctx.sv = spec, sv
+            ctx.save_for_backward(*params)
+            ctx.x_requires_grad = x.requires_grad
+            return out
         h = ops.ncl_to_c8(x, dt)
         x_op = h
         out = None
@@ -114,6 +268,9 @@ class OSStackFunction(torch.autograd.Function):
         dt = spec.op_dtype
         nl = len(spec.layers)
         dout = dout.contiguous().float()
+        if sv.fused:
+            dx, grads = _fused_backward(spec, sv, params, dout, ctx.x_requires_grad)
+            return (None, dx, *grads)
         dz = ops.ncl_to_c8(dout, L.TSC_F32)
         grads: List[Optional[torch.Tensor]] = [None] * len(params)
         dx_short = None

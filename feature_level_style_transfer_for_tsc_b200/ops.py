@@ -204,6 +204,33 @@ def pack_weights_pair(g: BankGeometry, W: torch.Tensor, dt: int, zero_masked: bo
     return pf, pd
 
 
+def pack_weights_multi(layers, dt: int):
+    """layers: [(geometry, W, zero_masked, want_dgrad)] -> [(packed_fwd, packed_dgrad | None)], one launch per
+    L.PACK_MAX_LAYERS layers (forward pack, dgrad pack and the in-place masking of every W)."""
+    esz = 2 if dt == L.TSC_BF16 else 4
+    out = []
+    for i0 in range(0, len(layers), L.PACK_MAX_LAYERS):
+        grp = layers[i0:i0 + L.PACK_MAX_LAYERS]
+        batch = L.PackBatch()
+        batch.n = len(grp)
+        for k, (g, W, zero_masked, want_dgrad) in enumerate(grp):
+            _req(W, name="weight")
+            if tuple(W.shape) != (g.cout, g.cin, g.kmax):
+                raise RuntimeError(f"weight shape {tuple(W.shape)} != {(g.cout, g.cin, g.kmax)}")
+            pf = torch.empty(g.packed_bytes(L.DIR_FWD, dt) // esz, device=W.device, dtype=torch_dtype(dt))
+            pd = (torch.empty(g.packed_bytes(L.DIR_DGRAD, dt) // esz, device=W.device, dtype=torch_dtype(dt))
+                  if want_dgrad else None)
+            ly = batch.layer[k]
+            ly.W, ly.packed_fwd = W.data_ptr(), pf.data_ptr()
+            ly.packed_dgrad = pd.data_ptr() if pd is not None else None
+            ly.Cin, ly.Cout, ly.Kmax, ly.zero_masked = g.cin, g.cout, g.kmax, 1 if zero_masked else 0
+            for t, sv in enumerate(g.s_of_tap):
+                ly.s_of_tap[t] = min(int(sv), 32767)
+            out.append((pf, pd))
+        L.check(L.load().tsc_pack_weights_multi(dt, ctypes.byref(batch), _stream()), "tsc_pack_weights_multi")
+    return out
+
+
 def rmsprop_step(params: torch.Tensor, grads: torch.Tensor, square_avg: torch.Tensor, group_end, group_lr,
                  alpha: float = 0.99, eps: float = 1e-8, grad_scale: float = 1.0):
     """Fused RMSprop over flat fp32 buffers (torch.optim.RMSprop defaults; per-group learning rates)."""
@@ -351,6 +378,93 @@ def bn_bwd_apply(dz8, y8, co: BNCoeffs, gamma, s1, s2, training: bool, C: int, d
                                       _ptr(m1y), _ptr(m1c.scale if m1c else None), _ptr(m1c.shift if m1c else None),
                                       _ptr(m2y), _ptr(m2c.scale if m2c else None), _ptr(m2c.shift if m2c else None),
                                       _ptr(dy), dt, B, C, Ln, _stream()), "tsc_bn_bwd_apply")
+    return dy
+
+
+# ---- fused BatchNorm path (tcgen05 engine) ----------------------------------------------------------
+@dataclass
+class BNLayerFwd:
+    """One conv+BN branch of a fused apply: y (c8 fp32), the conv's per-CTA statistics (None = eval mode)."""
+    y8: torch.Tensor
+    stat_partial: Optional[torch.Tensor]
+    gamma: torch.Tensor
+    beta: torch.Tensor
+    running_mean: Optional[torch.Tensor]
+    running_var: Optional[torch.Tensor]
+    momentum: float
+    eps: float
+    coef: torch.Tensor          # [4, Cp] out: mean, invstd, scale, shift
+
+    def c(self) -> "L.BNBranch":
+        b = L.BNBranch()
+        b.y_c8 = self.y8.data_ptr()
+        b.stat_partial = self.stat_partial.data_ptr() if self.stat_partial is not None else None
+        b.gamma, b.beta = self.gamma.data_ptr(), self.beta.data_ptr()
+        b.running_mean = self.running_mean.data_ptr() if self.running_mean is not None else None
+        b.running_var = self.running_var.data_ptr() if self.running_var is not None else None
+        b.momentum, b.eps = float(self.momentum), float(self.eps)
+        b.coef = self.coef.data_ptr()
+        return b
+
+
+def bn_apply_fused(a: BNLayerFwd, b: Optional[BNLayerFwd], C: int, relu: bool, out_kind: int):
+    B, cpc, Ln, _ = a.y8.shape
+    if out_kind == L.OUT_NCL_F32:
+        out = torch.empty((B, C, Ln), device=a.y8.device, dtype=torch.float32)
+    else:
+        out = torch.empty((B, cpc, Ln, 8), device=a.y8.device,
+                          dtype=torch.bfloat16 if out_kind == L.OUT_C8_BF16 else torch.float32)
+    ca = a.c()
+    cb = b.c() if b is not None else None
+    L.check(L.load().tsc_bn_apply_fused(ctypes.byref(ca), ctypes.byref(cb) if cb is not None else None,
+                                        n_conv_ctas(B, Ln), 1 if relu else 0, _ptr(out), out_kind, B, C, Ln, _stream()),
+            "tsc_bn_apply_fused")
+    return out
+
+
+@dataclass
+class BNLayerBwd:
+    y8: torch.Tensor
+    coef: torch.Tensor
+    gamma: torch.Tensor
+    training: bool
+    red_partial: torch.Tensor
+    dgamma: Optional[torch.Tensor] = None
+    dbeta: Optional[torch.Tensor] = None
+    dbias: Optional[torch.Tensor] = None
+
+    def c(self) -> "L.BNBwdBranch":
+        b = L.BNBwdBranch()
+        b.y_c8, b.coef, b.gamma = self.y8.data_ptr(), self.coef.data_ptr(), self.gamma.data_ptr()
+        b.training = 1 if self.training else 0
+        b.red_partial = self.red_partial.data_ptr()
+        b.dgamma = self.dgamma.data_ptr() if self.dgamma is not None else None
+        b.dbeta = self.dbeta.data_ptr() if self.dbeta is not None else None
+        b.dbias = self.dbias.data_ptr() if self.dbias is not None else None
+        return b
+
+
+def bn_fused_splits(B: int, C: int, Ln: int) -> int:
+    return int(L.load().tsc_bn_fused_splits(B, C, Ln))
+
+
+def bn_bwd_top(dout: torch.Tensor, a: BNLayerBwd, b: Optional[BNLayerBwd], relu: bool) -> torch.Tensor:
+    _req(dout, name="dout")
+    B, C, Ln = dout.shape
+    d8 = torch.empty_like(a.y8)
+    ca = a.c()
+    cb = b.c() if b is not None else None
+    L.check(L.load().tsc_bn_bwd_top(_ptr(dout), ctypes.byref(ca), ctypes.byref(cb) if cb is not None else None,
+                                    1 if relu else 0, _ptr(d8), B, C, Ln, _stream()), "tsc_bn_bwd_top")
+    return d8
+
+
+def bn_bwd_apply_fused(d8: torch.Tensor, a: BNLayerBwd, n_part: int, C: int, dt: int, accumulate: bool) -> torch.Tensor:
+    B, cpc, Ln, _ = d8.shape
+    dy = torch.empty((B, cpc, Ln, 8), device=d8.device, dtype=torch_dtype(dt))
+    ca = a.c()
+    L.check(L.load().tsc_bn_bwd_apply_fused(_ptr(d8), ctypes.byref(ca), n_part, 1 if accumulate else 0, _ptr(dy), dt,
+                                            B, C, Ln, _stream()), "tsc_bn_bwd_apply_fused")
     return dy
 
 

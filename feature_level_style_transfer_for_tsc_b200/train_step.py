@@ -143,8 +143,15 @@ class Trainer:
 
     def _fwd_bwd(self, xt, yt, xs, ys):
         self.flat.zero_grad()
-        out = self.model(xt, yt, xs, ys, self.style_weight)
-        out["loss"].backward()
+        # every parameter owns a slice of the flat gradient bucket: the wgrad / BatchNorm-backward kernels add into it
+        # in place (no AccumulateGrad kernels), so the bucket is complete the moment backward returns
+        prev = TF.direct_grads()
+        TF.set_direct_grads(True)
+        try:
+            out = self.model(xt, yt, xs, ys, self.style_weight)
+            out["loss"].backward()
+        finally:
+            TF.set_direct_grads(prev)
         return out["loss"].detach()
 
     def _capture(self, xt, yt, xs, ys):

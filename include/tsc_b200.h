@@ -73,6 +73,23 @@ int tsc_pack_weights(int direction, int dtype, float* W, void* packed, int Cin, 
 int tsc_pack_weights_pair(int dtype, float* W, void* packed_fwd, void* packed_dgrad, int Cin, int Cout, int Kmax,
                           const int* s_of_tap, int zero_masked, tsc_stream_t stream);
 
+/* Every layer of a stack (or of a whole model set) in ONE launch: same outputs as tsc_pack_weights_pair per layer.
+ * The batch is a HOST struct passed by value to the kernel (<= TSC_PACK_MAX_LAYERS layers per call). */
+#define TSC_PACK_MAX_LAYERS 8
+typedef struct tsc_pack_layer {
+    float* W;                 /* [Cout, Cin, Kmax] fp32 (masked in place when zero_masked) */
+    void* packed_fwd;         /* tsc_packed_weight_bytes(TSC_DIR_FWD, ...) bytes */
+    void* packed_dgrad;       /* tsc_packed_weight_bytes(TSC_DIR_DGRAD, ...) bytes, or NULL */
+    int Cin, Cout, Kmax, zero_masked;
+    short s_of_tap[TSC_MAX_TAPS];
+} tsc_pack_layer;
+typedef struct tsc_pack_batch {
+    int n;
+    int pad_;
+    tsc_pack_layer layer[TSC_PACK_MAX_LAYERS];
+} tsc_pack_batch;
+int tsc_pack_weights_multi(int dtype, const tsc_pack_batch* batch, tsc_stream_t stream);
+
 /* ---- multi-kernel-size Conv1d as one implicit GEMM: replaces ConstantPad1d + Conv1d
  * (OS_CNN.py:70-71, 163-164) and their cuDNN/oneDNN dgrad -------------------------------------
  * FWD  : x = X  [B, Cin, L] c8(dtype), y = Y  [B, Cout, L] c8 fp32, bias[Cout] or NULL.
@@ -147,6 +164,52 @@ int tsc_bn_bwd_apply(const float* dz_c8, const float* y_c8, const float* mean, c
                      const float* ym_c8, const float* scale, const float* shift,
                      const float* ym2_c8, const float* scale2, const float* shift2,
                      void* dy_c8, int dy_dtype, int B, int C, int L, tsc_stream_t stream);
+
+/* ---- fused BatchNorm path of the tcgen05 engine ------------------------------------------------------------
+ * The statistics of a training-mode layer arrive as per-CTA partials from the conv epilogue (tsc_osconv) and are
+ * merged in the prologue of the apply kernels: forward = conv + tsc_bn_apply_fused (no statistics pass), backward
+ * = tsc_bn_bwd_apply_fused + wgrad + dgrad (whose epilogue masks and reduces for the layer below).
+ *
+ * tsc_bn_branch: one conv+BN branch.  stat_partial != NULL = training mode: [n_part][Cp][2] (mean, M2) per 128-row
+ * CTA -> batch statistics (biased variance for normalisation; running statistics, when given and momentum > 0,
+ * updated with the unbiased one).  stat_partial == NULL = eval mode with autograd (train_and_test.py:583-586): the
+ * running statistics are used.  coef [4][Cp] (mean, invstd, scale, shift) is written for the backward pass. */
+typedef struct tsc_bn_branch {
+    const float* y_c8;
+    const float* stat_partial;
+    const float* gamma;
+    const float* beta;
+    float* running_mean;
+    float* running_var;
+    float momentum;
+    float eps;
+    float* coef;
+} tsc_bn_branch;
+/* out = act(BN_a(y_a) [+ BN_b(y_b)]) : OS_CNN.py:72-74 and, with b, the shortcut add of :176-180.
+ * n_part must be B*ceil(L/128) (the conv kernel's CTA count). */
+int tsc_bn_apply_fused(const tsc_bn_branch* a, const tsc_bn_branch* b, int n_part, int relu, void* out, int out_kind,
+                       int B, int C, int L, tsc_stream_t stream);
+/* number of row splits the fused BN kernels use per 8-channel chunk (rows of tsc_bn_bwd_top's red_partial) */
+int tsc_bn_fused_splits(int B, int C, int L);
+
+typedef struct tsc_bn_bwd_branch {
+    const float* y_c8;        /* pre-BN conv output */
+    const float* coef;        /* [4][Cp] from the forward */
+    const float* gamma;
+    int training;
+    float* red_partial;       /* [n_part][Cp][2] (S1, S2) partial sums */
+    float* dgamma;            /* outputs of tsc_bn_bwd_apply_fused (nullable) */
+    float* dbeta;
+    float* dbias;
+} tsc_bn_bwd_branch;
+/* Top of a stack (gradient arrives NCL fp32): d = dout*[act'] as c8 fp32 and red_partial[tsc_bn_fused_splits][Cp][2]
+ * of branch a (and b: same d, its own yhat). */
+int tsc_bn_bwd_top(const float* dout_ncl, const tsc_bn_bwd_branch* a, const tsc_bn_bwd_branch* b, int relu, float* d_c8,
+                   int B, int C, int L, tsc_stream_t stream);
+/* dy = gamma*invstd*(d - S1/N - yhat*S2/N) (training) or gamma*invstd*d (eval) as c8(dy_dtype); d is already masked;
+ * (S1, S2) = sum of the n_part rows of red_partial.  Also dgamma = S2, dbeta = S1, dbias (+= when accumulate). */
+int tsc_bn_bwd_apply_fused(const float* d_c8, const tsc_bn_bwd_branch* a, int n_part, int accumulate, void* dy_c8,
+                           int dy_dtype, int B, int C, int L, tsc_stream_t stream);
 
 /* ---- feature-level style transfer (inserted at train_and_test.py:552-561; no reference operator,
  * spec = SURVEY 8c).  Rows are the (b, c) rows of an NCL fp32 tensor: R = B*C rows of L floats. ---- */

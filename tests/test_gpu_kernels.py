@@ -265,6 +265,79 @@ def test_batchnorm_fwd_bwd(T, B, C, L):
     assert rel_err(ops.c8_to_ncl(dy8, C).cpu() * safe, dy_ref * safe) < 1e-4
 
 
+@pytest.mark.parametrize("B,C,L,relu,two", [(5, 20, 100, True, False), (5, 20, 128, True, True), (4, 7, 100, False, False),
+                                            (6, 40, 300, True, True), (16, 228, 128, True, False)])
+def test_fused_batchnorm_matches_the_unfused_kernels(T, B, C, L, relu, two):
+    """The fused BatchNorm path (statistics merged from 128-row partials in the apply prologue; backward sums from
+    partials) against the stand-alone kernels that are themselves checked against the oracle in
+    test_batchnorm_fwd_bwd: same formulas, so fp32 round-off only."""
+    ops, Lb = T.ops, T._lib
+    gen = torch.Generator().manual_seed(13)
+    Cp = ops.pad16(C)
+    ncta, ltiles = ops.n_conv_ctas(B, L), (L + 127) // 128
+
+    def partials(y):            # what the conv epilogue writes: (mean, M2) per 128-row tile, computed here in fp64
+        part = torch.zeros(ncta, Cp, 2, dtype=torch.float64)
+        for i in range(ncta):
+            b, l0 = i // ltiles, (i % ltiles) * 128
+            seg = y[b, :, l0:l0 + 128].double()
+            part[i, :C, 0] = seg.mean(-1)
+            part[i, :C, 1] = ((seg - seg.mean(-1, keepdim=True)) ** 2).sum(-1)
+        return part.float().cuda()
+
+    def make():
+        y = torch.randn(B, C, L, generator=gen) * 2 + 0.5
+        gamma, beta = torch.rand(C, generator=gen) + 0.5, torch.randn(C, generator=gen) * 0.2
+        return y, gamma.cuda(), beta.cuda()
+
+    branches = []
+    for _ in range(2 if two else 1):
+        y, gamma, beta = make()
+        y8 = ops.ncl_to_c8(y.cuda(), Lb.TSC_F32)
+        rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+        rm2, rv2 = rm.clone(), rv.clone()
+        co = ops.bn_stats(y8, C, gamma, beta, rm, rv, 0.1, 1e-5)
+        coef = torch.empty(4, Cp, device="cuda")
+        fw = ops.BNLayerFwd(y8, partials(y), gamma, beta, rm2, rv2, 0.1, 1e-5, coef)
+        branches.append((y8, gamma, co, fw, rm, rv, rm2, rv2))
+    (y8, gamma, co, fw, rm, rv, rm2, rv2) = branches[0]
+    second = branches[1] if two else None
+    for kind in (Lb.OUT_C8_BF16, Lb.OUT_NCL_F32):
+        ref = ops.bn_apply(y8, co, C, relu, kind, y2=second[0] if two else None, co2=second[2] if two else None)
+        for br in branches:                       # running statistics advance once per call
+            br[6].copy_(torch.zeros_like(br[6])); br[7].copy_(torch.ones_like(br[7]))
+        got = ops.bn_apply_fused(fw, second[3] if two else None, C, relu, kind)
+        tol = 1e-2 if kind == Lb.OUT_C8_BF16 else 2e-6
+        assert rel_err(got.float().cpu(), ref.float().cpu()) < tol
+    assert rel_err(fw.coef.cpu()[0, :C], co.mean.cpu()[:C]) < 1e-6 and rel_err(fw.coef.cpu()[1, :C], co.invstd.cpu()[:C]) < 1e-5
+    assert rel_err(rm2.cpu(), rm.cpu()) < 1e-6 and rel_err(rv2.cpu(), rv.cpu()) < 1e-5
+    # eval mode: coefficients from the running statistics
+    ce = ops.bn_eval_coeffs(C, gamma, branches[0][3].beta, rm, rv, 1e-5)
+    fe_ = ops.BNLayerFwd(y8, None, gamma, branches[0][3].beta, rm, rv, 0.0, 1e-5, torch.empty(4, Cp, device="cuda"))
+    assert rel_err(ops.bn_apply_fused(fe_, None, C, relu, Lb.OUT_NCL_F32).cpu(), ops.bn_apply(y8, ce, C, relu, Lb.OUT_NCL_F32).cpu()) < 2e-6
+    # backward
+    dout = torch.randn(B, C, L, generator=gen).cuda()
+    dz8 = ops.ncl_to_c8(dout, Lb.TSC_F32)
+    m1 = (y8, co) if relu else None
+    m2 = (second[0], second[2]) if (two and relu) else None
+    S = ops.bn_fused_splits(B, C, L)
+    bws = []
+    for (yy, gg, cc, ff, *_r) in branches:
+        coef = torch.stack([cc.mean, cc.invstd, cc.scale, cc.shift]).contiguous()
+        bws.append(ops.BNLayerBwd(yy, coef, gg, True, torch.empty(S, Cp, 2, device="cuda")))
+    d8 = ops.bn_bwd_top(dout, bws[0], bws[1] if two else None, relu)
+    for (yy, gg, cc, ff, *_r), bw in zip(branches, bws):
+        s1, s2 = ops.bn_bwd_reduce(dz8, yy, cc, C, m1, m2)
+        dy_ref = ops.bn_bwd_apply(dz8, yy, cc, gg, s1, s2, True, C, Lb.TSC_F32, m1, m2)
+        bw.dgamma, bw.dbeta = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+        dy = ops.bn_bwd_apply_fused(d8, bw, S, C, Lb.TSC_F32, False)
+        assert rel_err(dy.cpu(), dy_ref.cpu()) < 2e-6
+        assert rel_err(bw.dgamma.cpu(), s2.cpu()[:C]) < 1e-6 and rel_err(bw.dbeta.cpu(), s1.cpu()[:C]) < 1e-6
+        dg0 = bw.dgamma.clone()
+        ops.bn_bwd_apply_fused(d8, bw, S, C, Lb.TSC_F32, True)          # accumulate
+        assert rel_err(bw.dgamma.cpu(), 2 * dg0.cpu()) < 1e-6
+
+
 @pytest.mark.parametrize("B,C,L", [(4, 6, 32), (8, 144, 128), (3, 5, 100), (2, 50, 1024), (2, 3, 4096), (2, 3, 777)])
 def test_rowstats_and_adain(T, B, C, L):
     ops = T.ops
@@ -315,6 +388,26 @@ def test_gram_style_loss_tcgen05(T, B, C, L):
     loss.backward()
     da_ref, ds_ref = S.gram_style_loss_backward(a.double(), s.double())
     assert rel_err(ad.grad.cpu(), da_ref) < TOL_BF16 and rel_err(sd_.grad.cpu(), ds_ref) < TOL_BF16
+
+
+def test_pack_weights_multi_matches_per_layer_pack(T):
+    """One launch for a list of banks == the per-layer pack (bit-exact), including the in-place masking of W."""
+    ops, L = T.ops, T._lib
+    names = ["small7", "mid13", "even2", "cfg2_l1", "cfg2_l0", "cfg2_l2", "cfg4_l1", "one", "cfg2_l1"]
+    jobs, refs = [], []
+    for k, name in enumerate(names):
+        layer, g, x, w, b, dy = make_case(name, seed=20 + k)
+        geom = ops.bank_geometry(layer)
+        w1, w2 = w.clone().cuda(), w.clone().cuda()
+        zero = k % 2 == 0
+        refs.append((ops.pack_weights_pair(geom, w1, L.TSC_BF16, zero, True), w1))
+        jobs.append((geom, w2, zero, True))
+    got = ops.pack_weights_multi(jobs, L.TSC_BF16)
+    torch.cuda.synchronize()
+    for k, (((pf_ref, pd_ref), w_ref), (pf, pd), job) in enumerate(zip(refs, got, jobs)):
+        assert torch.equal(pf.view(torch.int16), pf_ref.view(torch.int16)), (names[k], "fwd")
+        assert torch.equal(pd.view(torch.int16), pd_ref.view(torch.int16)), (names[k], "dgrad")
+        assert torch.equal(job[1], w_ref), (names[k], "masked W")
 
 
 def test_bad_arguments_raise(T):
