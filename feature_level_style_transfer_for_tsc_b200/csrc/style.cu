@@ -399,6 +399,11 @@ int gram_fwd_simt(const float* a, const float* s, float* D, float* loss, float* 
     TSC_LAUNCH_CHECK();
     return 0;
 }
+int gram_sum_partials(const float* partial, int n, float scale, float* out, cudaStream_t cs) {
+    sum_partials_kernel<<<1, 256, 0, cs>>>(partial, n, scale, out);
+    TSC_LAUNCH_CHECK();
+    return 0;
+}
 int gram_bwd_simt(const float* D, const float* a, const float* s, const float* dloss, float* da, float* ds, int B, int C,
                   int L, cudaStream_t cs) {
     gram_bwd_simt_kernel<<<dim3(cdiv(L, 64), cdiv(C, 32), B * 2), 256, 0, cs>>>(D, a, s, dloss, da, ds, B, C, L);

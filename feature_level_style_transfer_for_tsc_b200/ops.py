@@ -19,7 +19,7 @@ from . import _lib as L
 #   "simt"      : fp32 CUDA-core kernels, fp32 operands                                        (<= 1e-5)
 #   "simt_bf16" : the CUDA-core kernels fed the SAME bf16 operands as the tensor-core engine -- not a
 #                 product mode: it is the bit-faithful checker of the tcgen05 kernels used by tests.
-_TC_READY = ("conv", "wgrad")          # families whose tcgen05 kernel exists (others stay on SIMT)
+_TC_READY = ("conv", "wgrad", "gram")   # families whose tcgen05 kernel exists
 _CFG = {"conv": L.ENGINE_TCGEN05, "wgrad": L.ENGINE_TCGEN05, "gram": L.ENGINE_SIMT, "op_dtype": L.TSC_BF16,
         "name": "tcgen05"}
 
