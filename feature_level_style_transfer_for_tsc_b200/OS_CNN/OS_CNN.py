@@ -53,12 +53,28 @@ def creak_layer_mask(layer_parameter_list):
             torch.cat(biases, 0).numpy().astype("float32"))
 
 
+_DEFERRED_COUNTERS = None      # a list while a trainer batches the ``num_batches_tracked += 1`` of a whole step
+
+
+def defer_batch_counters(on: bool):
+    """on: collect the ``num_batches_tracked`` tensors of the BatchNorm layers that run in training mode instead of
+    incrementing each with its own kernel; off: return the collected list (the caller does one
+    ``torch._foreach_add_``).  Only valid for BatchNorm layers with a fixed momentum."""
+    global _DEFERRED_COUNTERS
+    got = _DEFERRED_COUNTERS
+    _DEFERRED_COUNTERS = [] if on else None
+    return got
+
+
 def _bn_layer_spec(geom, bn, relu, zero_masked=True):
     """LayerSpec for one conv+BN pair; advances ``num_batches_tracked`` like nn.BatchNorm1d.forward."""
     use_batch_stats = bn.training or bn.running_mean is None
     momentum = 0.0
     if bn.training and bn.track_running_stats and bn.running_mean is not None:
-        bn.num_batches_tracked.add_(1)
+        if _DEFERRED_COUNTERS is not None and bn.momentum is not None:
+            _DEFERRED_COUNTERS.append(bn.num_batches_tracked)
+        else:
+            bn.num_batches_tracked.add_(1)
         momentum = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked.item())
     return LayerSpec(geom=geom, relu=relu, training=use_batch_stats, momentum=float(momentum), eps=float(bn.eps),
                      running_mean=bn.running_mean, running_var=bn.running_var, zero_masked=zero_masked)

@@ -260,51 +260,47 @@ struct PackTaps {
     int off_d[TSC_MAX_TAPS];
 };
 
-__device__ void pack_build_taps(const tsc_pack_layer& ly, PackTaps* pt) {
+__device__ void pack_build_taps(const tsc_pack_layer& ly, PackTaps* pt, int* scratch /* [2 * TSC_MAX_TAPS + 1] */) {
     const int Kmax = ly.Kmax, Cout = ly.Cout;
     const int np_f = (ly.Cout + 15) & ~15, kc_f = ((ly.Cin + 15) & ~15) / 8;     // forward: N = out, K = in
     const int np_d = (ly.Cin + 15) & ~15, kc_d = ((ly.Cout + 15) & ~15) / 8;     // dgrad  : N = in,  K = out
     const int t = threadIdx.x;
+    int* key_f = scratch;                      // sort key of tap t (n_lo; the widened first tap gets -1), dead = INT_MAX
+    int* key_d = scratch + TSC_MAX_TAPS;
+    int* first_key = scratch + 2 * TSC_MAX_TAPS;
+    if (t == 0) *first_key = 0x7fffffff;
+    __syncthreads();
     if (t < Kmax) {
         const int sf = ly.s_of_tap[t];
-        pt->n_lo_f[t] = sf >= Cout ? -1 : (short)((sf / 16) * 16);
+        const int nf = sf >= Cout ? -1 : (sf / 16) * 16;
+        pt->n_lo_f[t] = (short)nf;
+        if (nf >= 0) atomicMin(first_key, nf * 256 + t);        // widest tap, lowest index on ties = first in issue order
         const int sd = ly.s_of_tap[Kmax - 1 - t];
-        pt->kc_lo_d[t] = sd >= Cout ? -1 : (short)((sd / 16) * 2);
+        const int kd = sd >= Cout ? -1 : (sd / 16) * 2;
+        pt->kc_lo_d[t] = (short)kd;
+        key_d[t] = kd < 0 ? 0x7fffffff : kd;
+    }
+    __syncthreads();
+    const int first = *first_key & 255;
+    if (t < Kmax) {
+        const int nf = pt->n_lo_f[t];
+        key_f[t] = nf < 0 ? 0x7fffffff : (t == first ? -1 : nf);
     }
     __syncthreads();
     if (t < Kmax) {
-        // forward: the first tap in (n_lo, t) order is widened to n_lo = 0 (it initialises every accumulator column)
-        int first = -1;
-        for (int u = 0; u < Kmax; ++u)
-            if (pt->n_lo_f[u] >= 0 && (first < 0 || pt->n_lo_f[u] < pt->n_lo_f[first])) first = u;
-        int off = 0;
-        const int mine = pt->n_lo_f[t];
-        if (mine >= 0) {
-            const int key = t == first ? -1 : mine;
-            for (int u = 0; u < Kmax; ++u) {
-                const int nu = pt->n_lo_f[u];
-                if (nu < 0 || u == t) continue;
-                const int ku = u == first ? -1 : nu;
-                if (ku < key || (ku == key && u < t)) off += kc_f * (np_f - (u == first ? 0 : nu));
-            }
+        // offsets = total size of the blobs that precede tap t in (key, index) order; iterations are independent
+        const int kf = key_f[t], kd = key_d[t];
+        int off = 0, offd = 0;
+#pragma unroll 8
+        for (int u = 0; u < Kmax; ++u) {
+            const int ku = key_f[u], kud = key_d[u];
+            const bool before_f = ku != 0x7fffffff && u != t && (ku < kf || (ku == kf && u < t));
+            const bool before_d = kud != 0x7fffffff && u != t && (kud < kd || (kud == kd && u < t));
+            off += before_f ? kc_f * (np_f - (ku < 0 ? 0 : ku)) : 0;
+            offd += before_d ? (kc_d - kud) * np_d : 0;
         }
-        pt->off_f[t] = off;
-        int offd = 0;
-        const int md = pt->kc_lo_d[t];
-        if (md >= 0) {
-            for (int u = 0; u < Kmax; ++u) {
-                const int ku = pt->kc_lo_d[u];
-                if (ku < 0 || u == t) continue;
-                if (ku < md || (ku == md && u < t)) offd += (kc_d - ku) * np_d;
-            }
-        }
-        pt->off_d[t] = offd;
-    }
-    __syncthreads();
-    if (t < Kmax) {
-        int first = -1;
-        for (int u = 0; u < Kmax; ++u)
-            if (pt->n_lo_f[u] >= 0 && (first < 0 || pt->n_lo_f[u] < pt->n_lo_f[first])) first = u;
+        pt->off_f[t] = kf == 0x7fffffff ? 0 : off;
+        pt->off_d[t] = kd == 0x7fffffff ? 0 : offd;
         if (t == first) pt->n_lo_f[t] = 0;
     }
     __syncthreads();
@@ -314,6 +310,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) pack_multi_kernel(const __grid_constant__ tsc_pack_batch batch) {
     extern __shared__ float wsm[];                    // [8][16][Kmax]
     __shared__ PackTaps pt;
+    __shared__ int scratch[2 * TSC_MAX_TAPS + 1];
     const tsc_pack_layer& ly = batch.layer[blockIdx.y];
     const int Cin = ly.Cin, Cout = ly.Cout, Kmax = ly.Kmax;
     const int np_f = (Cout + 15) & ~15, cin_p = (Cin + 15) & ~15;
@@ -321,7 +318,7 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const __grid_constant__
     if ((int)blockIdx.x >= n_cc * n_kp) return;
     const int cc = blockIdx.x / n_kp, kp = blockIdx.x % n_kp;
     const int co0 = cc * 8, ci0 = kp * 16;
-    pack_build_taps(ly, &pt);
+    pack_build_taps(ly, &pt, scratch);
     // ---- load (and mask in place) ----
     float* W = ly.W;
     const int slab = 16 * Kmax;

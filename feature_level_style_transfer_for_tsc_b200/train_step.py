@@ -25,6 +25,7 @@ import torch.nn.functional as F
 
 from . import functional as TF
 from . import ops
+from .OS_CNN import OS_CNN as OSM
 from .OS_CNN.OS_CNN import OS_CNN, OS_CNN_res, layer_parameter_list_input_change
 from .OS_CNN.OS_CNN_Structure_build import generate_layer_parameter_list
 from .widgets import DimensionUnification
@@ -147,11 +148,22 @@ class Trainer:
         # in place (no AccumulateGrad kernels), so the bucket is complete the moment backward returns
         prev = TF.direct_grads()
         TF.set_direct_grads(True)
+        # the dense GEMMs of DimensionUnification and of the classifier heads stay with cuBLAS ("next" rows); next to
+        # the bf16 tensor-core engine they may use TF32 (the reference's own GPU default for its convolutions), the
+        # fp32 engine keeps them exact
+        tf32_prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = ops.engine_name() == "tcgen05"
+        OSM.defer_batch_counters(True)
         try:
             out = self.model(xt, yt, xs, ys, self.style_weight)
+            counters = OSM.defer_batch_counters(False)
+            if counters:
+                torch._foreach_add_(counters, 1)          # one launch for every BatchNorm's num_batches_tracked
             out["loss"].backward()
         finally:
+            OSM.defer_batch_counters(False)
             TF.set_direct_grads(prev)
+            torch.backends.cuda.matmul.allow_tf32 = tf32_prev
         return out["loss"].detach()
 
     def _capture(self, xt, yt, xs, ys):
