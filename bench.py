@@ -212,7 +212,8 @@ class KernelProfile:
 def conv_roofline(torch, ops, L, conv_calls, peaks, reps=20):
     """Roofline of the dominant kernel (osconv_tc_kernel, forward + dgrad): every distinct (bank, direction, epilogue)
     launch of the step is replayed in isolation -- `reps` back-to-back launches between two CUDA events on the launching
-    stream, operands L2-warm as they are inside the step -- and weighted by its call count.
+    stream (captured in a CUDA graph, so no host latency sits between them), operands L2-warm as they are inside the
+    step -- and weighted by its call count.
     achieved = live-tap FLOPs of all conv launches of one step / their summed device time."""
     dev = torch.device("cuda", torch.cuda.current_device())
     groups = {}
@@ -238,17 +239,24 @@ def conv_roofline(torch, ops, L, conv_calls, peaks, reps=20):
             one = torch.ones(cp, device=dev)
             kw["mask"] = (yb, one, one * 0.1, one * 0.0, one)
             kw["red_partial"] = torch.empty(ncta, cp, 2, device=dev)
-        lib, args = ops.L.load(), None
         for _ in range(3):
             ops.osconv(L.ENGINE_TCGEN05, direction, g, x8, wp, bias, **kw)
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        # keep the GPU busy while the host enqueues, so the events bracket device time only
-        pad = torch.empty(64 * 1024 * 1024, device=dev)
-        pad.zero_()
-        e0.record()
-        for _ in range(reps):
+        # `reps` launches captured in a CUDA graph: the events then bracket device time only (no host launch latency)
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
             ops.osconv(L.ENGINE_TCGEN05, direction, g, x8, wp, bias, **kw)
+        torch.cuda.current_stream().wait_stream(side)
+        with torch.cuda.graph(graph):
+            for _ in range(reps):
+                ops.osconv(L.ENGINE_TCGEN05, direction, g, x8, wp, bias, **kw)
+        graph.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        graph.replay()
         e1.record()
         torch.cuda.synchronize()
         t = e0.elapsed_time(e1) * 1e-3 / reps

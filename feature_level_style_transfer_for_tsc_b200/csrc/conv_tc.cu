@@ -31,8 +31,8 @@ namespace tsc {
 namespace tc {
 
 static constexpr int TC_THREADS = 192;
-static constexpr int PLAN_STAGE_BYTES = 32 * 1024;
-static constexpr int STAGE_SLOT_BYTES = PLAN_STAGE_BYTES + 512;   // + a zero block: the B operand of padding MMAs
+static constexpr int PLAN_STAGE_BYTES = 32 * 1024;               // weight stage; 16 KB for banks whose activation tile is large
+static constexpr int ZERO_BLOCK_BYTES = 512;                      // behind every stage slot: the B operand of padding MMAs
 static constexpr int MMA_GROUP = 4;                               // MMAs issued per elect block
 static constexpr uint32_t PF_FIRST = 1u << 16, PF_LAST = 1u << 17;
 static constexpr int SMEM_HDR = 256;                       // barriers + tmem slot
@@ -56,6 +56,7 @@ struct ConvTcParams {
     int kc;
     int pad_left;
     int NS;            // weight stages
+    int stage_bytes;   // bytes of one weight stage (the slot is stage_bytes + ZERO_BLOCK_BYTES)
     int plan_bytes;
     int n_stages, n_mma;
     int off_bias, off_wstat, off_plan, off_xs, off_stages;
@@ -147,7 +148,7 @@ osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const ConvTcParams p)
     if (warp >= 2) {
         // zero block at the end of every stage slot (read by the padding MMAs that round a stage up to MMA_GROUP)
         for (int i = threadIdx.x - 64; i < p.NS * 32; i += 128)
-            *reinterpret_cast<uint4*>(stages + (size_t)(i >> 5) * STAGE_SLOT_BYTES + PLAN_STAGE_BYTES + (i & 31) * 16) =
+            *reinterpret_cast<uint4*>(stages + (size_t)(i >> 5) * (p.stage_bytes + ZERO_BLOCK_BYTES) + p.stage_bytes + (i & 31) * 16) =
                 make_uint4(0u, 0u, 0u, 0u);
         fence_proxy_async();
         // per-channel epilogue constants -> shared memory: [0] bias | mask scale, [1] mask shift, [2] mean, [3] invstd
@@ -180,7 +181,7 @@ osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const ConvTcParams p)
                 const uint2 e = st[i];                        // {source offset in 16 B units, bytes}
                 mbar_wait(&empty[s], ph ^ 1u, dead, 1);
                 mbar_arrive_expect_tx(&full[s], e.y);
-                bulk_load(stages + (size_t)s * STAGE_SLOT_BYTES, reinterpret_cast<const uint8_t*>(p.w) + (size_t)e.x * 16,
+                bulk_load(stages + (size_t)s * (p.stage_bytes + ZERO_BLOCK_BYTES), reinterpret_cast<const uint8_t*>(p.w) + (size_t)e.x * 16,
                           e.y, &full[s]);
                 if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; }
             }
@@ -199,7 +200,7 @@ osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const ConvTcParams p)
         const uint32_t desc_hi = (128u >> 4) | (1u << 14);                        // SBO = 128 B, descriptor version 1
         const uint32_t a_base16 = (smem_u32(xs) >> 4) | ((uint32_t)p.Rp << 16);    // LBO = Rp * 16 B
         const uint32_t st_base16 = smem_u32(stages) >> 4;
-        const uint32_t stage16 = (uint32_t)STAGE_SLOT_BYTES >> 4;
+        const uint32_t stage16 = (uint32_t)(p.stage_bytes + ZERO_BLOCK_BYTES) >> 4;
         uint32_t s = 0, ph = 0, b_base16 = st_base16, acc = 0;
         const int n_grp = p.n_mma / MMA_GROUP;
         uint4 e0 = mm[0], e1 = mm[1], e2 = mm[2], e3 = mm[3];
@@ -409,6 +410,7 @@ int make_c8_map(CUtensorMap* map, const void* base, int B, int kc, int L, int bo
 }
 
 static constexpr int SMEM_CAP = 227 * 1024;
+static constexpr int SMEM_HALF = 113 * 1024;
 static long long* g_timeline = nullptr;     // debug only: device buffer of >= 8 clock64 samples
 
 static inline int conv_rp(int Kmax) { return (128 + Kmax - 1 + 7) & ~7; }
@@ -417,6 +419,7 @@ static inline int conv_rp(int Kmax) { return (128 + Kmax - 1 + 7) & ~7; }
 struct PlanHost {
     std::vector<uint2> stages;
     std::vector<uint4> mmas;
+    int stage_bytes = PLAN_STAGE_BYTES;
 };
 
 // A stage ends: pad its MMA list to a multiple of MMA_GROUP with instructions that add zero (N = 16, B = the zero
@@ -426,7 +429,7 @@ static void close_stage(PlanHost* ph, uint32_t src16, uint32_t bytes) {
     while (ph->mmas.size() % MMA_GROUP != 0) {
         uint4 e;
         e.x = 0;
-        e.y = ((uint32_t)PLAN_STAGE_BYTES >> 4) | (16u << 16);     // LBO = 16 rows * 16 B
+        e.y = ((uint32_t)ph->stage_bytes >> 4) | (16u << 16);      // LBO = 16 rows * 16 B
         e.z = (1u << 4) | (1u << 7) | (1u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
         e.w = 0;
         ph->mmas.push_back(e);
@@ -438,6 +441,9 @@ static int build_plan(int direction, int Cin, int Cout, int Kmax, const int* s_o
     TapTable tt;
     if (build_tap_table(direction, Cin, Cout, Kmax, s_of_tap, &tt) != 0) return -1;
     const int Rp = conv_rp(Kmax);
+    // a large activation tile leaves less room for the weight ring: halve the stage so that two stages still fit the
+    // half-SM shared-memory budget (two CTAs of different launches can then share an SM)
+    ph->stage_bytes = tt.kc * Rp * 16 > 48 * 1024 ? PLAN_STAGE_BYTES / 2 : PLAN_STAGE_BYTES;
     uint32_t stage_src16 = 0, stage_bytes = 0;
     bool open = false;
     for (int oi = 0; oi < tt.n_order; ++oi) {
@@ -449,7 +455,7 @@ static int build_plan(int direction, int Cin, int Cout, int Kmax, const int* s_o
         for (int kp = 0; kp < kspan / 2; ++kp) {
             const uint32_t unit_bytes = (uint32_t)(2 * nt * 16);
             const uint32_t unit_src16 = (uint32_t)tt.w_off[t] + (uint32_t)(2 * kp * nt);
-            if (open && stage_bytes + unit_bytes > (uint32_t)PLAN_STAGE_BYTES) {
+            if (open && stage_bytes + unit_bytes > (uint32_t)ph->stage_bytes) {
                 close_stage(ph, stage_src16, stage_bytes);
                 open = false;
             }
@@ -488,7 +494,7 @@ int osconv_plan_build(int direction, int Cin, int Cout, int Kmax, const int* s_o
     if (tc::build_plan(direction, Cin, Cout, Kmax, s_of_tap, &ph) != 0) return -1;
     uint8_t* o = (uint8_t*)host_plan;
     memset(o, 0, tc::plan_bytes_of(ph));
-    int hdr[4] = {(int)ph.mmas.size(), (int)ph.stages.size(), tc::PLAN_STAGE_BYTES, 0x504c414e};
+    int hdr[4] = {(int)ph.mmas.size(), (int)ph.stages.size(), ph.stage_bytes, 0x504c414e};
     memcpy(o, hdr, 16);
     memcpy(o + 16, ph.stages.data(), ph.stages.size() * 8);
     memcpy(o + 16 + ((ph.stages.size() * 8 + 15) & ~(size_t)15), ph.mmas.data(), ph.mmas.size() * 16);
@@ -534,7 +540,13 @@ int osconv_tc(int direction, const void* x, int dtype, const void* w, const void
     p.off_plan = (p.off_wstat + 4 * p.np * 8 + 15) & ~15;
     p.off_xs = (p.off_plan + p.plan_bytes + 127) & ~127;
     p.off_stages = (p.off_xs + p.kc * p.Rp * 16 + 127) & ~127;
-    int ns = (SMEM_CAP - p.off_stages) / STAGE_SLOT_BYTES;
+    p.stage_bytes = ph.stage_bytes;
+    const int slot = p.stage_bytes + ZERO_BLOCK_BYTES;
+    // prefer half of an SM's shared memory (113 KB): CTAs of two independent launches (the target and the source branch
+    // of a step run on two streams) can then be co-resident and hide each other's load / epilogue latency
+    int cap = SMEM_HALF;
+    int ns = (cap - p.off_stages) / slot;
+    if (ns < 2 && p.n_stages > 1) { cap = SMEM_CAP; ns = (cap - p.off_stages) / slot; }
     if (ns > 8) ns = 8;
     if (ns > p.n_stages) ns = p.n_stages;
     TSC_REQUIRE(ns >= 1 && (ns >= 2 || p.n_stages == 1), "shape needs %d B of shared memory before the weight stages: unsupported",
@@ -544,7 +556,7 @@ int osconv_tc(int direction, const void* x, int dtype, const void* w, const void
     p.tmem_cols = p.np <= 32 ? 32 : p.np <= 64 ? 64 : p.np <= 128 ? 128 : 256;
     CUtensorMap xmap;
     if (make_c8_map(&xmap, x, B, p.kc, L, p.Rp, p.kc) != 0) return -1;
-    const int smem = p.off_stages + ns * STAGE_SLOT_BYTES;
+    const int smem = p.off_stages + ns * slot;
     static bool attr_set = false;          // once per process: opt in to the full 227 KB of dynamic shared memory
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(osconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

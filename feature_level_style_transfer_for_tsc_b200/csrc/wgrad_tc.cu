@@ -8,7 +8,7 @@
 // B-operand descriptor, so ONE staged (dY tile, X tile + halo) pair feeds every tap of a CTA.
 //
 // Work decomposition: a work item = (128-channel out tile, up to NT consecutive taps) with
-// NT = 512 / Cin_p TMEM accumulators of [128 x Cin_p] fp32 each; a CTA owns one item and a share of the
+// NT = 256 / Cin_p TMEM accumulators of [128 x Cin_p] fp32 each (half of TMEM, so that two CTAs can share an SM); a CTA owns one item and a share of the
 // (b, l) position tiles, accumulates in TMEM over all of them, and writes its partial dW once.
 // Out tiles are anchored at the END of the channel axis: by nestedness of the kernel bank the outer
 // taps are live only on a channel suffix, so they need the last tile only (masked taps cost nothing).
@@ -31,6 +31,7 @@ static constexpr int WG_LT = 128;          // positions per stage
 static constexpr int WG_MAX_ITEMS = 192;
 static constexpr int WG_HDR = 256;
 static constexpr int WG_STAGES = 2;
+static constexpr int WG_TMEM_COLS = 256;     // half of TMEM: CTAs of two independent launches can be co-resident
 
 struct WgItem { short m0, t0, nt, pad; };
 struct WgItems { int n; WgItem it[WG_MAX_ITEMS]; };
@@ -77,7 +78,7 @@ oswgrad_tc_kernel(const __grid_constant__ WgItems items, const WgParams p) {
         mbar_init(acc_full, 2);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (warp == 1) tmem_alloc(tmem_slot, WG_TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -170,7 +171,7 @@ oswgrad_tc_kernel(const __grid_constant__ WgItems items, const WgParams p) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (warp == 1) tmem_dealloc(tmem_base, WG_TMEM_COLS);
     if (warp == 1 && lane == 0) WTL(7);
 }
 
@@ -239,7 +240,7 @@ static int wgrad_tc_items(int Cin, int Cout, int Kmax, const int* s_of_tap, tc::
                           int* m_split) {
     using namespace tc;
     const int np = pad16(Cout), cinp = pad16(Cin);
-    const int NT = 512 / cinp;
+    const int NT = tc::WG_TMEM_COLS / cinp;
     const int MT = np > 128 ? 2 : 1;
     *m_split = MT == 2 ? np - 128 : 0;
     items->n = 0;
@@ -267,7 +268,7 @@ static int wgrad_tc_items(int Cin, int Cout, int Kmax, const int* s_of_tap, tc::
 
 // upper bound on the number of work items without the tap table: 2 tiles x ceil(Kmax / NT)
 static int wgrad_tc_max_items(int Cin, int Cout, int Kmax) {
-    const int cinp = pad16(Cin), NT = 512 / cinp, MT = pad16(Cout) > 128 ? 2 : 1;
+    const int cinp = pad16(Cin), NT = tc::WG_TMEM_COLS / cinp, MT = pad16(Cout) > 128 ? 2 : 1;
     return MT * cdiv(Kmax, NT);
 }
 
@@ -282,7 +283,7 @@ int wgrad_tc_splits(int B, int L, int Cin, int Cout, int Kmax) {
 }
 
 size_t wgrad_tc_workspace_bytes(int B, int L, int Cin, int Cout, int Kmax) {
-    const int cinp = pad16(Cin), NT = 512 / cinp;
+    const int cinp = pad16(Cin), NT = tc::WG_TMEM_COLS / cinp;
     return (size_t)wgrad_tc_splits(B, L, Cin, Cout, Kmax) * wgrad_tc_max_items(Cin, Cout, Kmax) * NT * cinp * 128 * sizeof(float);
 }
 
@@ -296,7 +297,7 @@ int oswgrad_tc(const void* dy, const void* x, int dtype, float* dW, void* worksp
     int m_split = 0;
     if (wgrad_tc_items(Cin, Cout, Kmax, s_of_tap, &items, &lk, &m_split) != 0) return -1;
     const int np = pad16(Cout), cinp = pad16(Cin);
-    const int NT = 512 / cinp;
+    const int NT = tc::WG_TMEM_COLS / cinp;
     p.part = (float*)workspace;
     p.B = B; p.L = L; p.ltiles = cdiv(L, WG_LT);
     p.taps = Kmax; p.pad_left = (Kmax - 1) / 2;
