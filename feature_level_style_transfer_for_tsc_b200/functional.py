@@ -70,6 +70,21 @@ def direct_grads() -> bool:
     return _DIRECT_GRADS
 
 
+_AUX_STREAMS = {}
+WGRAD_ON_AUX_STREAM = False     # optional: run the weight gradient (off the backward's critical path) on an auxiliary
+                                # stream beside dgrad; measured no gain at cfg2 (the two branch streams already fill the
+                                # two CTA slots per SM), so it is off by default
+
+
+def _aux_stream(cur: "torch.cuda.Stream") -> "torch.cuda.Stream":
+    """One auxiliary stream per calling stream (the two branches of a step each get their own)."""
+    key = (cur.device.index, cur.cuda_stream)
+    st = _AUX_STREAMS.get(key)
+    if st is None:
+        st = _AUX_STREAMS[key] = torch.cuda.Stream(device=cur.device)
+    return st
+
+
 def _fused_forward(spec: StackSpec, sv: "_Saved", x: torch.Tensor, params, need_dgrad_first: bool):
     """tcgen05 engine: conv (+ per-CTA BatchNorm statistics in its epilogue) -> fused merge + apply, one pack launch."""
     eng, dt = spec.engine, spec.op_dtype
@@ -150,11 +165,23 @@ def _fused_backward(spec: StackSpec, sv: "_Saved", params, dout: torch.Tensor, x
         grads[k + 2], grads[k + 3] = dg, db
         return dg, db, dbias_buf
 
+    cur_stream = torch.cuda.current_stream()
+    aux = _aux_stream(cur_stream) if WGRAD_ON_AUX_STREAM else None
+
     def wgrad(k, g, dy, x_op):
-        if direct:
-            ops.oswgrad(spec.wgrad_engine, g, dy, x_op, out=params[k].grad, accumulate=True)
-        else:
-            grads[k] = ops.oswgrad(spec.wgrad_engine, g, dy, x_op)
+        # dW depends on (dy, x) only and nothing in this backward depends on it: it runs on the auxiliary stream next to
+        # the dgrad -> BatchNorm-backward chain of the layers below (joined before this function returns)
+        if aux is not None:
+            aux.wait_stream(cur_stream)
+            dy.record_stream(aux)
+            x_op.record_stream(aux)
+        with torch.cuda.stream(aux if aux is not None else cur_stream):
+            if direct:
+                ops.oswgrad(spec.wgrad_engine, g, dy, x_op, out=params[k].grad, accumulate=True)
+            else:
+                grads[k] = ops.oswgrad(spec.wgrad_engine, g, dy, x_op)
+                if aux is not None:
+                    grads[k].record_stream(cur_stream)
 
     last = spec.layers[-1]
     S_top = ops.bn_fused_splits(B, last.geom.cout, Ln)
@@ -196,6 +223,8 @@ def _fused_backward(spec: StackSpec, sv: "_Saved", params, dout: torch.Tensor, x
         if dx_short is not None:
             dz = dz + dx_short
         dx = ops.c8_to_ncl(dz, spec.layers[0].geom.cin)
+    if aux is not None:
+        cur_stream.wait_stream(aux)
     return dx, grads
 
 
