@@ -125,36 +125,53 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gram_fwd_tc_kernel(const GramFw
             mbar_wait(&empty[s], ph ^ 1u, dead, 11);
             uint8_t* st = stages + (size_t)s * stage_bytes;
             const int l0 = ck * GR_KC;
-            // item = (row r, quad q of 4 positions): quads of a row are contiguous in global memory
-            for (int it = ptid; it < C * (GR_KC / 4); it += 128) {
+            // item = (row r, quad q of 4 positions): quads of a row are contiguous in global memory.  All loads of the
+            // chunk are issued before the first use (one L2 round trip per chunk instead of one per item).
+            constexpr int FI = (256 * (GR_KC / 4) + 127) / 128;          // items per thread for C <= 256
+            float4 ra[FI], rs[FI];
+#pragma unroll
+            for (int u = 0; u < FI; ++u) {
+                const int it = ptid + u * 128;
                 const int r = it / (GR_KC / 4), q = it % (GR_KC / 4);
                 const int l = l0 + q * 4;
-                float va[4], vs[4];
-                if (vec && l + 3 < L) {
-                    const float4 t = __ldg(reinterpret_cast<const float4*>(ab + (size_t)r * L + l));
-                    const float4 u = __ldg(reinterpret_cast<const float4*>(sb + (size_t)r * L + l));
-                    va[0] = t.x; va[1] = t.y; va[2] = t.z; va[3] = t.w;
-                    vs[0] = u.x; vs[1] = u.y; vs[2] = u.z; vs[3] = u.w;
-                } else {
+                ra[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                rs[u] = ra[u];
+                if (it < C * (GR_KC / 4)) {
+                    if (vec && l + 3 < L) {
+                        ra[u] = __ldg(reinterpret_cast<const float4*>(ab + (size_t)r * L + l));
+                        rs[u] = __ldg(reinterpret_cast<const float4*>(sb + (size_t)r * L + l));
+                    } else {
+                        float va[4], vs[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        va[j] = l + j < L ? __ldg(ab + (size_t)r * L + l + j) : 0.f;
-                        vs[j] = l + j < L ? __ldg(sb + (size_t)r * L + l + j) : 0.f;
+                        for (int j = 0; j < 4; ++j) {
+                            va[j] = l + j < L ? __ldg(ab + (size_t)r * L + l + j) : 0.f;
+                            vs[j] = l + j < L ? __ldg(sb + (size_t)r * L + l + j) : 0.f;
+                        }
+                        ra[u] = make_float4(va[0], va[1], va[2], va[3]);
+                        rs[u] = make_float4(vs[0], vs[1], vs[2], vs[3]);
                     }
                 }
-                float ah[4], al[4], sh[4], sl[4];
+            }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    ah[j] = __uint_as_float(__float_as_uint(va[j]) & 0xffffe000u);
-                    al[j] = va[j] - ah[j];
-                    sh[j] = __uint_as_float(__float_as_uint(vs[j]) & 0xffffe000u);
-                    sl[j] = vs[j] - sh[j];
+            for (int u = 0; u < FI; ++u) {
+                const int it = ptid + u * 128;
+                if (it < C * (GR_KC / 4)) {
+                    const int r = it / (GR_KC / 4), q = it % (GR_KC / 4);
+                    const float va[4] = {ra[u].x, ra[u].y, ra[u].z, ra[u].w}, vs[4] = {rs[u].x, rs[u].y, rs[u].z, rs[u].w};
+                    float ah[4], al[4], sh[4], sl[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        ah[j] = __uint_as_float(__float_as_uint(va[j]) & 0xffffe000u);
+                        al[j] = va[j] - ah[j];
+                        sh[j] = __uint_as_float(__float_as_uint(vs[j]) & 0xffffe000u);
+                        sl[j] = vs[j] - sh[j];
+                    }
+                    uint8_t* dst = st + ((size_t)q * (Rp + 1) + r) * 16;
+                    *reinterpret_cast<float4*>(dst) = make_float4(ah[0], ah[1], ah[2], ah[3]);
+                    *reinterpret_cast<float4*>(dst + p.buf_bytes) = make_float4(al[0], al[1], al[2], al[3]);
+                    *reinterpret_cast<float4*>(dst + 2 * p.buf_bytes) = make_float4(sh[0], sh[1], sh[2], sh[3]);
+                    *reinterpret_cast<float4*>(dst + 3 * p.buf_bytes) = make_float4(sl[0], sl[1], sl[2], sl[3]);
                 }
-                uint8_t* dst = st + ((size_t)q * (Rp + 1) + r) * 16;
-                *reinterpret_cast<float4*>(dst) = make_float4(ah[0], ah[1], ah[2], ah[3]);
-                *reinterpret_cast<float4*>(dst + p.buf_bytes) = make_float4(al[0], al[1], al[2], al[3]);
-                *reinterpret_cast<float4*>(dst + 2 * p.buf_bytes) = make_float4(sh[0], sh[1], sh[2], sh[3]);
-                *reinterpret_cast<float4*>(dst + 3 * p.buf_bytes) = make_float4(sl[0], sl[1], sl[2], sl[3]);
             }
             fence_proxy_async();          // generic-proxy stores -> visible to the tensor core's async-proxy reads
             mbar_arrive(&full[s]);
@@ -282,35 +299,54 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gram_bwd_tc_kernel(const GramBw
             mbar_wait(&empty[s], ph ^ 1u, dead, 14);
             uint8_t* st = stages + (size_t)s * stage_bytes;
             const int j0 = ck * GR_KC;
+            // All loads of the chunk are issued before the first use.
             // A operand: D[i][j0 .. j0+KC): item = (row i, quad q); zero beyond C
-            for (int it = ptid; it < C * (GR_KC / 4); it += 128) {
+            constexpr int DI = (256 * (GR_KC / 4) + 127) / 128;
+            float4 rd[DI];
+#pragma unroll
+            for (int u = 0; u < DI; ++u) {
+                const int it = ptid + u * 128;
                 const int i = it / (GR_KC / 4), q = it % (GR_KC / 4);
                 const int j = j0 + q * 4;
-                float4 v;
-                if (vecD && j + 3 < C) {
-                    v = __ldg(reinterpret_cast<const float4*>(Db + (size_t)i * C + j));
-                } else {
-                    v.x = j < C ? __ldg(Db + (size_t)i * C + j) : 0.f;
-                    v.y = j + 1 < C ? __ldg(Db + (size_t)i * C + j + 1) : 0.f;
-                    v.z = j + 2 < C ? __ldg(Db + (size_t)i * C + j + 2) : 0.f;
-                    v.w = j + 3 < C ? __ldg(Db + (size_t)i * C + j + 3) : 0.f;
+                rd[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (it < C * (GR_KC / 4)) {
+                    if (vecD && j + 3 < C) {
+                        rd[u] = __ldg(reinterpret_cast<const float4*>(Db + (size_t)i * C + j));
+                    } else {
+                        rd[u].x = j < C ? __ldg(Db + (size_t)i * C + j) : 0.f;
+                        rd[u].y = j + 1 < C ? __ldg(Db + (size_t)i * C + j + 1) : 0.f;
+                        rd[u].z = j + 2 < C ? __ldg(Db + (size_t)i * C + j + 2) : 0.f;
+                        rd[u].w = j + 3 < C ? __ldg(Db + (size_t)i * C + j + 3) : 0.f;
+                    }
                 }
-                *reinterpret_cast<float4*>(st + ((size_t)q * (Rp + 1) + i) * 16) = v;
             }
             // B operands: x^T[l][j0 .. j0+KC): item = (position l, quad q): four rows j of x at one position
-            for (int it = ptid; it < 128 * (GR_KC / 4); it += 128) {
-                const int l = it % 128, q = it / 128;
-                const int j = j0 + q * 4, gl = l0 + l;
-                float va[4], vs[4];
+            constexpr int XI = GR_KC / 4;          // 128 positions x (KC/4) quads over 128 threads
+            float xa[XI][4], xs_[XI][4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const bool ok = gl < L && j + u < C;
-                    va[u] = ok ? __ldg(ab + (size_t)(j + u) * L + gl) : 0.f;
-                    vs[u] = ok ? __ldg(sb + (size_t)(j + u) * L + gl) : 0.f;
+            for (int u = 0; u < XI; ++u) {
+                const int l = ptid, q = u;
+                const int j = j0 + q * 4, gl = l0 + l;
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const bool ok = gl < L && j + v < C;
+                    xa[u][v] = ok ? __ldg(ab + (size_t)(j + v) * L + gl) : 0.f;
+                    xs_[u][v] = ok ? __ldg(sb + (size_t)(j + v) * L + gl) : 0.f;
                 }
-                uint8_t* dst = st + p.dbuf_bytes + ((size_t)q * 129 + l) * 16;
-                *reinterpret_cast<float4*>(dst) = make_float4(va[0], va[1], va[2], va[3]);
-                *reinterpret_cast<float4*>(dst + p.xbuf_bytes) = make_float4(vs[0], vs[1], vs[2], vs[3]);
+            }
+#pragma unroll
+            for (int u = 0; u < DI; ++u) {
+                const int it = ptid + u * 128;
+                if (it < C * (GR_KC / 4)) {
+                    const int i = it / (GR_KC / 4), q = it % (GR_KC / 4);
+                    *reinterpret_cast<float4*>(st + ((size_t)q * (Rp + 1) + i) * 16) = rd[u];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < XI; ++u) {
+                uint8_t* dst = st + p.dbuf_bytes + ((size_t)u * 129 + ptid) * 16;
+                *reinterpret_cast<float4*>(dst) = make_float4(xa[u][0], xa[u][1], xa[u][2], xa[u][3]);
+                *reinterpret_cast<float4*>(dst + p.xbuf_bytes) = make_float4(xs_[u][0], xs_[u][1], xs_[u][2], xs_[u][3]);
             }
             fence_proxy_async();
             mbar_arrive(&full[s]);

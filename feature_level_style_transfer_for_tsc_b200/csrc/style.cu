@@ -68,7 +68,32 @@ __global__ void __launch_bounds__(256) rowstats_kernel(const float* __restrict__
     if (row >= R) return;
     const float* p = x + (long long)row * L;
     WState s = {0.f, 0.f, 0.f};
-    if ((L & 3) == 0) {
+    if ((L & 3) == 0 && L <= 1024) {
+        // the row fits the warp's registers: local two-pass (n, mean, M2), no per-element division
+        float4 v[8];
+        float sum = 0.f;
+        int cnt = 0;
+        const float4* p4 = reinterpret_cast<const float4*>(p);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int q = lane + i * 32;
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q < L / 4) {
+                v[i] = __ldg(p4 + q);
+                sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+                cnt += 4;
+            }
+        }
+        s.n = (float)cnt;
+        s.mean = cnt ? sum / (float)cnt : 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (lane + i * 32 < L / 4) {
+                const float a = v[i].x - s.mean, b = v[i].y - s.mean, c = v[i].z - s.mean, d = v[i].w - s.mean;
+                s.m2 += (a * a + b * b) + (c * c + d * d);
+            }
+        }
+    } else if ((L & 3) == 0) {
         const float4* p4 = reinterpret_cast<const float4*>(p);
         for (int i = lane; i < L / 4; i += 32) {
             const float4 v = __ldg(p4 + i);
@@ -96,10 +121,14 @@ __global__ void __launch_bounds__(256) adain_fwd_kernel(const float* __restrict_
     const bool active = row < R;       // G == 256 -> one row per block, always active
     const long long base = (long long)(active ? row : 0) * L;
     float c[V][VEC], s[V][VEC];
-    WState wc = {0.f, 0.f, 0.f}, ws_ = {0.f, 0.f, 0.f};
+    // The thread's own (n, mean, M2) come from two passes over its REGISTER-resident values (no per-element division);
+    // the threads of a row are then combined with Chan's parallel Welford merge.  HBM is still read exactly once.
+    float cnt = 0.f, sum_c = 0.f, sum_s = 0.f;
 #pragma unroll
     for (int i = 0; i < V; ++i) {
         const int e = (i * G + tg) * VEC;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) { c[i][k] = 0.f; s[i][k] = 0.f; }
         if (active && e < L) {
             if (VEC == 4) {
                 const float4 a = __ldg(reinterpret_cast<const float4*>(content + base + e));
@@ -110,8 +139,23 @@ __global__ void __launch_bounds__(256) adain_fwd_kernel(const float* __restrict_
                 c[i][0] = __ldg(content + base + e);
                 s[i][0] = __ldg(style + base + e);
             }
+            cnt += (float)VEC;
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) { wf_add(wc, c[i][k]); wf_add(ws_, s[i][k]); }
+            for (int k = 0; k < VEC; ++k) { sum_c += c[i][k]; sum_s += s[i][k]; }
+        }
+    }
+    const float rc = cnt > 0.f ? 1.f / cnt : 0.f;
+    WState wc = {cnt, sum_c * rc, 0.f}, ws_ = {cnt, sum_s * rc, 0.f};
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const int e = (i * G + tg) * VEC;
+        if (active && e < L) {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                const float dc = c[i][k] - wc.mean, ds = s[i][k] - ws_.mean;
+                wc.m2 = fmaf(dc, dc, wc.m2);
+                ws_.m2 = fmaf(ds, ds, ws_.m2);
+            }
         }
     }
     wc = wf_group_merge<G>(wc, sh[0]);
@@ -125,14 +169,13 @@ __global__ void __launch_bounds__(256) adain_fwd_kernel(const float* __restrict_
         if (active && e < L) {
             float o[VEC];
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) o[k] = (c[i][k] - wc.mean) / sig_c * sig_s + ws_.mean;
+            for (int k = 0; k < VEC; ++k) o[k] = fmaf(c[i][k] - wc.mean, a, ws_.mean);
             if (VEC == 4)
                 *reinterpret_cast<float4*>(out + base + e) = make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]);
             else
                 out[base + e] = o[0];
         }
     }
-    (void)a;
     if (active && tg == 0) {
         float4 st = make_float4(wc.mean, sig_c, ws_.mean, sig_s);
         *reinterpret_cast<float4*>(stats + (long long)row * 4) = st;
@@ -152,6 +195,7 @@ __global__ void __launch_bounds__(256) adain_bwd_kernel(const float* __restrict_
     const long long base = (long long)(active ? row : 0) * L;
     const float4 st = __ldg(reinterpret_cast<const float4*>(stats + (long long)(active ? row : 0) * 4));
     const float mu_c = st.x, sig_c = st.y, mu_s = st.z, sig_s = st.w;
+    const float inv_c = 1.f / sig_c, inv_s = 1.f / sig_s;
     float g[V][VEC], xh[V][VEC], shh[V][VEC];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -173,8 +217,8 @@ __global__ void __launch_bounds__(256) adain_bwd_kernel(const float* __restrict_
             }
 #pragma unroll
             for (int k = 0; k < VEC; ++k) {
-                xh[i][k] = (cc[k] - mu_c) / sig_c;
-                shh[i][k] = (ss[k] - mu_s) / sig_s;
+                xh[i][k] = (cc[k] - mu_c) * inv_c;
+                shh[i][k] = (ss[k] - mu_s) * inv_s;
                 s1 += g[i][k];
                 s2 = fmaf(g[i][k], xh[i][k], s2);
             }
@@ -341,7 +385,27 @@ static int launch_adain_bwd(const float* dy, const float* c, const float* s, con
             if (L <= 128) return FN<32, 1, 4>(__VA_ARGS__);                                  \
             if (L <= 256) return FN<32, 2, 4>(__VA_ARGS__);                                  \
             if (L <= 512) return FN<32, 4, 4>(__VA_ARGS__);                                  \
-            if (L <= 1024) return FN<256, 1, 4>(__VA_ARGS__);                                \
+            if (L <= 1024) return FN<32, 8, 4>(__VA_ARGS__);                                 \
+            if (L <= 2048) return FN<256, 2, 4>(__VA_ARGS__);                                \
+            if (L <= 4096) return FN<256, 4, 4>(__VA_ARGS__);                                \
+            if (L <= 8192) return FN<256, 8, 4>(__VA_ARGS__);                                \
+        } else {                                                                             \
+            if (L <= 128) return FN<32, 4, 1>(__VA_ARGS__);                                  \
+            if (L <= 512) return FN<256, 2, 1>(__VA_ARGS__);                                 \
+            if (L <= 2048) return FN<256, 8, 1>(__VA_ARGS__);                                \
+        }                                                                                    \
+        TSC_REQUIRE(false, "row length L=%d not supported by the in-register AdaIN kernel", L); \
+    } while (0)
+
+// Same for the backward kernel (dy, content and style are register resident)
+// Dispatch on the row length: elements per thread = V*VEC, threads per row G.
+#define TSC_ADAIN_BWD_DISPATCH(FN, ...)                                                          \
+    do {                                                                                     \
+        if ((L & 3) == 0) {                                                                  \
+            if (L <= 128) return FN<32, 1, 4>(__VA_ARGS__);                                  \
+            if (L <= 256) return FN<32, 2, 4>(__VA_ARGS__);                                  \
+            if (L <= 512) return FN<32, 4, 4>(__VA_ARGS__);                                  \
+            if (L <= 1024) return FN<256, 1, 4>(__VA_ARGS__);   /* three tensors in registers */ \
             if (L <= 2048) return FN<256, 2, 4>(__VA_ARGS__);                                \
             if (L <= 4096) return FN<256, 4, 4>(__VA_ARGS__);                                \
             if (L <= 8192) return FN<256, 8, 4>(__VA_ARGS__);                                \
@@ -379,7 +443,7 @@ int tsc_adain_bwd(const float* dy, const float* content, const float* style, con
     TSC_REQUIRE(dy && content && style && stats && dcontent && dstyle, "NULL tensor");
     TSC_REQUIRE(R > 0 && L > 1, "bad shape [%d,%d]", R, L);
     cudaStream_t cs = (cudaStream_t)stream;
-    TSC_ADAIN_DISPATCH(launch_adain_bwd, dy, content, style, stats, dcontent, dstyle, R, L, cs);
+    TSC_ADAIN_BWD_DISPATCH(launch_adain_bwd, dy, content, style, stats, dcontent, dstyle, R, L, cs);
 }
 
 size_t tsc_gram_workspace_bytes(int B, int C, int L) {
