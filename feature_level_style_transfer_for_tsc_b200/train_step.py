@@ -79,16 +79,16 @@ class StyleTransferModelSet(nn.Module):
             if side is None:
                 side = self._side_stream = torch.cuda.Stream()
             side.wait_stream(main)
-            tf = self.fe_t(xt)
-            with torch.cuda.stream(side):
+            with torch.cuda.stream(side):             # the longer branch: source extractor + DimensionUnification
                 sf = self.fe_s(xs)
                 ssf = self.du(sf)
+            tf = self.fe_t(xt)
+            logits_t, _ = self.cl_t(tf)               # needs tf only: runs while the source branch is still busy
+            ce_t = F.cross_entropy(logits_t, yt)
             main.wait_stream(side)
             ssf.record_stream(main)
             s2t = TF.adain(ssf, tf)
             l_style = TF.gram_style_loss(s2t, tf)
-            logits_t, _ = self.cl_t(tf)
-            ce_t = F.cross_entropy(logits_t, yt)
             with torch.cuda.stream(side):
                 logits_s, _ = self.cl_s(ssf)
                 ce_s = F.cross_entropy(logits_s, ys)
