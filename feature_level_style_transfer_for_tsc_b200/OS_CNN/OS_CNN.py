@@ -10,11 +10,13 @@ implicit GEMM, BatchNorm statistics / apply, ReLU, shortcut add) on the c8 devic
 There is no CPU path: inputs must be CUDA fp32 tensors and ``libtsc_b200.so`` must be built.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
 
 from .. import ops
+from .. import functional as _F
 from ..functional import LayerSpec, StackSpec, direct_grads, os_stack
 
 
@@ -86,7 +88,7 @@ def _bn_params(conv, bn):
     return [conv.weight, conv.bias, bn.weight, bn.bias]
 
 
-def _run_stack(layers, x, shortcut=None, final_relu=False):
+def _run_stack(layers, x, shortcut=None, final_relu=False, pooled=False):
     specs, params = [], []
     for layer in layers:
         specs.append(_bn_layer_spec(layer.geometry, layer.bn, layer.relu_or_not_at_last_layer))
@@ -96,10 +98,15 @@ def _run_stack(layers, x, shortcut=None, final_relu=False):
         sc_spec = _bn_layer_spec(shortcut.geometry, shortcut.bn, False, zero_masked=False)
         params += _bn_params(shortcut.conv1d, shortcut.bn)
     spec = StackSpec(layers=specs, shortcut=sc_spec, final_relu=final_relu, engine=ops.get_engine("conv"),
-                     wgrad_engine=ops.get_engine("wgrad"), op_dtype=ops.op_dtype(), direct_grads=direct_grads())
+                     wgrad_engine=ops.get_engine("wgrad"), op_dtype=ops.op_dtype(), direct_grads=direct_grads(),
+                     pooled=(pooled and shortcut is None and ops.engine_name() == "tcgen05" and _F.FUSED_PATH
+                             and os.environ.get("TSC_NO_POOLED") != "1"))
     if x.dtype != torch.float32:
         raise RuntimeError(f"OS-CNN input must be float32 (the reference casts with .float()), got {x.dtype}")
-    return os_stack(spec, x.contiguous(), params)
+    out = os_stack(spec, x.contiguous(), params)
+    if pooled and not spec.pooled:
+        out = out.mean(dim=-1)                    # engines without the fused pooled epilogue
+    return out
 
 
 class build_layer_with_layer_parameter(nn.Module):
@@ -141,8 +148,7 @@ class OS_CNN(nn.Module):
         self.length_before_classification = out_put_channel_numebr
 
     def forward(self, X):
-        X = _run_stack(list(self.net), X)
-        X_f = X.mean(dim=-1)                      # AdaptiveAvgPool1d(1) + squeeze(-1)
+        X_f = _run_stack(list(self.net), X, pooled=True)        # AdaptiveAvgPool1d(1) + squeeze(-1), fused into the stack
         if not self.few_shot:
             return self.hidden(X_f), X_f
         return X_f.unsqueeze(-1), X_f

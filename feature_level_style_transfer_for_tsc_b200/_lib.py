@@ -22,7 +22,7 @@ HEADER = os.path.join(_ROOT, "include", "tsc_b200.h")
 TSC_F32, TSC_BF16 = 0, 1
 ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1
 DIR_FWD, DIR_DGRAD = 0, 1
-OUT_C8_F32, OUT_C8_BF16, OUT_NCL_F32 = 0, 1, 2
+OUT_C8_F32, OUT_C8_BF16, OUT_NCL_F32, OUT_POOLED = 0, 1, 2, 3
 MAX_TAPS, MAX_CHANNELS = 96, 256
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -89,6 +89,7 @@ SIGNATURES = {
     "tsc_bn_apply_fused": (_i, [_bp, _bp, _i, _i, _p, _i, _i, _i, _i, _p]),
     "tsc_bn_fused_splits": (_i, [_i, _i, _i]),
     "tsc_bn_bwd_top": (_i, [_p, _bbp, _bbp, _i, _p, _i, _i, _i, _p]),
+    "tsc_bn_bwd_top_pooled": (_i, [_p, _bbp, _i, _p, _i, _i, _i, _p]),
     "tsc_bn_bwd_apply_fused": (_i, [_p, _bbp, _i, _i, _p, _i, _i, _i, _i, _p]),
     "tsc_rmsprop_step": (_i, [_p, _p, _p, ctypes.c_longlong, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_float),
                          _i, _f, _f, _f, _p]),

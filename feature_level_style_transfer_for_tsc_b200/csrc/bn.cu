@@ -550,12 +550,50 @@ __global__ void __launch_bounds__(BF_THREADS) bn_apply_fused_kernel(const tsc_bn
     }
 }
 
+// Pooled output: out[b][c] = mean_l act(scale*y + shift).  grid (Cpc, S): block = one chunk x a range of whole samples.
+__global__ void __launch_bounds__(BF_THREADS) bn_apply_pooled_kernel(const tsc_bn_branch a, int n_part, int relu,
+                                                                      float* __restrict__ out, int B, int C, int Cpc, int L,
+                                                                      int S) {
+    __shared__ float coef_a[32], sh[64];
+    const int ch = blockIdx.x, sp = blockIdx.y;
+    const int ltiles = (L + 127) / 128;
+    bn_branch_coeffs(a, ch, C, Cpc * 8, n_part, ltiles, L, sp == 0, coef_a, sh);
+    float sc[8], sf[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = coef_a[16 + j]; sf[j] = coef_a[24 + j]; }
+    const int b0 = (int)((long long)B * sp / S), b1 = (int)((long long)B * (sp + 1) / S);
+    const float inv_l = 1.f / (float)L;
+    for (int bb = b0; bb < b1; ++bb) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int l = threadIdx.x; l < L; l += BF_THREADS) {
+            Row8<float> v;
+            v.load(a.y_c8 + (((long long)bb * Cpc + ch) * L + l) * 8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float o = fmaf(v.v[j], sc[j], sf[j]);
+                if (relu) o = fmaxf(o, 0.f);
+                acc[j] += o;
+            }
+        }
+        block_sum8(acc, sh);
+        if (threadIdx.x < 8) {
+            const int j = threadIdx.x, c = ch * 8 + j;
+            float v = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { if (k == j) v = acc[k]; }
+            if (c < C) out[(long long)bb * C + c] = v * inv_l;
+        }
+    }
+}
+
 // Top of a stack: the incoming gradient is NCL fp32.  d = dout * [z > 0] (z = scale*y + shift [+ second branch]) is
 // written as c8 fp32 and the per-block partial sums (S1, S2) of each branch go to red_partial[S][Cp][2].
 __global__ void __launch_bounds__(BF_THREADS) bn_bwd_top_kernel(const float* __restrict__ dout, const tsc_bn_bwd_branch a,
                                                                  const tsc_bn_bwd_branch b2, int two, int relu,
                                                                  float* __restrict__ d_c8, int B, int C, int Cpc, int L,
-                                                                 int S) {
+                                                                 int S, int pooled) {
     __shared__ float sh[64];
     const int ch = blockIdx.x, sp = blockIdx.y, Cp = Cpc * 8;
     float mean[8], invstd[8], sc[8], sf[8], mean2[8], invstd2[8], sc2[8], sf2[8];
@@ -580,7 +618,8 @@ __global__ void __launch_bounds__(BF_THREADS) bn_bwd_top_kernel(const float* __r
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = ch * 8 + j;
-            float g = c < C ? __ldg(dout + ((long long)bb * C + c) * L + l) : 0.f;
+            float g = 0.f;
+            if (c < C) g = pooled ? __ldg(dout + (long long)bb * C + c) / (float)L : __ldg(dout + ((long long)bb * C + c) * L + l);
             if (relu) {
                 float z = fmaf(y.v[j], sc[j], sf[j]);
                 if (two) z += fmaf(y2.v[j], sc2[j], sf2[j]);
@@ -693,6 +732,12 @@ int tsc_bn_apply_fused(const tsc_bn_branch* a, const tsc_bn_branch* b, int n_par
         case TSC_OUT_C8_F32: bn_apply_fused_kernel<TSC_OUT_C8_F32><<<grid, BF_THREADS, 0, cs>>>(*a, bb, b != nullptr, n_part, relu, out, B, C, Cpc, L, S); break;
         case TSC_OUT_C8_BF16: bn_apply_fused_kernel<TSC_OUT_C8_BF16><<<grid, BF_THREADS, 0, cs>>>(*a, bb, b != nullptr, n_part, relu, out, B, C, Cpc, L, S); break;
         case TSC_OUT_NCL_F32: bn_apply_fused_kernel<TSC_OUT_NCL_F32><<<grid, BF_THREADS, 0, cs>>>(*a, bb, b != nullptr, n_part, relu, out, B, C, Cpc, L, S); break;
+        case TSC_OUT_POOLED: {
+            TSC_REQUIRE(b == nullptr, "pooled output supports a single branch");
+            const int Sb = S < B ? S : B;
+            bn_apply_pooled_kernel<<<dim3(Cpc, Sb), BF_THREADS, 0, cs>>>(*a, n_part, relu, (float*)out, B, C, Cpc, L, Sb);
+            break;
+        }
         default: TSC_REQUIRE(false, "bad out_kind %d", out_kind);
     }
     TSC_LAUNCH_CHECK();
@@ -708,7 +753,18 @@ int tsc_bn_bwd_top(const float* dout_ncl, const tsc_bn_bwd_branch* a, const tsc_
     const int Cpc = pad16(C) / 8, S = bn_splits(B, Cpc, L);
     const tsc_bn_bwd_branch bb = b ? *b : *a;
     bn_bwd_top_kernel<<<dim3(Cpc, S), BF_THREADS, 0, (cudaStream_t)stream>>>(dout_ncl, *a, bb, b != nullptr, relu, d_c8, B, C,
-                                                                            Cpc, L, S);
+                                                                            Cpc, L, S, 0);
+    TSC_LAUNCH_CHECK();
+    return 0;
+}
+
+int tsc_bn_bwd_top_pooled(const float* dpooled, const tsc_bn_bwd_branch* a, int relu, float* d_c8, int B, int C, int L,
+                          tsc_stream_t stream) {
+    using namespace tsc;
+    TSC_REQUIRE(dpooled && a && a->y_c8 && a->coef && a->red_partial && d_c8, "NULL argument");
+    TSC_REQUIRE(B > 0 && C > 0 && L > 0, "bad shape [%d,%d,%d]", B, C, L);
+    const int Cpc = pad16(C) / 8, S = bn_splits(B, Cpc, L);
+    bn_bwd_top_kernel<<<dim3(Cpc, S), BF_THREADS, 0, (cudaStream_t)stream>>>(dpooled, *a, *a, 0, relu, d_c8, B, C, Cpc, L, S, 1);
     TSC_LAUNCH_CHECK();
     return 0;
 }

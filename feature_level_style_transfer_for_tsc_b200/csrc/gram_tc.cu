@@ -190,13 +190,21 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gram_fwd_tc_kernel(const GramFw
                 float v[16];
                 tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * p.Np + c0), v);
                 if (i < C) {
+                    float d[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        if (c0 + j < C) {
-                            const float d = v[j] * p.inv_cl;
-                            drow[c0 + j] = d;
-                            sq = fmaf(d, d, sq);
-                        }
+                        d[j] = c0 + j < C ? v[j] * p.inv_cl : 0.f;
+                        sq = fmaf(d[j], d[j], sq);
+                    }
+                    if ((C & 3) == 0) {
+                        // rows of D are 16 B aligned: 64 contiguous bytes per thread in four vector stores
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4)
+                            if (c0 + j < C) *reinterpret_cast<float4*>(drow + c0 + j) = make_float4(d[j], d[j + 1], d[j + 2], d[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c0 + j < C) drow[c0 + j] = d[j];
                     }
                 }
             }

@@ -46,6 +46,7 @@ class StackSpec:
     wgrad_engine: int
     op_dtype: int                      # operand dtype of the stack (bf16 for the tensor-core engine)
     direct_grads: bool = False         # backward adds parameter gradients straight into the existing .grad buffers
+    pooled: bool = False               # return mean over L, [B, C] (the classifier's AdaptiveAvgPool1d(1) + squeeze)
 
 
 class _Saved:
@@ -123,7 +124,7 @@ def _fused_forward(spec: StackSpec, sv: "_Saved", x: torch.Tensor, params, need_
         if i < nl - 1:
             h = ops.bn_apply_fused(br, None, g.cout, ls.relu, L.OUT_C8_BF16)
         elif spec.shortcut is None:
-            out = ops.bn_apply_fused(br, None, g.cout, ls.relu, L.OUT_NCL_F32)
+            out = ops.bn_apply_fused(br, None, g.cout, ls.relu, L.OUT_POOLED if spec.pooled else L.OUT_NCL_F32)
         else:
             sc = spec.shortcut
             Wr, br_, gr, betar = params[4 * nl: 4 * nl + 4]
@@ -198,6 +199,8 @@ def _fused_backward(spec: StackSpec, sv: "_Saved", params, dout: torch.Tensor, x
         wgrad(4 * nl, sc.geom, dy_r, sv.x_ops[0])
         if x_requires_grad:
             dx_short = ops.osconv(eng, L.DIR_DGRAD, sc.geom, dy_r, sv.wd_r, None)
+    elif spec.pooled:
+        d = ops.bn_bwd_top_pooled(dout, a_top, last.relu, Ln)
     else:
         d = ops.bn_bwd_top(dout, a_top, None, last.relu)
     cur, n_part = a_top, S_top

@@ -411,6 +411,8 @@ def bn_apply_fused(a: BNLayerFwd, b: Optional[BNLayerFwd], C: int, relu: bool, o
     B, cpc, Ln, _ = a.y8.shape
     if out_kind == L.OUT_NCL_F32:
         out = torch.empty((B, C, Ln), device=a.y8.device, dtype=torch.float32)
+    elif out_kind == L.OUT_POOLED:
+        out = torch.empty((B, C), device=a.y8.device, dtype=torch.float32)
     else:
         out = torch.empty((B, cpc, Ln, 8), device=a.y8.device,
                           dtype=torch.bfloat16 if out_kind == L.OUT_C8_BF16 else torch.float32)
@@ -456,6 +458,16 @@ def bn_bwd_top(dout: torch.Tensor, a: BNLayerBwd, b: Optional[BNLayerBwd], relu:
     cb = b.c() if b is not None else None
     L.check(L.load().tsc_bn_bwd_top(_ptr(dout), ctypes.byref(ca), ctypes.byref(cb) if cb is not None else None,
                                     1 if relu else 0, _ptr(d8), B, C, Ln, _stream()), "tsc_bn_bwd_top")
+    return d8
+
+
+def bn_bwd_top_pooled(dpooled: torch.Tensor, a: BNLayerBwd, relu: bool, Ln: int) -> torch.Tensor:
+    _req(dpooled, name="dpooled")
+    B, C = dpooled.shape
+    d8 = torch.empty_like(a.y8)
+    ca = a.c()
+    L.check(L.load().tsc_bn_bwd_top_pooled(_ptr(dpooled), ctypes.byref(ca), 1 if relu else 0, _ptr(d8), B, C, Ln, _stream()),
+            "tsc_bn_bwd_top_pooled")
     return d8
 
 

@@ -47,7 +47,9 @@ enum tsc_dtype { TSC_F32 = 0, TSC_BF16 = 1 };
  * fp32 accumulation in TMEM (the "<=1e-2" mode). */
 enum tsc_engine { TSC_ENGINE_SIMT = 0, TSC_ENGINE_TCGEN05 = 1 };
 enum tsc_direction { TSC_DIR_FWD = 0, TSC_DIR_DGRAD = 1 };
-enum tsc_out_kind { TSC_OUT_C8_F32 = 0, TSC_OUT_C8_BF16 = 1, TSC_OUT_NCL_F32 = 2 };
+/* TSC_OUT_POOLED (fused BatchNorm apply only): out[B, C] = mean over L of the activated output -- the
+ * AdaptiveAvgPool1d(1) + squeeze of the classifier (OS_CNN.py:93,105) without materialising [B, C, L] */
+enum tsc_out_kind { TSC_OUT_C8_F32 = 0, TSC_OUT_C8_BF16 = 1, TSC_OUT_NCL_F32 = 2, TSC_OUT_POOLED = 3 };
 
 int tsc_version(void);
 const char* tsc_last_error(void);
@@ -206,6 +208,9 @@ typedef struct tsc_bn_bwd_branch {
  * of branch a (and b: same d, its own yhat). */
 int tsc_bn_bwd_top(const float* dout_ncl, const tsc_bn_bwd_branch* a, const tsc_bn_bwd_branch* b, int relu, float* d_c8,
                    int B, int C, int L, tsc_stream_t stream);
+/* The same when the stack's output was pooled (TSC_OUT_POOLED): dpooled [B, C], dout[b,c,l] = dpooled[b,c] / L. */
+int tsc_bn_bwd_top_pooled(const float* dpooled, const tsc_bn_bwd_branch* a, int relu, float* d_c8, int B, int C, int L,
+                          tsc_stream_t stream);
 /* dy = gamma*invstd*(d - S1/N - yhat*S2/N) (training) or gamma*invstd*d (eval) as c8(dy_dtype); d is already masked;
  * (S1, S2) = sum of the n_part rows of red_partial.  Also dgamma = S2, dbeta = S1, dbias (+= when accumulate). */
 int tsc_bn_bwd_apply_fused(const float* d_c8, const tsc_bn_bwd_branch* a, int n_part, int accumulate, void* dy_c8,
