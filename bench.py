@@ -289,6 +289,8 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"             # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     T._lib.load()
     T.set_engine(args.engine)
@@ -394,7 +396,7 @@ def run_ours(args):
                             series_per_step_per_gpu=2 * B, engine=args.engine, parallelism=f"dp{world}",
                             cuda_graph=not args.no_graph,
                             l2="flushed between timed steps (256 MiB write, outside the per-step events)"),
-                e2e=dict(value=series / t_e2e, unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=4,
+                e2e=dict(value=series / t_e2e, unit=UNIT, h2d_bytes_per_step=h2d_bytes * world, d2h_bytes_per_step=4 * world,
                          ms_per_step=t_e2e / args.steps * 1e3),
                 gpu_launches=int(launches), clocks=clocks.summary(), roofline=roof, kernels=kern)
     if cpu:

@@ -191,6 +191,78 @@ def test_cfg1_full_width(T, tables, cfg1_seeded, engine, tol):
     T.set_engine("tcgen05")
 
 
+@pytest.mark.parametrize("engine,tol", [("simt", 2e-4), ("tcgen05", 1.5e-2)])
+def test_cfg4_long_series_against_the_oracle(T, engine, tol):
+    """cfg4 shapes (C=3, L=1024, primes up to 89, widths 25 / 225 / 50) at a small batch: the extractor + classifier
+    forward, the loss, and the first layer's live-tap weight gradient against the CPU oracle on the same seed."""
+    T.set_engine(engine)
+    C, Ln, K, B = 3, 1024, 4, 3
+    lpl_e, lpl_c = O.trainer_layer_lists(C, Ln)
+    fe, cl = build_modules(T, lpl_e, lpl_c, K, 5)
+    torch.manual_seed(5)
+    ofe, ocl = O.init_extractor(lpl_e), O.init_classifier(lpl_c, K)
+    ofe, ocl = O.clone_state(ofe, requires_grad=True), O.clone_state(ocl, requires_grad=True)
+    x, y = O.synthetic_batch(B, C, Ln, K, 3)
+    feat = fe(x.cuda())
+    logits, pooled = cl(feat)
+    loss = torch.nn.functional.cross_entropy(logits, y.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    assert T.ops.read_watchdog() == 0
+    ofeat = O.extractor_forward(ofe, lpl_e, x, True)
+    ologits, opooled = O.classifier_forward(ocl, lpl_c, ofeat, True)
+    oloss = torch.nn.functional.cross_entropy(ologits, y)
+    oloss.backward()
+    assert rel_err(feat.detach().cpu(), ofeat.detach()) < tol
+    assert rel_err(pooled.detach().cpu(), opooled.detach()) < tol
+    assert rel_err(logits.detach().cpu(), ologits.detach()) < 4 * tol
+    assert abs(float(loss) - float(oloss)) < 10 * tol
+    gh = cl.hidden.weight.grad.cpu().numpy()
+    assert l2_rel(gh, ocl["hidden.weight"].grad.numpy()) < (1e-4 if engine == "simt" else 2e-2)
+    gw = cl.net[2].conv1d.weight.grad.cpu().numpy()
+    gref = ocl["net.2.conv1d.weight"].grad.numpy() * O.build_mask(lpl_c[2])
+    # Behind the average pool the incoming gradient is constant along L, and BatchNorm's backward removes its
+    # projections on {1, yhat}: what is left is a small residual that amplifies the bf16 rounding of yhat (SURVEY F7;
+    # worst for this layer and a batch of 3).  Tight for the fp32 engine, an L2 sanity bound for the bf16 one.
+    assert (rel_err(gw, gref) < 1e-3) if engine == "simt" else (l2_rel(gw, gref) < 0.3)
+    assert np.abs(fe.net_1.net.net[1].conv1d.weight.grad.cpu().numpy() * (1 - O.build_mask(lpl_e[1]))).max() == 0.0
+    T.set_engine("tcgen05")
+
+
+def test_eval_mode_batchnorm_with_grad_on_the_fused_path(T):
+    """train_and_test.py:583-586: the classifier is flipped to .eval() for one forward WITH autograd.  The fused path
+    then takes its BatchNorm coefficients from the running statistics, leaves them untouched, and its backward is a
+    per-channel scale (plus a real conv-bias gradient)."""
+    T.set_engine("tcgen05")
+    lpl_e, lpl_c = O.trainer_layer_lists(9, 128)
+    from feature_level_style_transfer_for_tsc_b200.OS_CNN.OS_CNN import OS_CNN
+    torch.manual_seed(2)
+    cl = OS_CNN(lpl_c, 6).cuda()
+    x = torch.randn(4, 144, 128, device="cuda").abs().requires_grad_(True)
+    cl.train()
+    cl(x)                                               # one training pass so that the running statistics are not (0, 1)
+    before = {k: v.clone() for k, v in cl.state_dict().items() if "running" in k or "num_batches" in k}
+    cl.eval()
+    logits, _ = cl(x)
+    logits.square().sum().backward()
+    torch.cuda.synchronize()
+    for k, v in before.items():
+        assert torch.equal(cl.state_dict()[k], v), k
+    # the same network in plain torch (fp32) on the same bf16-rounded operands is not available: compare with the
+    # fp32 engine, whose eval-mode path is checked against the oracle in test_small_pair_fp32_engine
+    g_tc = {k: p.grad.clone() for k, p in cl.named_parameters()}
+    dx_tc = x.grad.clone()
+    T.set_engine("simt")
+    cl.zero_grad(); x.grad = None
+    logits2, _ = cl(x)
+    logits2.square().sum().backward()
+    assert rel_err(logits.detach().cpu(), logits2.detach().cpu()) < 1e-2
+    assert l2_rel(dx_tc.cpu(), x.grad.cpu()) < 0.15          # three bf16 layers against three fp32 layers
+    bias_g = g_tc["net.0.conv1d.bias"]
+    assert float(bias_g.abs().max()) > 0 and l2_rel(bias_g.cpu(), dict(cl.named_parameters())["net.0.conv1d.bias"].grad.cpu()) < 0.15
+    T.set_engine("tcgen05")
+
+
 def test_autograd_semantics_of_the_reference_trainer(T):
     """retain_graph + second backward, autograd.grad on a sub-loss over return_last_layer().parameters()
     (train_and_test.py:678-690,741), and the eval-mode forward with gradient (train_and_test.py:583-586)."""
