@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include <string.h>
 #include <algorithm>
+#include <stdlib.h>
 
 namespace tsc {
 
@@ -12,6 +13,13 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+bool pdl_enabled() {
+    // off by default: measured on the cfg2 step it costs 2-3 % (early-resident CTAs of the next kernel take the SM slot
+    // that the other branch's stream would have used) -- profiles/README.md; TSC_PDL=1 switches it on
+    static const bool on = [] { const char* e = getenv("TSC_PDL"); return e && e[0] == '1'; }();
+    return on;
 }
 
 // Per-tap geometry of the implicit GEMM (see TapTable in common.cuh).

@@ -503,6 +503,8 @@ __global__ void __launch_bounds__(BF_THREADS) bn_apply_fused_kernel(const tsc_bn
                                                                      int n_part, int relu, void* __restrict__ out, int B,
                                                                      int C, int Cpc, int L, int S) {
     __shared__ float coef_a[32], coef_b[32], sh[64];
+    pdl_trigger();
+    pdl_wait();
     const int ch = blockIdx.x, sp = blockIdx.y;
     const int ltiles = (L + 127) / 128;
     bn_branch_coeffs(a, ch, C, Cpc * 8, n_part, ltiles, L, sp == 0, coef_a, sh);
@@ -555,6 +557,8 @@ __global__ void __launch_bounds__(BF_THREADS) bn_apply_pooled_kernel(const tsc_b
                                                                       float* __restrict__ out, int B, int C, int Cpc, int L,
                                                                       int S) {
     __shared__ float coef_a[32], sh[64];
+    pdl_trigger();
+    pdl_wait();
     const int ch = blockIdx.x, sp = blockIdx.y;
     const int ltiles = (L + 127) / 128;
     bn_branch_coeffs(a, ch, C, Cpc * 8, n_part, ltiles, L, sp == 0, coef_a, sh);
@@ -595,6 +599,8 @@ __global__ void __launch_bounds__(BF_THREADS) bn_bwd_top_kernel(const float* __r
                                                                  float* __restrict__ d_c8, int B, int C, int Cpc, int L,
                                                                  int S, int pooled) {
     __shared__ float sh[64];
+    pdl_trigger();
+    pdl_wait();
     const int ch = blockIdx.x, sp = blockIdx.y, Cp = Cpc * 8;
     float mean[8], invstd[8], sc[8], sf[8], mean2[8], invstd2[8], sc2[8], sf2[8];
 #pragma unroll
@@ -653,6 +659,8 @@ __global__ void __launch_bounds__(BF_THREADS) bn_bwd_apply_fused_kernel(const fl
                                                                          int n_part, int accumulate, T* __restrict__ dy,
                                                                          int B, int C, int Cpc, int L, int S) {
     __shared__ float sh[64];
+    pdl_trigger();
+    pdl_wait();
     const int ch = blockIdx.x, sp = blockIdx.y, Cp = Cpc * 8;
     float s1[8], s2[8];
 #pragma unroll
@@ -729,13 +737,13 @@ int tsc_bn_apply_fused(const tsc_bn_branch* a, const tsc_bn_branch* b, int n_par
     cudaStream_t cs = (cudaStream_t)stream;
     dim3 grid(Cpc, S);
     switch (out_kind) {
-        case TSC_OUT_C8_F32: bn_apply_fused_kernel<TSC_OUT_C8_F32><<<grid, BF_THREADS, 0, cs>>>(*a, bb, b != nullptr, n_part, relu, out, B, C, Cpc, L, S); break;
-        case TSC_OUT_C8_BF16: bn_apply_fused_kernel<TSC_OUT_C8_BF16><<<grid, BF_THREADS, 0, cs>>>(*a, bb, b != nullptr, n_part, relu, out, B, C, Cpc, L, S); break;
-        case TSC_OUT_NCL_F32: bn_apply_fused_kernel<TSC_OUT_NCL_F32><<<grid, BF_THREADS, 0, cs>>>(*a, bb, b != nullptr, n_part, relu, out, B, C, Cpc, L, S); break;
+        case TSC_OUT_C8_F32: launch_pdl(bn_apply_fused_kernel<TSC_OUT_C8_F32>, grid, dim3(BF_THREADS), 0, cs, *a, bb, (int)(b != nullptr), n_part, relu, out, B, C, Cpc, L, S); break;
+        case TSC_OUT_C8_BF16: launch_pdl(bn_apply_fused_kernel<TSC_OUT_C8_BF16>, grid, dim3(BF_THREADS), 0, cs, *a, bb, (int)(b != nullptr), n_part, relu, out, B, C, Cpc, L, S); break;
+        case TSC_OUT_NCL_F32: launch_pdl(bn_apply_fused_kernel<TSC_OUT_NCL_F32>, grid, dim3(BF_THREADS), 0, cs, *a, bb, (int)(b != nullptr), n_part, relu, out, B, C, Cpc, L, S); break;
         case TSC_OUT_POOLED: {
             TSC_REQUIRE(b == nullptr, "pooled output supports a single branch");
             const int Sb = S < B ? S : B;
-            bn_apply_pooled_kernel<<<dim3(Cpc, Sb), BF_THREADS, 0, cs>>>(*a, n_part, relu, (float*)out, B, C, Cpc, L, Sb);
+            launch_pdl(bn_apply_pooled_kernel, dim3(Cpc, Sb), dim3(BF_THREADS), 0, cs, *a, n_part, relu, (float*)out, B, C, Cpc, L, Sb);
             break;
         }
         default: TSC_REQUIRE(false, "bad out_kind %d", out_kind);
@@ -752,8 +760,8 @@ int tsc_bn_bwd_top(const float* dout_ncl, const tsc_bn_bwd_branch* a, const tsc_
     TSC_REQUIRE(B > 0 && C > 0 && L > 0, "bad shape [%d,%d,%d]", B, C, L);
     const int Cpc = pad16(C) / 8, S = bn_splits(B, Cpc, L);
     const tsc_bn_bwd_branch bb = b ? *b : *a;
-    bn_bwd_top_kernel<<<dim3(Cpc, S), BF_THREADS, 0, (cudaStream_t)stream>>>(dout_ncl, *a, bb, b != nullptr, relu, d_c8, B, C,
-                                                                            Cpc, L, S, 0);
+    launch_pdl(bn_bwd_top_kernel, dim3(Cpc, S), dim3(BF_THREADS), 0, (cudaStream_t)stream, dout_ncl, *a, bb, (int)(b != nullptr), relu, d_c8,
+               B, C, Cpc, L, S, 0);
     TSC_LAUNCH_CHECK();
     return 0;
 }
@@ -764,7 +772,7 @@ int tsc_bn_bwd_top_pooled(const float* dpooled, const tsc_bn_bwd_branch* a, int 
     TSC_REQUIRE(dpooled && a && a->y_c8 && a->coef && a->red_partial && d_c8, "NULL argument");
     TSC_REQUIRE(B > 0 && C > 0 && L > 0, "bad shape [%d,%d,%d]", B, C, L);
     const int Cpc = pad16(C) / 8, S = bn_splits(B, Cpc, L);
-    bn_bwd_top_kernel<<<dim3(Cpc, S), BF_THREADS, 0, (cudaStream_t)stream>>>(dpooled, *a, *a, 0, relu, d_c8, B, C, Cpc, L, S, 1);
+    launch_pdl(bn_bwd_top_kernel, dim3(Cpc, S), dim3(BF_THREADS), 0, (cudaStream_t)stream, dpooled, *a, *a, 0, relu, d_c8, B, C, Cpc, L, S, 1);
     TSC_LAUNCH_CHECK();
     return 0;
 }
@@ -779,9 +787,9 @@ int tsc_bn_bwd_apply_fused(const float* d_c8, const tsc_bn_bwd_branch* a, int n_
     cudaStream_t cs = (cudaStream_t)stream;
     dim3 grid(Cpc, S);
     if (dy_dtype == TSC_BF16)
-        bn_bwd_apply_fused_kernel<__nv_bfloat16><<<grid, BF_THREADS, 0, cs>>>(d_c8, *a, n_part, accumulate, (__nv_bfloat16*)dy_c8, B, C, Cpc, L, S);
+        launch_pdl(bn_bwd_apply_fused_kernel<__nv_bfloat16>, grid, dim3(BF_THREADS), 0, cs, d_c8, *a, n_part, accumulate, (__nv_bfloat16*)dy_c8, B, C, Cpc, L, S);
     else if (dy_dtype == TSC_F32)
-        bn_bwd_apply_fused_kernel<float><<<grid, BF_THREADS, 0, cs>>>(d_c8, *a, n_part, accumulate, (float*)dy_c8, B, C, Cpc, L, S);
+        launch_pdl(bn_bwd_apply_fused_kernel<float>, grid, dim3(BF_THREADS), 0, cs, d_c8, *a, n_part, accumulate, (float*)dy_c8, B, C, Cpc, L, S);
     else
         TSC_REQUIRE(false, "bad dtype %d", dy_dtype);
     TSC_LAUNCH_CHECK();

@@ -27,6 +27,33 @@ void set_error(const char* fmt, ...);
         }                                                             \
     } while (0)
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------
+// The step is a chain of ~100 short dependent kernels.  Kernels launched through launch_pdl carry the
+// programmatic-stream-serialization attribute: the next kernel of the stream may be scheduled, and run its
+// prologue (barrier init, TMEM allocation, shared-memory clearing), while this one drains; it blocks in
+// pdl_wait() -- which every such kernel executes before its first global-memory access -- until the whole
+// preceding grid has completed and flushed.  pdl_trigger() marks the point from which dependents may be launched.
+// The attribute is opt-in (TSC_PDL=1): without it the device-side calls are no-ops.
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline int pad16(int c) { return (c + 15) & ~15; }
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 

@@ -139,6 +139,7 @@ osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const ConvTcParams p)
         mbar_init(acc_full, 1);
         mbar_init(plan_full, 1);
         fence_barrier_init();
+        pdl_wait();               // everything above overlapped the tail of the previous kernel of the stream
         mbar_arrive_expect_tx(plan_full, (uint32_t)p.plan_bytes);
         bulk_load(smem + p.off_plan, p.plan, (uint32_t)p.plan_bytes, plan_full);
         mbar_arrive_expect_tx(x_full, (uint32_t)(p.kc * p.Rp * 16));
@@ -146,6 +147,7 @@ osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const ConvTcParams p)
     }
     if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     if (warp >= 2) {
+        pdl_wait();
         // zero block at the end of every stage slot (read by the padding MMAs that round a stage up to MMA_GROUP)
         for (int i = threadIdx.x - 64; i < p.NS * 32; i += 128)
             *reinterpret_cast<uint4*>(stages + (size_t)(i >> 5) * (p.stage_bytes + ZERO_BLOCK_BYTES) + p.stage_bytes + (i & 31) * 16) =
@@ -172,6 +174,7 @@ osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const ConvTcParams p)
         // ===== copy producer: one bulk copy per plan stage =====
         if (lane == 0) {
             bool dead = false;
+            pdl_wait();
             TL(1);
             mbar_wait(plan_full, 0, dead, 8);
             const uint2* st = reinterpret_cast<const uint2*>(plan_s + 16);
@@ -234,6 +237,7 @@ osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const ConvTcParams p)
         }
         __syncwarp();
         if (elect_one()) tc_commit(acc_full);
+        pdl_trigger();            // the next kernel of the stream may start its prologue while the epilogue runs
         if (lane == 0) TL(4);
     } else {
         // ===== epilogue: TMEM -> registers -> (+bias | mask) -> c8 fp32 (+ per-CTA partial reductions) =====
@@ -563,7 +567,7 @@ int osconv_tc(int direction, const void* x, int dtype, const void* w, const void
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         attr_set = true;
     }
-    osconv_tc_kernel<<<B * p.ltiles, TC_THREADS, smem, cs>>>(xmap, p);
+    { cudaError_t le = launch_pdl(osconv_tc_kernel, dim3(B * p.ltiles), dim3(TC_THREADS), (size_t)smem, cs, xmap, p); if (le != cudaSuccess) { set_error("osconv launch: %s", cudaGetErrorString(le)); return (int)le; } }
     TSC_LAUNCH_CHECK();
     return 0;
 }

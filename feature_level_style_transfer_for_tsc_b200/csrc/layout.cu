@@ -9,6 +9,8 @@ namespace tsc {
 template <typename T>
 __global__ void __launch_bounds__(256) ncl_to_c8_kernel(const float* __restrict__ src, T* __restrict__ dst,
                                                          int B, int C, int Cpc, int L) {
+    pdl_trigger();
+    pdl_wait();
     const long long total = (long long)B * Cpc * L;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -28,6 +30,8 @@ __global__ void __launch_bounds__(256) ncl_to_c8_kernel(const float* __restrict_
 
 __global__ void __launch_bounds__(256) c8_to_ncl_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                                          int B, int C, int Cpc, int L) {
+    pdl_trigger();
+    pdl_wait();
     const long long total = (long long)B * Cpc * L;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -172,9 +176,9 @@ int tsc_ncl_to_c8(const float* src, void* dst, int dst_dtype, int B, int C, int 
     const long long rows = (long long)B * Cpc * L;
     cudaStream_t st = (cudaStream_t)stream;
     if (dst_dtype == TSC_BF16)
-        ncl_to_c8_kernel<__nv_bfloat16><<<grid_for(rows), 256, 0, st>>>(src, (__nv_bfloat16*)dst, B, C, Cpc, L);
+        launch_pdl(ncl_to_c8_kernel<__nv_bfloat16>, dim3(grid_for(rows)), dim3(256), 0, st, src, (__nv_bfloat16*)dst, B, C, Cpc, L);
     else if (dst_dtype == TSC_F32)
-        ncl_to_c8_kernel<float><<<grid_for(rows), 256, 0, st>>>(src, (float*)dst, B, C, Cpc, L);
+        launch_pdl(ncl_to_c8_kernel<float>, dim3(grid_for(rows)), dim3(256), 0, st, src, (float*)dst, B, C, Cpc, L);
     else
         TSC_REQUIRE(false, "bad dtype %d", dst_dtype);
     TSC_LAUNCH_CHECK();
@@ -186,7 +190,7 @@ int tsc_c8_to_ncl(const float* src, float* dst, int B, int C, int L, tsc_stream_
     TSC_REQUIRE(src && dst, "NULL tensor");
     TSC_REQUIRE(B > 0 && C > 0 && L > 0, "bad shape [%d,%d,%d]", B, C, L);
     const int Cpc = pad16(C) / 8;
-    c8_to_ncl_kernel<<<grid_for((long long)B * Cpc * L), 256, 0, (cudaStream_t)stream>>>(src, dst, B, C, Cpc, L);
+    launch_pdl(c8_to_ncl_kernel, dim3(grid_for((long long)B * Cpc * L)), dim3(256), 0, (cudaStream_t)stream, src, dst, B, C, Cpc, L);
     TSC_LAUNCH_CHECK();
     return 0;
 }
@@ -315,10 +319,12 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const __grid_constant__
     const int Cin = ly.Cin, Cout = ly.Cout, Kmax = ly.Kmax;
     const int np_f = (Cout + 15) & ~15, cin_p = (Cin + 15) & ~15;
     const int n_cc = np_f / 8, n_kp = cin_p / 16;
+    pdl_trigger();
     if ((int)blockIdx.x >= n_cc * n_kp) return;
     const int cc = blockIdx.x / n_kp, kp = blockIdx.x % n_kp;
     const int co0 = cc * 8, ci0 = kp * 16;
-    pack_build_taps(ly, &pt, scratch);
+    pack_build_taps(ly, &pt, scratch);       // geometry only: overlaps the tail of the previous kernel
+    pdl_wait();
     // ---- load (and mask in place) ----
     float* W = ly.W;
     const int slab = 16 * Kmax;
@@ -384,10 +390,10 @@ extern "C" int tsc_pack_weights_multi(int dtype, const tsc_pack_batch* batch, ts
     cudaStream_t cs = (cudaStream_t)stream;
     if (dtype == TSC_BF16) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(pack_multi_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        pack_multi_kernel<__nv_bfloat16><<<grid, 256, smem, cs>>>(*batch);
+        launch_pdl(pack_multi_kernel<__nv_bfloat16>, grid, dim3(256), (size_t)smem, cs, *batch);
     } else if (dtype == TSC_F32) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(pack_multi_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        pack_multi_kernel<float><<<grid, 256, smem, cs>>>(*batch);
+        launch_pdl(pack_multi_kernel<float>, grid, dim3(256), (size_t)smem, cs, *batch);
     } else {
         TSC_REQUIRE(false, "bad dtype %d", dtype);
     }

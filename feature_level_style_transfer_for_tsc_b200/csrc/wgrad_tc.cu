@@ -83,6 +83,7 @@ oswgrad_tc_kernel(const __grid_constant__ WgItems items, const WgParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                   // the prologue above overlapped the tail of the previous kernel of the stream
 
     if (warp == 0) {
         // (idle: the tiles are staged by the four epilogue warps)
@@ -126,6 +127,7 @@ oswgrad_tc_kernel(const __grid_constant__ WgItems items, const WgParams p) {
         }
         __syncwarp();
         if (elect_one()) tc_commit(acc_full);
+        pdl_trigger();
         if (wi == 0 && lane == 0) WTL(4);
     } else {
         bool dead = false;
@@ -185,6 +187,8 @@ __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __res
                                                                 const __grid_constant__ STable st, int S, int NT, int Cin,
                                                                 int Cout, int Kmax, int np, int cinp, int m_split,
                                                                 int accumulate) {
+    pdl_trigger();
+    pdl_wait();
     const int r = threadIdx.x & 7;
     const int co = blockIdx.x * 8 + r;
     const int t_base = blockIdx.y * 8;
@@ -317,12 +321,13 @@ int oswgrad_tc(const void* dy, const void* x, int dtype, float* dW, void* worksp
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         attr_set = true;
     }
-    oswgrad_tc_kernel<<<dim3(items.n, p.S), WG_THREADS, smem, cs>>>(items, p);
+    { cudaError_t le = launch_pdl(oswgrad_tc_kernel, dim3(items.n, p.S), dim3(WG_THREADS), (size_t)smem, cs, items, p); if (le != cudaSuccess) { set_error("oswgrad launch: %s", cudaGetErrorString(le)); return (int)le; } }
     TSC_LAUNCH_CHECK();
     STable st;
     fill_stable(&st, s_of_tap, Kmax);
-    wgrad_tc_reduce_kernel<<<dim3(cdiv(Cout, 8), cdiv(Kmax, 8), cdiv(Cin, 32)), 256, 0, cs>>>(p.part, dW, items, lk, st, p.S, NT, Cin, Cout,
-                                                                          Kmax, np, cinp, m_split, accumulate);
+    { cudaError_t le = launch_pdl(wgrad_tc_reduce_kernel, dim3(cdiv(Cout, 8), cdiv(Kmax, 8), cdiv(Cin, 32)), dim3(256), 0, cs, (const float*)p.part,
+                                  dW, items, lk, st, p.S, NT, Cin, Cout, Kmax, np, cinp, m_split, accumulate);
+      if (le != cudaSuccess) { set_error("wgrad reduce launch: %s", cudaGetErrorString(le)); return (int)le; } }
     TSC_LAUNCH_CHECK();
     return 0;
 }
