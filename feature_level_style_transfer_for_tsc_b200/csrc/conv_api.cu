@@ -20,6 +20,7 @@ int read_clear_watchdog_wgrad(int* code);
 int read_clear_watchdog_gram(int* code);
 void set_conv_timeline(long long* dev);
 void set_wgrad_timeline(long long* dev);
+void set_gram_timeline(long long* dev);
 }  // namespace tsc
 
 extern "C" {
@@ -76,6 +77,7 @@ int tsc_oswgrad(int engine, const void* dy, const void* x, int dtype, float* dW,
 int tsc_debug_set_timeline(void* dev_buf) {
     tsc::set_conv_timeline((long long*)dev_buf);
     tsc::set_wgrad_timeline((long long*)dev_buf);
+    tsc::set_gram_timeline((long long*)dev_buf);
     return 0;
 }
 

@@ -38,8 +38,11 @@ struct GramFwdParams {
     int buf_bytes;    // one operand buffer of one stage: (GR_KC/4) * (Rp + 1) * 16
     int tmem_cols;
     float inv_cl;
+    long long* tl;
 };
+#define GTL(i) do { if (p.tl && blockIdx.x == 0) p.tl[i] = clock64(); } while (0)
 
+template <int FI>
 __global__ void __launch_bounds__(GR_THREADS, 1) gram_fwd_tc_kernel(const GramFwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);            // [8]
@@ -56,14 +59,21 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gram_fwd_tc_kernel(const GramFw
     const int mtiles = Rp / 128;
 
     if (warp == 0 && lane == 0) {
+        GTL(0);
         for (int i = 0; i < p.NS; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], 1); }
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc_cols(tmem_slot, (uint32_t)p.tmem_cols);
-    // rows [C, Rp) of every buffer are never written by the producers: zero the stage area once
-    for (int i = threadIdx.x; i < p.NS * stage_bytes / 16; i += GR_THREADS)
-        reinterpret_cast<uint4*>(stages)[i] = make_uint4(0u, 0u, 0u, 0u);
+    // rows [C, Rp] of every k-group of every buffer are never written by the producers: zero them once
+    {
+        const int pad_rows = Rp + 1 - C;
+        const int groups = p.NS * 4 * (GR_KC / 4);                  // (stage, buffer, k-group)
+        for (int i = threadIdx.x; i < groups * pad_rows; i += GR_THREADS) {
+            const int gidx = i / pad_rows, r = C + i % pad_rows;
+            *reinterpret_cast<uint4*>(stages + ((size_t)gidx * (Rp + 1) + r) * 16) = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -82,6 +92,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gram_fwd_tc_kernel(const GramFw
             mbar_wait(&full[s], ph, dead, 10);
             __syncwarp();
             tc_fence_after();
+            if (lane == 0 && p.tl && blockIdx.x == 0 && ck < 16) p.tl[8 + ck] = clock64();
             const uint32_t base16 = (smem_u32(stages) + s * (uint32_t)stage_bytes) >> 4;
             const uint32_t buf16 = (uint32_t)p.buf_bytes >> 4;
             const uint32_t lbo_f = (lbo_bytes >> 4) << 16;
@@ -120,15 +131,11 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gram_fwd_tc_kernel(const GramFw
         const float* ab = p.a + (size_t)b * C * L;
         const float* sb = p.s + (size_t)b * C * L;
         const bool vec = (L & 3) == 0;
-        uint32_t s = 0, ph = 0;
-        for (int ck = 0; ck < nchunk; ++ck) {
-            mbar_wait(&empty[s], ph ^ 1u, dead, 11);
-            uint8_t* st = stages + (size_t)s * stage_bytes;
+        // item = (row r, quad q of 4 positions): quads of a row are contiguous in global memory.  All loads of a chunk
+        // are issued before their first use, and (FI <= 5, i.e. C <= 160) the loads of chunk ck+1 are in flight while
+        // chunk ck is split and stored: one L2 round trip is hidden behind the other chunk's work.
+        auto load_chunk = [&](int ck, float4 (&ra)[FI], float4 (&rs)[FI]) {
             const int l0 = ck * GR_KC;
-            // item = (row r, quad q of 4 positions): quads of a row are contiguous in global memory.  All loads of the
-            // chunk are issued before the first use (one L2 round trip per chunk instead of one per item).
-            constexpr int FI = (256 * (GR_KC / 4) + 127) / 128;          // items per thread for C <= 256
-            float4 ra[FI], rs[FI];
 #pragma unroll
             for (int u = 0; u < FI; ++u) {
                 const int it = ptid + u * 128;
@@ -152,6 +159,8 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gram_fwd_tc_kernel(const GramFw
                     }
                 }
             }
+        };
+        auto store_chunk = [&](uint8_t* st, const float4 (&ra)[FI], const float4 (&rs)[FI]) {
 #pragma unroll
             for (int u = 0; u < FI; ++u) {
                 const int it = ptid + u * 128;
@@ -173,38 +182,61 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gram_fwd_tc_kernel(const GramFw
                     *reinterpret_cast<float4*>(dst + 3 * p.buf_bytes) = make_float4(sl[0], sl[1], sl[2], sl[3]);
                 }
             }
+        };
+        uint32_t s = 0, ph = 0;
+        float4 ra[FI], rs[FI], na[FI], ns_[FI];
+        if (FI <= 5) load_chunk(0, ra, rs);
+        for (int ck = 0; ck < nchunk; ++ck) {
+            if (FI <= 5) {
+                if (ck + 1 < nchunk) load_chunk(ck + 1, na, ns_);
+            } else {
+                load_chunk(ck, ra, rs);
+            }
+            mbar_wait(&empty[s], ph ^ 1u, dead, 11);
+            store_chunk(stages + (size_t)s * stage_bytes, ra, rs);
             fence_proxy_async();          // generic-proxy stores -> visible to the tensor core's async-proxy reads
             mbar_arrive(&full[s]);
+            if (threadIdx.x == 64 && p.tl && blockIdx.x == 0 && ck < 16) p.tl[24 + ck] = clock64();
+            if (FI <= 5) {
+#pragma unroll
+                for (int u = 0; u < FI; ++u) { ra[u] = na[u]; rs[u] = ns_[u]; }
+            }
             if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; }
         }
         // ===== epilogue =====
         if (threadIdx.x == 64) mbar_wait(acc_full, 0, dead, 12);
         asm volatile("bar.sync 1, 128;" ::: "memory");
         tc_fence_after();
+        if (threadIdx.x == 64) GTL(5);
         const int q = warp & 3;
         float sq = 0.f;
         for (int m = 0; m < mtiles; ++m) {
+            if (m * 128 + q * 32 >= C) continue;              // none of this warp's 32 rows is a real channel (warp-uniform)
             const int i = m * 128 + q * 32 + lane;
-            float* drow = p.D + ((size_t)b * C + (i < C ? i : 0)) * C;
+            // D is symmetric: thread i stores its element (i, c0+j) at [c0+j][i], so the 32 lanes of a warp write
+            // 128 contiguous bytes per instruction instead of 32 rows 576 B apart
+            float* dcol = p.D + (size_t)b * C * C + i;
             for (int c0 = 0; c0 < p.Np; c0 += 16) {
                 float v[16];
                 tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * p.Np + c0), v);
                 if (i < C) {
-                    float d[16];
+                    float* d0 = dcol + (size_t)c0 * C;
+                    if (c0 + 16 <= C) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        d[j] = c0 + j < C ? v[j] * p.inv_cl : 0.f;
-                        sq = fmaf(d[j], d[j], sq);
-                    }
-                    if ((C & 3) == 0) {
-                        // rows of D are 16 B aligned: 64 contiguous bytes per thread in four vector stores
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4)
-                            if (c0 + j < C) *reinterpret_cast<float4*>(drow + c0 + j) = make_float4(d[j], d[j + 1], d[j + 2], d[j + 3]);
+                        for (int j = 0; j < 16; ++j) {
+                            const float d = v[j] * p.inv_cl;
+                            d0[j * C] = d;
+                            sq = fmaf(d, d, sq);
+                        }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (c0 + j < C) drow[c0 + j] = d[j];
+                        for (int j = 0; j < 16; ++j) {
+                            if (c0 + j < C) {
+                                const float d = v[j] * p.inv_cl;
+                                d0[j * C] = d;
+                                sq = fmaf(d, d, sq);
+                            }
+                        }
                     }
                 }
             }
@@ -213,6 +245,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gram_fwd_tc_kernel(const GramFw
         if (lane == 0) red[q] = sq;
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (threadIdx.x == 64) p.partial[b] = (red[0] + red[1]) + (red[2] + red[3]);
+        if (threadIdx.x == 64) GTL(6);
     }
     tc_fence_before();
     __syncthreads();
@@ -396,6 +429,8 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gram_bwd_tc_kernel(const GramBw
 }  // namespace tc
 
 int gram_sum_partials(const float* partial, int n, float scale, float* out, cudaStream_t cs);     // style.cu
+static long long* g_gram_timeline = nullptr;
+void set_gram_timeline(long long* dev) { g_gram_timeline = dev; }
 
 int gram_fwd_tc(const float* a, const float* s, float* D, float* loss, float* ws, int B, int C, int L, cudaStream_t cs) {
     using namespace tc;
@@ -414,14 +449,19 @@ int gram_fwd_tc(const float* a, const float* s, float* D, float* loss, float* ws
     const int cols = (p.Rp / 128) * p.Np;
     p.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
     p.inv_cl = 1.f / ((float)C * (float)L);
+    p.tl = g_gram_timeline;
     const int smem = GR_HDR + ns * stage_bytes;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gram_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(gram_fwd_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gram_fwd_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         attr_set = true;
     }
-    gram_fwd_tc_kernel<<<B, GR_THREADS, smem, cs>>>(p);
+    if (C * (GR_KC / 4) <= 5 * 128)
+        gram_fwd_tc_kernel<5><<<B, GR_THREADS, smem, cs>>>(p);
+    else
+        gram_fwd_tc_kernel<8><<<B, GR_THREADS, smem, cs>>>(p);
     TSC_LAUNCH_CHECK();
     return gram_sum_partials(ws, B, 1.f / ((float)B * (float)C * (float)C), loss, cs);
 }
