@@ -27,6 +27,7 @@ sys.path.insert(0, ROOT)
 METRIC = "OS-CNN+style-transfer train samples/sec"
 UNIT = "samples/s"
 CFG = dict(name="cfg2", B=128, C=9, L=128, K=6)          # per domain, per GPU
+WORKLOAD = "cfg2: OS-CNN + AdaIN/Gram style transfer, B=128 per domain per GPU, C=9, L=128, 6 classes"
 STYLE_WEIGHT = 1.0
 
 
@@ -107,8 +108,8 @@ def run_reference(args):
     line = dict(metric=METRIC, value=value, unit=UNIT, impl="reference", n_gpus=args.gpus, steps=steps,
                 warmup=max(1, min(args.warmup, 2)), ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload="cfg2: OS-CNN + AdaIN/Gram style transfer, B=128 per domain, C=9, L=128, 6 classes",
-                            series_per_step=2 * CFG["B"]),
+                config=dict(workload=WORKLOAD, series_per_step_per_gpu=2 * CFG["B"], engine="cpu oracle port (torch/oneDNN fp32)",
+                            parallelism="rank 0 only"),
                 cpu_baseline=dict(value=value, unit=UNIT, cores=threads, kind="port", sample=sample),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
@@ -392,8 +393,7 @@ def run_ours(args):
     line = dict(metric=METRIC, value=series / t_dev, unit=UNIT, n_gpus=world, steps=args.steps,
                 warmup=max(args.warmup, 3), ms_per_step=t_dev / args.steps * 1e3, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="bf16" if args.engine == "tcgen05" else "f32", data="synthetic",
-                config=dict(workload="cfg2: OS-CNN + AdaIN/Gram style transfer, B=128 per domain per GPU, C=9, L=128, 6 classes",
-                            series_per_step_per_gpu=2 * B, engine=args.engine, parallelism=f"dp{world}",
+                config=dict(workload=WORKLOAD, series_per_step_per_gpu=2 * B, engine=args.engine, parallelism=f"dp{world}",
                             cuda_graph=not args.no_graph,
                             l2="flushed between timed steps (256 MiB write, outside the per-step events)"),
                 e2e=dict(value=series / t_e2e, unit=UNIT, h2d_bytes_per_step=h2d_bytes * world, d2h_bytes_per_step=4 * world,
