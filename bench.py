@@ -28,6 +28,9 @@ METRIC = "OS-CNN+style-transfer train samples/sec"
 UNIT = "samples/s"
 CFG = dict(name="cfg2", B=128, C=9, L=128, K=6)          # per domain, per GPU
 WORKLOAD = "cfg2: OS-CNN + AdaIN/Gram style transfer, B=128 per domain per GPU, C=9, L=128, 6 classes"
+# secondary workload (--workload cfg4, BASELINE configs[3]; not the headline line): long-series OS-CNN forward + backward
+CFG4 = dict(name="cfg4", B=256, C=3, L=1024, K=4)
+WORKLOAD4 = "cfg4: long-series OS-CNN extractor + classifier, forward + backward + RMSprop, B=256 per GPU, C=3, L=1024, primes up to 89"
 STYLE_WEIGHT = 1.0
 
 
@@ -297,13 +300,23 @@ def run_ours(args):
     T.set_engine(args.engine)
 
     torch.manual_seed(0)
-    model = StyleTransferModelSet(CFG["C"], CFG["L"], CFG["K"], CFG["C"], CFG["L"], CFG["K"]).to(dev)
+    cfg4 = args.workload == "cfg4"
+    if cfg4:
+        from feature_level_style_transfer_for_tsc_b200.train_step import SingleDomainModelSet
+        model = SingleDomainModelSet(CFG4["C"], CFG4["L"], CFG4["K"]).to(dev)
+        B = CFG4["B"]
+        x_h, y_h = O.synthetic_batch(B, CFG4["C"], CFG4["L"], CFG4["K"], rank)
+        host = [t.pin_memory() for t in (x_h, y_h)]
+        series_per_gpu = B
+    else:
+        model = StyleTransferModelSet(CFG["C"], CFG["L"], CFG["K"], CFG["C"], CFG["L"], CFG["K"]).to(dev)
+        B = CFG["B"]
+        xt_h, yt_h = O.synthetic_batch(B, CFG["C"], CFG["L"], CFG["K"], 2 * rank)
+        xs_h, ys_h = O.synthetic_batch(B, CFG["C"], CFG["L"], CFG["K"], 2 * rank + 1)
+        host = [t.pin_memory() for t in (xt_h, yt_h, xs_h, ys_h)]
+        series_per_gpu = 2 * B
     trainer = Trainer(model, STYLE_WEIGHT, use_graph=not args.no_graph)
     trainer.broadcast_parameters(0)
-    B = CFG["B"]
-    xt_h, yt_h = O.synthetic_batch(B, CFG["C"], CFG["L"], CFG["K"], 2 * rank)
-    xs_h, ys_h = O.synthetic_batch(B, CFG["C"], CFG["L"], CFG["K"], 2 * rank + 1)
-    host = [t.pin_memory() for t in (xt_h, yt_h, xs_h, ys_h)]
     dev_in = [t.to(dev) for t in host]
     h2d_bytes = sum(t.numel() * t.element_size() for t in host)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)      # 256 MiB > 126 MB L2
@@ -354,7 +367,7 @@ def run_ours(args):
         tt = torch.tensor([t_dev, t_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_dev, t_e2e = float(tt[0]), float(tt[1])
-    series = 2 * B * world * args.steps
+    series = series_per_gpu * world * args.steps
 
     # instrumented pass (per-kernel-family device time; not part of any reported step time)
     prof.timing = True
@@ -386,14 +399,14 @@ def run_ours(args):
                     achieved=d["tflops"] or 0.0, peak=peaks["bf16"], unit="TFLOP/s", frac=(d["tflops"] or 0.0) / peaks["bf16"],
                     traffic=None, peak_source=peaks["source"] + " bf16 burst")
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not cfg4:
         v, dt, cores, threads = cpu_step_rate(3, 1)
         cpu = dict(value=v, unit=UNIT, cores=threads, kind="port",
                    sample=f"3 full cfg2 steps (B=128 per domain) of the oracle port, {dt * 1e3:.0f} ms/step, {cores} host cores")
     line = dict(metric=METRIC, value=series / t_dev, unit=UNIT, n_gpus=world, steps=args.steps,
                 warmup=max(args.warmup, 3), ms_per_step=t_dev / args.steps * 1e3, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="bf16" if args.engine == "tcgen05" else "f32", data="synthetic",
-                config=dict(workload=WORKLOAD, series_per_step_per_gpu=2 * B, engine=args.engine, parallelism=f"dp{world}",
+                config=dict(workload=WORKLOAD4 if cfg4 else WORKLOAD, series_per_step_per_gpu=series_per_gpu, engine=args.engine, parallelism=f"dp{world}",
                             cuda_graph=not args.no_graph,
                             l2="flushed between timed steps (256 MiB write, outside the per-step events)"),
                 e2e=dict(value=series / t_e2e, unit=UNIT, h2d_bytes_per_step=h2d_bytes * world, d2h_bytes_per_step=4 * world,
@@ -414,6 +427,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--engine", default="tcgen05", choices=["tcgen05", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"],
+                    help="cfg2 = the headline step (default); cfg4 = long-series OS-CNN forward + backward (secondary)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -99,6 +99,24 @@ class StyleTransferModelSet(nn.Module):
                     logits_t=logits_t, logits_s=logits_s, tf=tf, ssf=ssf, s2t=s2t)
 
 
+class SingleDomainModelSet(nn.Module):
+    """Extractor + classifier of one domain (the pre-training stages, train_and_test.py:143-220, and BASELINE config 4:
+    long-series OS-CNN forward + backward).  forward(x, y) -> dict(loss, logits)."""
+
+    LRS = dict(fe=0.001, cl=0.003)          # train_and_test.py:97-98
+
+    def __init__(self, C: int, L: int, K: int):
+        super().__init__()
+        lpl, lpl_c, cf = trainer_layer_lists(C, L)
+        self.fe = OS_CNN_res(lpl)
+        self.cl = OS_CNN(lpl_c, K)
+        self.feature_channels = cf
+
+    def forward(self, x, y, style_weight: float = 1.0) -> Dict[str, torch.Tensor]:
+        logits, _ = self.cl(self.fe(x))
+        return dict(loss=F.cross_entropy(logits, y), logits=logits)
+
+
 class FlatParameters:
     """Every trainable parameter, its gradient and its RMSprop state as views into three flat fp32 buffers
     (group by group), so that the data-parallel exchange is ONE all-reduce and the optimizer ONE kernel launch
@@ -153,11 +171,12 @@ class Trainer:
     ``use_graph=True`` captures forward + backward of one step in a CUDA graph (fixed shapes): the step is
     launch-bound at cfg2 size (about 200 small kernels), and replaying one graph removes the host from the loop."""
 
-    def __init__(self, model: StyleTransferModelSet, style_weight: float = 1.0, group=None, use_graph: bool = False):
+    def __init__(self, model: nn.Module, style_weight: float = 1.0, group=None, use_graph: bool = False, lrs=None):
         self.model = model
         self.style_weight = style_weight
         self.group = group
-        self.flat = FlatParameters([(list(getattr(model, name).parameters()), lr) for name, lr in LEARNING_RATES.items()])
+        lrs = lrs if lrs is not None else getattr(model, "LRS", LEARNING_RATES)
+        self.flat = FlatParameters([(list(getattr(model, name).parameters()), lr) for name, lr in lrs.items()])
         self.use_graph = use_graph
         self._graph = None
         self._static_in = None
@@ -170,7 +189,7 @@ class Trainer:
             for t in self.model.buffers():
                 dist.broadcast(t.data, src=src, group=self.group)
 
-    def _fwd_bwd(self, xt, yt, xs, ys):
+    def _fwd_bwd(self, *inputs):
         self.flat.zero_grad()
         # every parameter owns a slice of the flat gradient bucket: the wgrad / BatchNorm-backward kernels add into it
         # in place (no AccumulateGrad kernels), so the bucket is complete the moment backward returns
@@ -183,7 +202,7 @@ class Trainer:
         torch.backends.cuda.matmul.allow_tf32 = ops.engine_name() == "tcgen05"
         OSM.defer_batch_counters(True)
         try:
-            out = self.model(xt, yt, xs, ys, self.style_weight)
+            out = self.model(*inputs, self.style_weight)
             counters = OSM.defer_batch_counters(False)
             if counters:
                 torch._foreach_add_(counters, 1)          # one launch for every BatchNorm's num_batches_tracked
@@ -194,8 +213,8 @@ class Trainer:
             torch.backends.cuda.matmul.allow_tf32 = tf32_prev
         return out["loss"].detach()
 
-    def _capture(self, xt, yt, xs, ys):
-        self._static_in = [t.clone() for t in (xt, yt, xs, ys)]
+    def _capture(self, *inputs):
+        self._static_in = [t.clone() for t in inputs]
         # the warm-up passes must leave no trace: BatchNorm running statistics are forward side effects
         saved = [b.detach().clone() for b in self.model.buffers()]
         side = torch.cuda.Stream()
@@ -211,16 +230,16 @@ class Trainer:
             for b, v in zip(self.model.buffers(), saved):
                 b.copy_(v)
 
-    def step(self, xt, yt, xs, ys) -> torch.Tensor:
+    def step(self, *inputs) -> torch.Tensor:
         if self.use_graph:
             if self._graph is None:
-                self._capture(xt, yt, xs, ys)
-            for dst, src in zip(self._static_in, (xt, yt, xs, ys)):
+                self._capture(*inputs)
+            for dst, src in zip(self._static_in, inputs):
                 dst.copy_(src, non_blocking=True)
             self._graph.replay()
             loss = self._static_loss
         else:
-            loss = self._fwd_bwd(xt, yt, xs, ys)
+            loss = self._fwd_bwd(*inputs)
         world = self.flat.all_reduce_sum(self.group)
         self.flat.rmsprop(grad_scale=1.0 / world)
         return loss
