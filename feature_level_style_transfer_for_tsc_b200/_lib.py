@@ -93,6 +93,8 @@ SIGNATURES = {
     "tsc_bn_bwd_apply_fused": (_i, [_p, _bbp, _i, _i, _p, _i, _i, _i, _i, _p]),
     "tsc_rmsprop_step": (_i, [_p, _p, _p, ctypes.c_longlong, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_float),
                          _i, _f, _f, _f, _p]),
+    "tsc_rmsprop_step_clamped": (_i, [_p, _p, _p, ctypes.c_longlong, ctypes.POINTER(ctypes.c_longlong),
+                                 ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), _i, _f, _f, _f, _p]),
     "tsc_osconv_plan_bytes": (_sz, [_i, _i, _i, _i, _ip]),
     "tsc_osconv_plan_build": (_i, [_i, _i, _i, _i, _ip, _p]),
     "tsc_osconv": (_i, [_i, _i, _p, _i, _p, _p, _p, _p, _ep, _i, _i, _i, _i, _i, _ip, _p]),
@@ -110,6 +112,10 @@ SIGNATURES = {
     "tsc_gram_workspace_bytes": (_sz, [_i, _i, _i]),
     "tsc_gram_loss_fwd": (_i, [_i, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "tsc_gram_loss_bwd": (_i, [_i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "tsc_cdan_fuse_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p]),
+    "tsc_cdan_fuse_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p]),
+    "tsc_cdan_distance_fwd": (_i, [_p, _p, _p, _p, _i, _p]),
+    "tsc_cdan_distance_bwd": (_i, [_p, _p, _p, _p, _i, _p]),
     "tsc_debug_read_and_clear_watchdog": (_i, [_ip]),
     "tsc_debug_set_timeline": (_i, [_p]),
 }

@@ -232,15 +232,20 @@ def pack_weights_multi(layers, dt: int):
 
 
 def rmsprop_step(params: torch.Tensor, grads: torch.Tensor, square_avg: torch.Tensor, group_end, group_lr,
-                 alpha: float = 0.99, eps: float = 1e-8, grad_scale: float = 1.0):
-    """Fused RMSprop over flat fp32 buffers (torch.optim.RMSprop defaults; per-group learning rates)."""
+                 alpha: float = 0.99, eps: float = 1e-8, grad_scale: float = 1.0, group_clamp=None):
+    """Fused RMSprop over flat fp32 buffers (torch.optim.RMSprop defaults; per-group learning rates; optional WGAN
+    weight clipping of chosen groups, ``group_clamp[i] > 0``)."""
     for t, nm in ((params, "params"), (grads, "grads"), (square_avg, "square_avg")):
         _req(t, name=nm)
     n = params.numel()
     ends = (ctypes.c_longlong * len(group_end))(*[int(e) for e in group_end])
     lrs = (ctypes.c_float * len(group_lr))(*[float(x) for x in group_lr])
-    L.check(L.load().tsc_rmsprop_step(_ptr(params), _ptr(grads), _ptr(square_avg), n, ends, lrs, len(group_end),
-                                      float(alpha), float(eps), float(grad_scale), _stream()), "tsc_rmsprop_step")
+    clamps = None
+    if group_clamp is not None and any(c > 0 for c in group_clamp):
+        clamps = (ctypes.c_float * len(group_lr))(*[float(c) for c in group_clamp])
+    L.check(L.load().tsc_rmsprop_step_clamped(_ptr(params), _ptr(grads), _ptr(square_avg), n, ends, lrs, clamps,
+                                              len(group_end), float(alpha), float(eps), float(grad_scale), _stream()),
+            "tsc_rmsprop_step_clamped")
 
 
 def n_conv_ctas(B: int, Ln: int) -> int:
@@ -531,6 +536,52 @@ def gram_loss_bwd(engine: int, D, a, s, dloss):
     L.check(L.load().tsc_gram_loss_bwd(engine, _ptr(D), _ptr(a), _ptr(s), _ptr(dloss), _ptr(da), _ptr(ds), B, C, Ln,
                                        _stream()), "tsc_gram_loss_bwd")
     return da, ds
+
+
+def cdan_fuse_fwd(y0, logits, r1, scale_div: float):
+    """C_DAN.py:20-25,32-37,53-54 for the stacked (target, generated) rows: returns (fusion [M,D], prob [M,K], u [M])."""
+    _req(y0, name="y0"); _req(logits, name="logits"); _req(r1, name="r1")
+    M, D = y0.shape
+    K = logits.shape[1]
+    if logits.shape[0] != M or tuple(r1.shape) != (K, D):
+        raise RuntimeError(f"cdan_fuse: y0 {tuple(y0.shape)}, logits {tuple(logits.shape)}, r1 {tuple(r1.shape)} do not agree")
+    fusion = torch.empty_like(y0)
+    prob = torch.empty((M, K), device=y0.device, dtype=torch.float32)
+    u = torch.empty((M,), device=y0.device, dtype=torch.float32)
+    L.check(L.load().tsc_cdan_fuse_fwd(_ptr(y0), _ptr(logits), _ptr(r1), _ptr(fusion), _ptr(prob), _ptr(u), M, K, D,
+                                       float(scale_div), _stream()), "tsc_cdan_fuse_fwd")
+    return fusion, prob, u
+
+
+def cdan_fuse_bwd(dfusion, y0, prob, r1, u, du, coeff, scale_div: float):
+    _req(dfusion, name="dfusion"); _req(coeff, name="coeff")
+    M, D = y0.shape
+    K = prob.shape[1]
+    dy0 = torch.empty_like(y0)
+    dlogits = torch.empty_like(prob)
+    L.check(L.load().tsc_cdan_fuse_bwd(_ptr(dfusion), _ptr(y0), _ptr(prob), _ptr(r1), _ptr(u), _ptr(du), _ptr(coeff),
+                                       _ptr(dy0), _ptr(dlogits), M // 2, K, D, float(scale_div), _stream()),
+            "tsc_cdan_fuse_bwd")
+    return dy0, dlogits
+
+
+def cdan_distance_fwd(u, critic_out):
+    _req(u, name="u"); _req(critic_out, name="critic_out")
+    B = u.numel() // 2
+    loss = torch.empty((), device=u.device, dtype=torch.float32)
+    saved = torch.empty((8,), device=u.device, dtype=torch.float32)
+    L.check(L.load().tsc_cdan_distance_fwd(_ptr(u), _ptr(critic_out), _ptr(loss), _ptr(saved), B, _stream()),
+            "tsc_cdan_distance_fwd")
+    return loss, saved
+
+
+def cdan_distance_bwd(dloss, saved, B: int):
+    _req(dloss, name="dloss")
+    du = torch.empty((2 * B,), device=saved.device, dtype=torch.float32)
+    dcritic = torch.empty((2 * B, 1), device=saved.device, dtype=torch.float32)
+    L.check(L.load().tsc_cdan_distance_bwd(_ptr(dloss), _ptr(saved), _ptr(du), _ptr(dcritic), B, _stream()),
+            "tsc_cdan_distance_bwd")
+    return du, dcritic
 
 
 def read_watchdog() -> int:

@@ -28,7 +28,8 @@ from . import ops
 from .OS_CNN import OS_CNN as OSM
 from .OS_CNN.OS_CNN import OS_CNN, OS_CNN_res, layer_parameter_list_input_change
 from .OS_CNN.OS_CNN_Structure_build import generate_layer_parameter_list
-from .widgets import DimensionUnification
+from .C_DAN import CDAN, RandomLayer
+from .widgets import AdversarialNetworkforCDAN, DimensionUnification
 
 MAX_KERNEL_SIZE = 89        # train_and_test.py:40
 LEARNING_RATES = dict(fe_t=0.001, cl_t=0.003, fe_s=0.001, du=0.001, cl_s=0.003)    # train_and_test.py:97-101
@@ -99,6 +100,102 @@ class StyleTransferModelSet(nn.Module):
                     logits_t=logits_t, logits_s=logits_s, tf=tf, ssf=ssf, s2t=s2t)
 
 
+class TransferPairModelSet(StyleTransferModelSet):
+    """One (source, target) pair of BASELINE configuration 3: the five modules of the cfg2 step plus the
+    C-DAN critic and its random layer (train_and_test.py:74-76).  The step adds the target classifier on the generated
+    features in **eval-BatchNorm mode with gradients** (train_and_test.py:584-586) and the C-DAN loss on
+    (target feature, generated feature, their logits) (train_and_test.py:590-591):
+
+        loss = CE_t + CE_s + style_weight * L_style + cdan_weight * CDAN      (cdan_weight = 3: train_and_test.py:660)
+    """
+
+    LRS = dict(fe_t=0.001, cl_t=0.003, fe_s=0.001, du=0.001, cl_s=0.003, ad_net=0.001)   # train_and_test.py:97-101,105
+    CLAMPS = dict(ad_net=0.0005)                                                          # train_and_test.py:763-764
+    cdan_weight = 3.0
+
+    def __init__(self, Ct: int, Lt: int, Kt: int, Cs: int, Ls: int, Ks: int, critic_hidden: int = 1024):
+        super().__init__(Ct, Lt, Kt, Cs, Ls, Ks)
+        self.random_layer = RandomLayer([self.feature_channels * Lt, Kt], with_nvidia=False)   # follows .cuda()
+        self.ad_net = AdversarialNetworkforCDAN(1024, critic_hidden)
+
+    def forward(self, xt, yt, xs, ys, style_weight: float = 1.0) -> Dict[str, torch.Tensor]:
+        out = super().forward(xt, yt, xs, ys, style_weight)
+        was_training = self.cl_t.training
+        self.cl_t.eval()                                  # train_and_test.py:584: running statistics, gradients still flow
+        try:
+            logits_s2t, _ = self.cl_t(out["s2t"])
+        finally:
+            self.cl_t.train(was_training)
+        cdan = CDAN(out["tf"], out["s2t"], out["logits_t"], logits_s2t, self.ad_net, self.random_layer)
+        out.update(loss=out["loss"] + self.cdan_weight * cdan, cdan=cdan, logits_s2t=logits_s2t)
+        return out
+
+    def advance_schedules(self):
+        """What the two critic calls of one step do to the reversal schedule, for steps replayed from a CUDA graph."""
+        self.ad_net.reversal_coefficients(calls=2)
+
+    def schedule_state(self):
+        return (self.ad_net.iter_num, self.ad_net.coeff)
+
+    def set_schedule_state(self, st):
+        self.ad_net.iter_num, self.ad_net.coeff = st
+        self.ad_net._coeff_host = None
+
+
+class MultiSourceModelSet(nn.Module):
+    """BASELINE configuration 3: several source domains, one target.  As in the reference, every (source_i, target)
+    pair is an independent training with its own module set (main.py:7-11, multi_source_voting.py:265-267); one step
+    advances all of them on the same target batch.  Pairs are independent, so each runs on its own pair of streams.
+
+    forward(xt, yt, xs_0, ys_0, xs_1, ys_1, ..., style_weight) -> dict(loss = sum of the pair losses, pairs = [...])."""
+
+    def __init__(self, target, sources, critic_hidden: int = 1024):
+        super().__init__()
+        Ct, Lt, Kt = target
+        self.pairs = nn.ModuleList([TransferPairModelSet(Ct, Lt, Kt, Cs, Ls, Ks, critic_hidden) for (Cs, Ls, Ks) in sources])
+        self._streams = None
+
+    def parameter_groups(self):
+        return [(list(getattr(pair, name).parameters()), lr, pair.CLAMPS.get(name, 0.0))
+                for pair in self.pairs for name, lr in pair.LRS.items()]
+
+    def forward(self, xt, yt, *rest) -> Dict[str, torch.Tensor]:
+        n = len(self.pairs)
+        style_weight = rest[2 * n] if len(rest) > 2 * n else 1.0
+        outs = [None] * n
+        if xt.is_cuda and n > 1:
+            main = torch.cuda.current_stream()
+            if self._streams is None:
+                self._streams = [torch.cuda.Stream() for _ in range(n - 1)]
+            for i in range(1, n):
+                st = self._streams[i - 1]
+                st.wait_stream(main)
+                with torch.cuda.stream(st):
+                    outs[i] = self.pairs[i](xt, yt, rest[2 * i], rest[2 * i + 1], style_weight)
+            outs[0] = self.pairs[0](xt, yt, rest[0], rest[1], style_weight)
+            for i in range(1, n):
+                main.wait_stream(self._streams[i - 1])
+                outs[i]["loss"].record_stream(main)
+        else:
+            for i in range(n):
+                outs[i] = self.pairs[i](xt, yt, rest[2 * i], rest[2 * i + 1], style_weight)
+        loss = outs[0]["loss"]
+        for o in outs[1:]:
+            loss = loss + o["loss"]
+        return dict(loss=loss, pairs=outs)
+
+    def advance_schedules(self):
+        for pair in self.pairs:
+            pair.advance_schedules()
+
+    def schedule_state(self):
+        return [pair.schedule_state() for pair in self.pairs]
+
+    def set_schedule_state(self, st):
+        for pair, s in zip(self.pairs, st):
+            pair.set_schedule_state(s)
+
+
 class SingleDomainModelSet(nn.Module):
     """Extractor + classifier of one domain (the pre-training stages, train_and_test.py:143-220, and BASELINE config 4:
     long-series OS-CNN forward + backward).  forward(x, y) -> dict(loss, logits)."""
@@ -123,8 +220,10 @@ class FlatParameters:
     per step.  ``p.data`` / ``p.grad`` are re-bound to their slices; module code is unaffected."""
 
     def __init__(self, groups):
-        """groups: list of (params, lr)."""
-        params = [p for ps, _ in groups for p in ps if p.requires_grad]
+        """groups: list of (params, lr) or (params, lr, clamp) -- clamp > 0 clips the group to [-clamp, clamp] after its
+        update (the WGAN clipping of the C-DAN critic, train_and_test.py:763-764)."""
+        groups = [(g[0], g[1], g[2] if len(g) > 2 else 0.0) for g in groups]
+        params = [p for ps, _, _ in groups for p in ps if p.requires_grad]
         dev = params[0].device
         # 4-element alignment of every tensor keeps the float4 path of the optimizer kernel on group boundaries
         sizes = [(p.numel() + 3) // 4 * 4 for p in params]
@@ -133,10 +232,10 @@ class FlatParameters:
         self.flat_p = torch.zeros(n, device=dev, dtype=torch.float32)
         self.flat_g = torch.zeros(n, device=dev, dtype=torch.float32)
         self.flat_v = torch.zeros(n, device=dev, dtype=torch.float32)
-        self.group_end, self.group_lr = [], []
+        self.group_end, self.group_lr, self.group_clamp = [], [], []
         off = 0
         it = iter(sizes)
-        for ps, lr in groups:
+        for ps, lr, clamp in groups:
             for p in ps:
                 if not p.requires_grad:
                     continue
@@ -148,6 +247,7 @@ class FlatParameters:
                 off += sz
             self.group_end.append(off)
             self.group_lr.append(lr)
+            self.group_clamp.append(clamp)
 
     def zero_grad(self):
         self.flat_g.zero_()
@@ -162,7 +262,8 @@ class FlatParameters:
         return 1
 
     def rmsprop(self, grad_scale: float = 1.0, alpha: float = 0.99, eps: float = 1e-8):
-        ops.rmsprop_step(self.flat_p, self.flat_g, self.flat_v, self.group_end, self.group_lr, alpha, eps, grad_scale)
+        ops.rmsprop_step(self.flat_p, self.flat_g, self.flat_v, self.group_end, self.group_lr, alpha, eps, grad_scale,
+                         self.group_clamp)
 
 
 class Trainer:
@@ -175,8 +276,13 @@ class Trainer:
         self.model = model
         self.style_weight = style_weight
         self.group = group
-        lrs = lrs if lrs is not None else getattr(model, "LRS", LEARNING_RATES)
-        self.flat = FlatParameters([(list(getattr(model, name).parameters()), lr) for name, lr in lrs.items()])
+        if lrs is None and hasattr(model, "parameter_groups"):
+            groups = model.parameter_groups()
+        else:
+            lrs = lrs if lrs is not None else getattr(model, "LRS", LEARNING_RATES)
+            clamps = getattr(model, "CLAMPS", {})
+            groups = [(list(getattr(model, name).parameters()), lr, clamps.get(name, 0.0)) for name, lr in lrs.items()]
+        self.flat = FlatParameters(groups)
         self.use_graph = use_graph
         self._graph = None
         self._static_in = None
@@ -217,6 +323,7 @@ class Trainer:
         self._static_in = [t.clone() for t in inputs]
         # the warm-up passes must leave no trace: BatchNorm running statistics are forward side effects
         saved = [b.detach().clone() for b in self.model.buffers()]
+        sched = self.model.schedule_state() if hasattr(self.model, "schedule_state") else None
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -229,6 +336,8 @@ class Trainer:
         with torch.no_grad():
             for b, v in zip(self.model.buffers(), saved):
                 b.copy_(v)
+        if sched is not None:
+            self.model.set_schedule_state(sched)
 
     def step(self, *inputs) -> torch.Tensor:
         if self.use_graph:
@@ -236,6 +345,8 @@ class Trainer:
                 self._capture(*inputs)
             for dst, src in zip(self._static_in, inputs):
                 dst.copy_(src, non_blocking=True)
+            if hasattr(self.model, "advance_schedules"):
+                self.model.advance_schedules()          # host-side schedules (C-DAN reversal strength) -> device scalars
             self._graph.replay()
             loss = self._static_loss
         else:

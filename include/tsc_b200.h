@@ -37,7 +37,7 @@ extern "C" {
 #define TSC_VERSION 100
 #define TSC_MAX_TAPS 96          /* largest supported Kmax (reference caps it at 89, train_and_test.py:40) */
 #define TSC_MAX_CHANNELS 256     /* largest padded channel count of one OS layer (reference: <= 228) */
-#define TSC_MAX_OPT_GROUPS 16    /* parameter groups of one tsc_rmsprop_step call */
+#define TSC_MAX_OPT_GROUPS 32    /* parameter groups of one tsc_rmsprop_step call */
 
 typedef void* tsc_stream_t;      /* cudaStream_t */
 
@@ -232,12 +232,39 @@ int tsc_gram_loss_fwd(int engine, const float* a, const float* s, float* D, floa
 int tsc_gram_loss_bwd(int engine, const float* D, const float* a, const float* s, const float* dloss,
                       float* da, float* ds, int B, int C, int L, tsc_stream_t stream);
 
+/* ---- C-DAN consumer of the transferred features (C_DAN.py:49-82; BASELINE configuration 3).  Rows are stacked:
+ * m in [0, B) = target half, [B, 2B) = generated (source-to-target) half.  The big random projection
+ * y0 = flatten(feature) @ R0 (C_DAN.py:20, a plain dense GEMM) is the caller's (cuBLAS); everything else between the
+ * classifier logits / y0 and the critic's input, and everything behind the critic's output, is here.
+ *   prob = softmax(logits)                       C_DAN.py:53-54      [2B, K], K <= 32
+ *   fusion = (y0 / scale_div) * (prob @ r1)      C_DAN.py:20-25      [2B, D]   (scale_div = D^(1/2) for two views)
+ *   u = 1 + exp(-H(prob)), H = -sum p log(p+1e-5) C_DAN.py:32-37,70-71 [2B] */
+int tsc_cdan_fuse_fwd(const float* y0, const float* logits, const float* r1, float* fusion, float* prob, float* u,
+                      int M, int K, int D, float scale_div, tsc_stream_t stream);
+/* Backward of the above including the reference's three gradient reversals (grl_hook, C_DAN.py:38-41):
+ * dfusion is the gradient at the critic's input (widgets.py:121-122); coeff (device, 3 floats) = reversal strength of
+ * the critic input for the target rows, for the generated rows, and of the entropy (C_DAN.py:68-69).  du may be NULL. */
+int tsc_cdan_fuse_bwd(const float* dfusion, const float* y0, const float* prob, const float* r1, const float* u,
+                      const float* du, const float* coeff, float* dy0, float* dlogits, int B, int K, int D,
+                      float scale_div, tsc_stream_t stream);
+/* w = u / sum(u) per half (the sum is a constant, C_DAN.py:72-75); loss = sum_t(w) * sum_t(critic) - the same over the
+ * generated half (C_DAN.py:78-81: [B] * [B,1] broadcasts to [B,B] before the sum).  saved: 6 floats for backward. */
+int tsc_cdan_distance_fwd(const float* u, const float* critic_out, float* loss, float* saved, int B,
+                          tsc_stream_t stream);
+int tsc_cdan_distance_bwd(const float* dloss, const float* saved, float* du, float* dcritic_out, int B,
+                          tsc_stream_t stream);
+
 /* ---- fused multi-tensor RMSprop over flat fp32 buffers: replaces the 5 torch.optim.RMSprop instances of the
  * path (train_and_test.py:97-101): v = alpha v + (1-alpha) g^2 ; p -= lr g / (sqrt(v)+eps), g = grad_scale*grad.
  * group_end / group_lr (HOST, ngroups entries): exclusive end offset and learning rate of each parameter group. */
 int tsc_rmsprop_step(float* params, const float* grads, float* square_avg, long long n,
                      const long long* group_end, const float* group_lr, int ngroups, float alpha, float eps,
                      float grad_scale, tsc_stream_t stream);
+/* The same with WGAN weight clipping of chosen groups after their update (the critic's p.data.clamp_(-c, c),
+ * train_and_test.py:763-766): group_clamp (HOST, ngroups entries, or NULL) = c, <= 0 for "not clipped". */
+int tsc_rmsprop_step_clamped(float* params, const float* grads, float* square_avg, long long n,
+                             const long long* group_end, const float* group_lr, const float* group_clamp, int ngroups,
+                             float alpha, float eps, float grad_scale, tsc_stream_t stream);
 
 /* ---- debugging aid: the tcgen05 kernels bound every mbarrier wait; a timed-out wait stores a
  * non-zero code here (device word, read back by the caller when it wants to). */

@@ -73,6 +73,45 @@ def run_pair(ref_os, lpl_ext, n_class, x, y, seed):
     return init_fe, init_cl, after_fe, after_cl, grads, out, lpl_cls
 
 
+def make_cdan_golden():
+    """Two consecutive training-mode calls (the schedule advances: coeff 0 / 0.9866 then ~1) and one eval-mode call of
+    the reference's CDAN on seeded tensors; dropout p = 0 (its mask is generator-specific)."""
+    if not hasattr(np, "float"):
+        np.float = float                                      # widgets.py:13 / C_DAN.py:44 (numpy < 1.24 spelling)
+    import C_DAN as ref_cdan                                  # noqa
+    import widgets as ref_w                                   # noqa
+    B, C, L, K, H = 5, 6, 8, 4, 32
+    torch.manual_seed(3)
+    rl = ref_cdan.RandomLayer([C * L, K], with_nvidia=False)
+    ad = ref_w.AdversarialNetworkforCDAN(1024, H)
+    ad.dropout1.p = 0.0
+    ad.dropout2.p = 0.0
+    g = torch.Generator().manual_seed(5)
+    out = {"R0": rl.random_matrix[0].numpy().copy(), "R1": rl.random_matrix[1].numpy().copy()}
+    out.update({f"ad/{k}": v.detach().numpy().copy() for k, v in ad.state_dict().items()})
+    coeffs = []
+    for call, training in enumerate((True, True, False)):
+        ad.train(training)
+        ft = torch.randn(B, C, L, generator=g).requires_grad_(True)
+        fs = torch.randn(B, C, L, generator=g).requires_grad_(True)
+        lt = torch.randn(B, K, generator=g).requires_grad_(True)
+        ls = torch.randn(B, K, generator=g).requires_grad_(True)
+        for p in ad.parameters():
+            p.grad = None
+        loss = ref_cdan.CDAN(ft, fs, lt, ls, ad, rl)
+        loss.backward()
+        coeffs.append(float(ad.coeff))
+        out.update({f"c{call}/ft": ft.detach().numpy(), f"c{call}/fs": fs.detach().numpy(),
+                    f"c{call}/lt": lt.detach().numpy(), f"c{call}/ls": ls.detach().numpy(),
+                    f"c{call}/loss": np.float64(loss.item()),
+                    f"c{call}/dft": ft.grad.numpy(), f"c{call}/dfs": fs.grad.numpy(),
+                    f"c{call}/dlt": lt.grad.numpy(), f"c{call}/dls": ls.grad.numpy()})
+        out.update({f"c{call}/dad/{k}": p.grad.numpy().copy() for k, p in ad.named_parameters()})
+    np.savez_compressed(os.path.join(OUT, "cdan_small.npz"), **out)
+    return {"B": B, "C": C, "L": L, "n_class": K, "hidden": H, "seed": 3, "coeff_after_call": coeffs,
+            "iter_num_after": float(ad.iter_num)}
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     sys.path.insert(0, os.path.dirname(HERE))
@@ -149,6 +188,9 @@ def main():
         **{"grad/fe.net_1.net.net.0.conv1d.weight": grads["fe.net_1.net.net.0.conv1d.weight"]},
         **{f"after_fe/{k}": v for k, v in after_fe.items() if "running" in k},
         **{f"after_cl/{k}": v for k, v in after_cl.items() if "running" in k})
+
+    # ---- C-DAN consumer (C_DAN.py + widgets.AdversarialNetworkforCDAN), small shapes -----------
+    tables["cdan_small"] = make_cdan_golden()
 
     with open(os.path.join(OUT, "tables.json"), "w") as f:
         json.dump(tables, f, indent=1, sort_keys=True)

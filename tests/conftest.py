@@ -58,3 +58,8 @@ def rel_err(a, b):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.fixture(scope="session")
+def cdan_small():
+    return np.load(os.path.join(GOLDEN, "cdan_small.npz"))
