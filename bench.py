@@ -31,6 +31,10 @@ WORKLOAD = "cfg2: OS-CNN + AdaIN/Gram style transfer, B=128 per domain per GPU, 
 # secondary workload (--workload cfg4, BASELINE configs[3]; not the headline line): long-series OS-CNN forward + backward
 CFG4 = dict(name="cfg4", B=256, C=3, L=1024, K=4)
 WORKLOAD4 = "cfg4: long-series OS-CNN extractor + classifier, forward + backward + RMSprop, B=256 per GPU, C=3, L=1024, primes up to 89"
+# secondary workload (--workload cfg3, BASELINE configs[2]): three source domains + one target, style transfer + C-DAN
+CFG3 = dict(name="cfg3", B=128, target=(9, 128, 6), sources=[(1, 128, 5), (3, 256, 4), (9, 128, 6)])
+WORKLOAD3 = ("cfg3: 3 source domains (C,L)=(1,128),(3,256),(9,128) + 1 target (9,128), per-pair module sets, AdaIN/Gram style "
+             "transfer + eval-BN classifier on the generated features + C-DAN loss, B=128 per domain per GPU")
 STYLE_WEIGHT = 1.0
 
 
@@ -127,7 +131,7 @@ class KernelProfile:
     LAUNCHES = dict(ncl_to_c8=1, c8_to_ncl=1, pack_weights=1, pack_weights_pair=1, pack_weights_multi=1, rmsprop_step=1,
                     osconv=1, oswgrad=2, bn_stats=2, bn_eval_coeffs=1, bn_apply=1, bn_bwd_reduce=2, bn_bwd_apply=1,
                     bn_apply_fused=1, bn_bwd_top=1, bn_bwd_apply_fused=1, adain_fwd=1, adain_bwd=1, gram_loss_fwd=2,
-                    gram_loss_bwd=1, rowstats=1)
+                    gram_loss_bwd=1, rowstats=1, cdan_fuse_fwd=1, cdan_fuse_bwd=1, cdan_distance_fwd=1, cdan_distance_bwd=1)
 
     def __init__(self, ops, torch):
         self.ops, self.torch, self.records, self.orig, self.count = ops, torch, [], {}, 0
@@ -301,7 +305,17 @@ def run_ours(args):
 
     torch.manual_seed(0)
     cfg4 = args.workload == "cfg4"
-    if cfg4:
+    cfg3 = args.workload == "cfg3"
+    if cfg3:
+        from feature_level_style_transfer_for_tsc_b200.train_step import MultiSourceModelSet
+        model = MultiSourceModelSet(CFG3["target"], CFG3["sources"]).to(dev)
+        B = CFG3["B"]
+        n_dom = 1 + len(CFG3["sources"])
+        batches = [O.synthetic_batch(B, *CFG3["target"], n_dom * rank)]
+        batches += [O.synthetic_batch(B, C, Ln, K, n_dom * rank + 1 + i) for i, (C, Ln, K) in enumerate(CFG3["sources"])]
+        host = [t.pin_memory() for xb in batches for t in xb]
+        series_per_gpu = n_dom * B
+    elif cfg4:
         from feature_level_style_transfer_for_tsc_b200.train_step import SingleDomainModelSet
         model = SingleDomainModelSet(CFG4["C"], CFG4["L"], CFG4["K"]).to(dev)
         B = CFG4["B"]
@@ -372,6 +386,12 @@ def run_ours(args):
     # instrumented pass (per-kernel-family device time; not part of any reported step time)
     prof.timing = True
     trainer.use_graph = False
+    # one stream for this pass: an event pair around a launch must not contain waits on the other branch's stream
+    for m in model.modules():
+        if hasattr(m, "two_streams"):
+            m.two_streams = False
+        if hasattr(m, "multi_stream"):
+            m.multi_stream = False
     psteps = 3
     for _ in range(psteps):
         # keep the GPU busy (~12 ms of memsets) while the host enqueues the whole eager step, so that every event
@@ -399,14 +419,14 @@ def run_ours(args):
                     achieved=d["tflops"] or 0.0, peak=peaks["bf16"], unit="TFLOP/s", frac=(d["tflops"] or 0.0) / peaks["bf16"],
                     traffic=None, peak_source=peaks["source"] + " bf16 burst")
     cpu = None
-    if world == 1 and not args.no_cpu_baseline and not cfg4:
+    if world == 1 and not args.no_cpu_baseline and not cfg4 and not cfg3:
         v, dt, cores, threads = cpu_step_rate(3, 1)
         cpu = dict(value=v, unit=UNIT, cores=threads, kind="port",
                    sample=f"3 full cfg2 steps (B=128 per domain) of the oracle port, {dt * 1e3:.0f} ms/step, {cores} host cores")
     line = dict(metric=METRIC, value=series / t_dev, unit=UNIT, n_gpus=world, steps=args.steps,
                 warmup=max(args.warmup, 3), ms_per_step=t_dev / args.steps * 1e3, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="bf16" if args.engine == "tcgen05" else "f32", data="synthetic",
-                config=dict(workload=WORKLOAD4 if cfg4 else WORKLOAD, series_per_step_per_gpu=series_per_gpu, engine=args.engine, parallelism=f"dp{world}",
+                config=dict(workload=WORKLOAD3 if cfg3 else WORKLOAD4 if cfg4 else WORKLOAD, series_per_step_per_gpu=series_per_gpu, engine=args.engine, parallelism=f"dp{world}",
                             cuda_graph=not args.no_graph,
                             l2="flushed between timed steps (256 MiB write, outside the per-step events)"),
                 e2e=dict(value=series / t_e2e, unit=UNIT, h2d_bytes_per_step=h2d_bytes * world, d2h_bytes_per_step=4 * world,
@@ -427,8 +447,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--engine", default="tcgen05", choices=["tcgen05", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"],
-                    help="cfg2 = the headline step (default); cfg4 = long-series OS-CNN forward + backward (secondary)")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4"],
+                    help="cfg2 = the headline step (default); cfg3 = multi-source transfer with the C-DAN loss; "
+                         "cfg4 = long-series OS-CNN forward + backward (both secondary)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

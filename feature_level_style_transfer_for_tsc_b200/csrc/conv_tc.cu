@@ -24,6 +24,7 @@
 //   with a transposing butterfly (31 shuffles per 32 columns).
 // Replaces ConstantPad1d + Conv1d (+ cuDNN dgrad), OS_CNN/OS_CNN.py:70-71; arithmetic SURVEY A1/A2.
 #include "tc_common.cuh"
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -62,6 +63,8 @@ struct ConvTcParams {
     int off_bias, off_wstat, off_plan, off_xs, off_stages;
     int tmem_cols;
     long long* tl;     // optional phase timeline of CTA 0 (tsc_debug_set_timeline), NULL in production
+    int debug;         // experiments only (TSC_CONV_DEBUG): 1 = the issuer does not wait for weight stages (garbage results,
+                       // pure issue rate), 2 = the issuer issues no MMAs (pure weight-stream rate)
 };
 
 #define TL(i) do { if (p.tl && blockIdx.x == 0) p.tl[i] = clock64(); } while (0)
@@ -210,14 +213,16 @@ osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const ConvTcParams p)
         for (int g = 0; g < n_grp; ++g) {
             const uint4* nx = mm + (size_t)min(g + 1, n_grp - 1) * MMA_GROUP;
             const uint4 f0 = nx[0], f1 = nx[1], f2 = nx[2], f3 = nx[3];
-            if (e0.w & PF_FIRST) {
+            if ((e0.w & PF_FIRST) && !(p.debug & 1)) {
                 mbar_wait(&full[s], ph, dead, 3);
                 __syncwarp();     // lanes leave the polling loop at different times: reconverge before the elect
                 tc_fence_after();
                 if (g == 0 && lane == 0) TL(3);
             }
             const bool last = (e3.w & PF_LAST) != 0;
-            if (elect_one()) {
+            if (p.debug & 2) {
+                if (last && elect_one()) tc_commit(&empty[s]);
+            } else if (elect_one()) {
                 umma_bf16(tmem_base + (e0.w & 0xffffu), ((uint64_t)desc_hi << 32) | (a_base16 + e0.x),
                           ((uint64_t)desc_hi << 32) | (b_base16 + e0.y), e0.z, acc);
                 umma_bf16(tmem_base + (e1.w & 0xffffu), ((uint64_t)desc_hi << 32) | (a_base16 + e1.x),
@@ -419,6 +424,15 @@ static long long* g_timeline = nullptr;     // debug only: device buffer of >= 8
 
 static inline int conv_rp(int Kmax) { return (128 + Kmax - 1 + 7) & ~7; }
 
+// experiment knobs (environment, read once): TSC_CONV_STAGE_KB, TSC_CONV_SMEM_FULL, TSC_CONV_DEBUG
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e && e[0] ? atoi(e) : dflt;
+}
+static int knob_stage_bytes() { static const int v = env_int("TSC_CONV_STAGE_KB", PLAN_STAGE_BYTES / 1024) * 1024; return v; }
+static int knob_smem_full() { static const int v = env_int("TSC_CONV_SMEM_FULL", 0); return v; }
+static int knob_debug() { static const int v = env_int("TSC_CONV_DEBUG", 0); return v; }
+
 // ---- the plan: header (16 B) | stage table (8 B each, padded to 16) | MMA table (16 B each) ----------
 struct PlanHost {
     std::vector<uint2> stages;
@@ -447,7 +461,7 @@ static int build_plan(int direction, int Cin, int Cout, int Kmax, const int* s_o
     const int Rp = conv_rp(Kmax);
     // a large activation tile leaves less room for the weight ring: halve the stage so that two stages still fit the
     // half-SM shared-memory budget (two CTAs of different launches can then share an SM)
-    ph->stage_bytes = tt.kc * Rp * 16 > 48 * 1024 ? PLAN_STAGE_BYTES / 2 : PLAN_STAGE_BYTES;
+    ph->stage_bytes = tt.kc * Rp * 16 > 48 * 1024 ? knob_stage_bytes() / 2 : knob_stage_bytes();
     uint32_t stage_src16 = 0, stage_bytes = 0;
     bool open = false;
     for (int oi = 0; oi < tt.n_order; ++oi) {
@@ -548,7 +562,7 @@ int osconv_tc(int direction, const void* x, int dtype, const void* w, const void
     const int slot = p.stage_bytes + ZERO_BLOCK_BYTES;
     // prefer half of an SM's shared memory (113 KB): CTAs of two independent launches (the target and the source branch
     // of a step run on two streams) can then be co-resident and hide each other's load / epilogue latency
-    int cap = SMEM_HALF;
+    int cap = knob_smem_full() ? SMEM_CAP : SMEM_HALF;
     int ns = (cap - p.off_stages) / slot;
     if (ns < 2 && p.n_stages > 1) { cap = SMEM_CAP; ns = (cap - p.off_stages) / slot; }
     if (ns > 8) ns = 8;
@@ -557,6 +571,7 @@ int osconv_tc(int direction, const void* x, int dtype, const void* w, const void
                 p.off_stages);
     p.NS = ns;
     p.tl = g_timeline;
+    p.debug = knob_debug();
     p.tmem_cols = p.np <= 32 ? 32 : p.np <= 64 ? 64 : p.np <= 128 ? 128 : 256;
     CUtensorMap xmap;
     if (make_c8_map(&xmap, x, B, p.kc, L, p.Rp, p.kc) != 0) return -1;

@@ -155,6 +155,8 @@ class MultiSourceModelSet(nn.Module):
         self.pairs = nn.ModuleList([TransferPairModelSet(Ct, Lt, Kt, Cs, Ls, Ks, critic_hidden) for (Cs, Ls, Ks) in sources])
         self._streams = None
 
+    multi_stream = True      # one stream (pair) per source; False runs the pairs one after the other
+
     def parameter_groups(self):
         return [(list(getattr(pair, name).parameters()), lr, pair.CLAMPS.get(name, 0.0))
                 for pair in self.pairs for name, lr in pair.LRS.items()]
@@ -163,7 +165,7 @@ class MultiSourceModelSet(nn.Module):
         n = len(self.pairs)
         style_weight = rest[2 * n] if len(rest) > 2 * n else 1.0
         outs = [None] * n
-        if xt.is_cuda and n > 1:
+        if xt.is_cuda and n > 1 and self.multi_stream:
             main = torch.cuda.current_stream()
             if self._streams is None:
                 self._streams = [torch.cuda.Stream() for _ in range(n - 1)]

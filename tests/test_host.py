@@ -88,3 +88,54 @@ def test_no_product_import_of_the_oracle():
             if fn.endswith(".py"):
                 src = open(os.path.join(dirpath, fn)).read()
                 assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+def test_multi_source_model_set_host_logic():
+    """Configuration 3 on the host: per-pair parameter groups (learning rates and the critic's WGAN clip of
+    train_and_test.py:97-105,763-764), the reversal schedule, and no CPU compute path."""
+    from feature_level_style_transfer_for_tsc_b200.train_step import FlatParameters, MultiSourceModelSet
+    torch.manual_seed(0)
+    model = MultiSourceModelSet((2, 96, 3), [(1, 96, 2), (2, 128, 3)], critic_hidden=8)
+    groups = model.parameter_groups()
+    assert len(groups) == 12 and [g[1] for g in groups[:6]] == [0.001, 0.003, 0.001, 0.001, 0.003, 0.001]
+    assert [g[2] for g in groups[:6]] == [0.0] * 5 + [0.0005]
+    flat = FlatParameters(groups)
+    assert flat.group_clamp.count(0.0005) == 2 and flat.group_end[-1] == flat.flat_p.numel()
+    assert all(p.grad.data_ptr() >= flat.flat_g.data_ptr() for p in flat.params)
+    # the critic's schedule: two calls per step, saturating at max_iter, restorable (graph warm-up leaves no trace)
+    pair = model.pairs[0]
+    st = pair.schedule_state()
+    assert st == (-1, 0.001)
+    vals = pair.ad_net.advance_schedule(2)
+    assert vals[0] == 0.0 and abs(vals[1] - 0.9866142981514305) < 1e-15 and vals[2] == vals[1] and pair.ad_net.iter_num == 1
+    for _ in range(20):
+        pair.ad_net.advance_schedule(2)
+    assert pair.ad_net.iter_num == 20.0 and pair.ad_net.coeff == 1.0
+    pair.set_schedule_state(st)
+    assert pair.ad_net.iter_num == -1
+    pair.ad_net.eval()
+    assert pair.ad_net.advance_schedule(2)[0] == pair.ad_net.coeff and pair.ad_net.iter_num == -1     # eval calls do not count
+    x = torch.zeros(2, 2, 96)
+    y = torch.zeros(2, dtype=torch.long)
+    with pytest.raises(RuntimeError):
+        model(x, y, torch.zeros(2, 1, 96), y, torch.zeros(2, 2, 128), y)
+
+
+def test_cdan_mirror_interface():
+    """Names and signatures of the reference's C_DAN.py / widgets.py critic."""
+    import inspect
+    from feature_level_style_transfer_for_tsc_b200 import C_DAN, widgets
+    assert list(inspect.signature(C_DAN.CDAN).parameters) == [
+        "input_target", "input_g_from_source", "prob_target", "prob_g_from_source", "ad_net", "random_layer"]
+    assert list(inspect.signature(C_DAN.RandomLayer.__init__).parameters)[1:] == ["input_dim_list", "output_dim", "with_nvidia"]
+    torch.manual_seed(0)
+    rl = C_DAN.RandomLayer([12, 3], with_nvidia=False)
+    torch.manual_seed(0)
+    assert torch.equal(rl.random_matrix[0], torch.randn(12, 1024)) and rl.scale_div == 32.0
+    ad = widgets.AdversarialNetworkforCDAN(1024, 16)
+    assert list(ad.state_dict()) == ["ad_layer1.weight", "ad_layer1.bias", "ad_layer2.weight", "ad_layer2.bias",
+                                     "ad_layer3.weight", "ad_layer3.bias"]
+    assert float(ad.ad_layer1.bias.abs().max()) == 0.0 and (ad.iter_num, ad.alpha, ad.max_iter) == (-1, 100.0, 20.0)
+    assert C_DAN.calc_coeff(1, 1.0, 0.0, 100.0, 20.0) == widgets.calc_coeff(1, 1.0, 0.0, 100.0, 20.0)
+    with pytest.raises(RuntimeError):
+        C_DAN.CDAN(torch.zeros(2, 3, 4), torch.zeros(2, 3, 4), torch.zeros(2, 3), torch.zeros(2, 3), ad, rl)
