@@ -35,7 +35,8 @@ static constexpr int TC_THREADS = 192;
 static constexpr int PLAN_STAGE_BYTES = 32 * 1024;               // weight stage; 16 KB for banks whose activation tile is large
 static constexpr int ZERO_BLOCK_BYTES = 512;                      // behind every stage slot: the B operand of padding MMAs
 static constexpr int MMA_GROUP = 4;                               // MMAs issued per elect block
-static constexpr uint32_t PF_FIRST = 1u << 16, PF_LAST = 1u << 17;
+static constexpr uint32_t PF_FIRST = 1u << 16, PF_LAST = 1u << 17;      // flags in the w word of a plan entry
+static constexpr int PF_STAGE_SHIFT = 18, PF_STAGE_MAX = 1 << 14;         // w >> 18: index of the entry's weight stage
 static constexpr int SMEM_HDR = 256;                       // barriers + tmem slot
 
 struct ConvTcParams {
@@ -63,11 +64,14 @@ struct ConvTcParams {
     int off_bias, off_wstat, off_plan, off_xs, off_stages;
     int tmem_cols;
     long long* tl;     // optional phase timeline of CTA 0 (tsc_debug_set_timeline), NULL in production
-    int debug;         // experiments only (TSC_CONV_DEBUG): 1 = the issuer does not wait for weight stages (garbage results,
-                       // pure issue rate), 2 = the issuer issues no MMAs (pure weight-stream rate)
+    int debug;         // experiments only (TSC_CONV_DEBUG; garbage results): 2 = the issuer issues no MMAs (pure weight-stream
+                       // rate), 4 = the producer signals its stages full without copying (pure issue rate), 8 = keep the
+                       // tcgen05 fence after every stage wait (the pre-session-3 behaviour)
 };
 
 #define TL(i) do { if (p.tl && blockIdx.x == 0) p.tl[i] = clock64(); } while (0)
+// per-stage samples of CTA 0 (debug timeline only): slot k of weight stage i, for the first 48 stages
+#define TLS(i, k) do { if (p.tl && blockIdx.x == 0 && (i) < 48) p.tl[8 + (i) * 8 + (k)] = clock64(); } while (0)
 
 // 32 lanes x 32 bit, 32 consecutive columns
 __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, float* v) {
@@ -185,10 +189,14 @@ osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const ConvTcParams p)
             const int n_stages = p.n_stages;
             for (int i = 0; i < n_stages; ++i) {
                 const uint2 e = st[i];                        // {source offset in 16 B units, bytes}
+                TLS(i, 4);
                 mbar_wait(&empty[s], ph ^ 1u, dead, 1);
+                TLS(i, 5);
+                if (p.debug & 4) { mbar_arrive(&full[s]); if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; } continue; }
                 mbar_arrive_expect_tx(&full[s], e.y);
                 bulk_load(stages + (size_t)s * (p.stage_bytes + ZERO_BLOCK_BYTES), reinterpret_cast<const uint8_t*>(p.w) + (size_t)e.x * 16,
                           e.y, &full[s]);
+                TLS(i, 6);
                 if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; }
             }
         }
@@ -202,43 +210,70 @@ osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const ConvTcParams p)
         __syncwarp();             // lanes leave the polling loops at different times: reconverge before every elect
         tc_fence_after();
         if (lane == 0) TL(2);
-        const uint4* mm = reinterpret_cast<const uint4*>(plan_s + 16 + ((p.n_stages * 8 + 15) & ~15));
+        uint4* mm = reinterpret_cast<uint4*>(smem + p.off_plan + 16 + ((p.n_stages * 8 + 15) & ~15));
         const uint32_t desc_hi = (128u >> 4) | (1u << 14);                        // SBO = 128 B, descriptor version 1
         const uint32_t a_base16 = (smem_u32(xs) >> 4) | ((uint32_t)p.Rp << 16);    // LBO = Rp * 16 B
         const uint32_t st_base16 = smem_u32(stages) >> 4;
         const uint32_t stage16 = (uint32_t)(p.stage_bytes + ZERO_BLOCK_BYTES) >> 4;
-        uint32_t s = 0, ph = 0, b_base16 = st_base16, acc = 0;
+        // Relocate the plan once, one issue group per lane: A / B descriptor words and the TMEM address become final
+        // values and the stage flags move to one byte per group, so that the issuing thread only moves four words per
+        // MMA to uniform registers (every instruction of its elect block costs ~6 cycles).
+        uint8_t* gflag = reinterpret_cast<uint8_t*>(mm + p.n_mma);
         const int n_grp = p.n_mma / MMA_GROUP;
-        uint4 e0 = mm[0], e1 = mm[1], e2 = mm[2], e3 = mm[3];
-        for (int g = 0; g < n_grp; ++g) {
-            const uint4* nx = mm + (size_t)min(g + 1, n_grp - 1) * MMA_GROUP;
-            const uint4 f0 = nx[0], f1 = nx[1], f2 = nx[2], f3 = nx[3];
-            if ((e0.w & PF_FIRST) && !(p.debug & 1)) {
-                mbar_wait(&full[s], ph, dead, 3);
-                __syncwarp();     // lanes leave the polling loop at different times: reconverge before the elect
-                tc_fence_after();
-                if (g == 0 && lane == 0) TL(3);
+        for (int g = lane; g < n_grp; g += 32) {
+            uint32_t fl = 0;
+#pragma unroll
+            for (int j = 0; j < MMA_GROUP; ++j) {
+                uint4 e = mm[g * MMA_GROUP + j];
+                const uint32_t slot = (e.w >> PF_STAGE_SHIFT) % (uint32_t)p.NS;
+                if (j == 0 && (e.w & PF_FIRST)) fl |= 1u;
+                if (j == MMA_GROUP - 1 && (e.w & PF_LAST)) fl |= 2u;
+                e.x += a_base16;
+                e.y += st_base16 + slot * stage16;
+                e.w = tmem_base + (e.w & 0xffffu);
+                mm[g * MMA_GROUP + j] = e;
             }
-            const bool last = (e3.w & PF_LAST) != 0;
+            gflag[g] = (uint8_t)fl;
+        }
+        __syncwarp();
+        uint32_t s = 0, ph = 0, acc = 0;
+        int stage_i = 0;
+        uint4 e0 = mm[0], e1 = mm[1], e2 = mm[2], e3 = mm[3];
+        uint32_t fl = gflag[0];
+        for (int g = 0; g < n_grp; ++g) {
+            const int gn = min(g + 1, n_grp - 1);
+            const uint4* nx = mm + (size_t)gn * MMA_GROUP;
+            const uint4 f0 = nx[0], f1 = nx[1], f2 = nx[2], f3 = nx[3];
+            const uint32_t fln = gflag[gn];
+            if (fl & 1u) {
+                if (lane == 0) TLS(stage_i, 0);
+                // The stage's bytes were written by the async proxy and published through the mbarrier's complete_tx:
+                // tcgen05.mma may read them without a tcgen05 fence (the fence is for ordering against other threads'
+                // tcgen05 operations).  With the fence here the issuer paid ~240 cycles per already-complete stage.
+                if (!mbar_test_wait(&full[s], ph)) mbar_wait(&full[s], ph, dead, 3);
+                __syncwarp();     // lanes leave the polling loop at different times: reconverge before the elect
+                if (p.debug & 8) tc_fence_after();
+                if (g == 0 && lane == 0) TL(3);
+                if (lane == 0) TLS(stage_i, 1);
+            }
+            const bool last = (fl & 2u) != 0;
             if (p.debug & 2) {
                 if (last && elect_one()) tc_commit(&empty[s]);
             } else if (elect_one()) {
-                umma_bf16(tmem_base + (e0.w & 0xffffu), ((uint64_t)desc_hi << 32) | (a_base16 + e0.x),
-                          ((uint64_t)desc_hi << 32) | (b_base16 + e0.y), e0.z, acc);
-                umma_bf16(tmem_base + (e1.w & 0xffffu), ((uint64_t)desc_hi << 32) | (a_base16 + e1.x),
-                          ((uint64_t)desc_hi << 32) | (b_base16 + e1.y), e1.z, 1u);
-                umma_bf16(tmem_base + (e2.w & 0xffffu), ((uint64_t)desc_hi << 32) | (a_base16 + e2.x),
-                          ((uint64_t)desc_hi << 32) | (b_base16 + e2.y), e2.z, 1u);
-                umma_bf16(tmem_base + (e3.w & 0xffffu), ((uint64_t)desc_hi << 32) | (a_base16 + e3.x),
-                          ((uint64_t)desc_hi << 32) | (b_base16 + e3.y), e3.z, 1u);
+                umma_bf16(e0.w, ((uint64_t)desc_hi << 32) | e0.x, ((uint64_t)desc_hi << 32) | e0.y, e0.z, acc);
+                umma_bf16(e1.w, ((uint64_t)desc_hi << 32) | e1.x, ((uint64_t)desc_hi << 32) | e1.y, e1.z, 1u);
+                umma_bf16(e2.w, ((uint64_t)desc_hi << 32) | e2.x, ((uint64_t)desc_hi << 32) | e2.y, e2.z, 1u);
+                umma_bf16(e3.w, ((uint64_t)desc_hi << 32) | e3.x, ((uint64_t)desc_hi << 32) | e3.y, e3.z, 1u);
                 if (last) tc_commit(&empty[s]);      // frees the stage when these MMAs have read it
             }
             acc = 1;
             if (last) {
+                if (lane == 0) TLS(stage_i, 2);
+                ++stage_i;
                 if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; }
-                b_base16 = st_base16 + s * stage16;
             }
             e0 = f0; e1 = f1; e2 = f2; e3 = f3;
+            fl = fln;
         }
         __syncwarp();
         if (elect_one()) tc_commit(acc_full);
@@ -440,16 +475,32 @@ struct PlanHost {
     int stage_bytes = PLAN_STAGE_BYTES;
 };
 
-// A stage ends: pad its MMA list to a multiple of MMA_GROUP with instructions that add zero (N = 16, B = the zero
-// block behind the stage slot, A = the tile base) and flag the last one.
-static void close_stage(PlanHost* ph, uint32_t src16, uint32_t bytes) {
-    ph->stages.push_back(make_uint2(src16, bytes));
+// One MMA of the plan before it is assigned to a stage.
+struct PlanUnit { uint32_t a_off, nt, n_lo, bytes, src16; };
+
+// Emit units [i0, i1) as one weight stage: entries carry their in-stage B offset and the stage index (the kernel turns
+// both into a shared-memory address once, at start-up); the list is padded to a multiple of MMA_GROUP with instructions
+// that add zero (N = 16, B = the zero block behind the stage slot, A = the tile base).
+static void emit_stage(PlanHost* ph, const std::vector<PlanUnit>& u, size_t i0, size_t i1) {
+    const uint32_t stage_idx = (uint32_t)ph->stages.size();
+    uint32_t bytes = 0;
+    for (size_t i = i0; i < i1; ++i) {
+        uint4 e;
+        e.x = u[i].a_off;                                        // A start, 16 B units from the tile base
+        e.y = (bytes >> 4) | (u[i].nt << 16);                    // B start within the stage | LBO = nt * 16 B
+        // = make_idesc_bf16(128, nt, K-major, K-major): F32 accumulate, BF16 x BF16
+        e.z = (1u << 4) | (1u << 7) | (1u << 10) | ((u[i].nt >> 3) << 17) | ((128u >> 4) << 24);
+        e.w = u[i].n_lo | (i == i0 ? PF_FIRST : 0u) | (stage_idx << PF_STAGE_SHIFT);
+        ph->mmas.push_back(e);
+        bytes += u[i].bytes;
+    }
+    ph->stages.push_back(make_uint2(u[i0].src16, bytes));
     while (ph->mmas.size() % MMA_GROUP != 0) {
         uint4 e;
         e.x = 0;
         e.y = ((uint32_t)ph->stage_bytes >> 4) | (16u << 16);      // LBO = 16 rows * 16 B
         e.z = (1u << 4) | (1u << 7) | (1u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
-        e.w = 0;
+        e.w = stage_idx << PF_STAGE_SHIFT;
         ph->mmas.push_back(e);
     }
     ph->mmas.back().w |= PF_LAST;
@@ -462,39 +513,37 @@ static int build_plan(int direction, int Cin, int Cout, int Kmax, const int* s_o
     // a large activation tile leaves less room for the weight ring: halve the stage so that two stages still fit the
     // half-SM shared-memory budget (two CTAs of different launches can then share an SM)
     ph->stage_bytes = tt.kc * Rp * 16 > 48 * 1024 ? knob_stage_bytes() / 2 : knob_stage_bytes();
-    uint32_t stage_src16 = 0, stage_bytes = 0;
-    bool open = false;
+    std::vector<PlanUnit> units;
     for (int oi = 0; oi < tt.n_order; ++oi) {
         const int t = tt.order[oi];
         const int n_lo = tt.n_lo[t], kc_lo = tt.kc_lo[t];
         const int nt = tt.np - n_lo, kspan = tt.kc - kc_lo;
-        // = make_idesc_bf16(128, nt, K-major, K-major): F32 accumulate, BF16 x BF16
-        const uint32_t idesc_host = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nt >> 3) << 17) | ((128u >> 4) << 24);
-        for (int kp = 0; kp < kspan / 2; ++kp) {
-            const uint32_t unit_bytes = (uint32_t)(2 * nt * 16);
-            const uint32_t unit_src16 = (uint32_t)tt.w_off[t] + (uint32_t)(2 * kp * nt);
-            if (open && stage_bytes + unit_bytes > (uint32_t)ph->stage_bytes) {
-                close_stage(ph, stage_src16, stage_bytes);
-                open = false;
-            }
-            uint32_t flags = 0;
-            if (!open) { stage_src16 = unit_src16; stage_bytes = 0; open = true; flags |= PF_FIRST; }
-            uint4 e;
-            e.x = (uint32_t)((kc_lo + 2 * kp) * Rp + t);               // A start, 16 B units from the tile base
-            e.y = (stage_bytes >> 4) | ((uint32_t)nt << 16);           // B start within the stage | LBO = nt * 16 B
-            e.z = idesc_host;
-            e.w = (uint32_t)n_lo | flags;
-            ph->mmas.push_back(e);
-            stage_bytes += unit_bytes;
-        }
+        for (int kp = 0; kp < kspan / 2; ++kp)
+            units.push_back({(uint32_t)((kc_lo + 2 * kp) * Rp + t), (uint32_t)nt, (uint32_t)n_lo, (uint32_t)(2 * nt * 16),
+                             (uint32_t)tt.w_off[t] + (uint32_t)(2 * kp * nt)});
     }
-    TSC_REQUIRE(open && !ph->mmas.empty(), "kernel bank has no live tap");
-    close_stage(ph, stage_src16, stage_bytes);
+    TSC_REQUIRE(!units.empty(), "kernel bank has no live tap");
+    // Stages hold whole issue groups: the issuing thread is the bottleneck of this kernel (~90 cycles per instruction
+    // whatever its N), so an instruction that only pads a group costs as much as a real one.  Units that would leave a
+    // partial group at the end of a stage open the next stage instead; only a stage too small for one group, and the
+    // last stage, are padded.
+    size_t i = 0;
+    while (i < units.size()) {
+        size_t k = 0;
+        uint32_t bytes = 0;
+        while (i + k < units.size() && bytes + units[i + k].bytes <= (uint32_t)ph->stage_bytes) { bytes += units[i + k].bytes; ++k; }
+        TSC_REQUIRE(k >= 1, "one MMA's weights (%u B) exceed the %d B stage", units[i].bytes, ph->stage_bytes);
+        if (i + k < units.size() && k >= (size_t)MMA_GROUP) k -= k % MMA_GROUP;
+        TSC_REQUIRE(ph->stages.size() < (size_t)PF_STAGE_MAX, "more than %d weight stages", PF_STAGE_MAX);
+        emit_stage(ph, units, i, i + k);
+        i += k;
+    }
     return 0;
 }
 
 static inline size_t plan_bytes_of(const PlanHost& ph) {
-    return 16 + ((ph.stages.size() * 8 + 15) & ~(size_t)15) + ph.mmas.size() * 16;
+    // ... | one flag byte per issue group (filled in by the kernel), padded to 16
+    return 16 + ((ph.stages.size() * 8 + 15) & ~(size_t)15) + ph.mmas.size() * 16 + ((ph.mmas.size() / MMA_GROUP + 15) & ~(size_t)15);
 }
 
 }  // namespace tc
