@@ -393,10 +393,26 @@ def run_ours(args):
         if hasattr(m, "multi_stream"):
             m.multi_stream = False
     psteps = 3
+    # keep the GPU busy with memsets while the host enqueues the whole eager step, so that every event pair brackets
+    # device time only -- without this the host's launch latency sits between the events.  The backlog is sized from
+    # the measured host time of one eager step and the measured duration of one memset (x1.5).
+    prof.timing = False
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    trainer.step(*dev_in)
+    host_s = time.perf_counter() - t0
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        flush.zero_()
+    e1.record()
+    torch.cuda.synchronize()
+    memset_s = e0.elapsed_time(e1) * 1e-3 / 20
+    backlog = int(1.5 * host_s / memset_s) + 50
+    prof.timing = True
     for _ in range(psteps):
-        # keep the GPU busy (~12 ms of memsets) while the host enqueues the whole eager step, so that every event
-        # pair brackets device time only -- without this the host's launch latency sits between the events
-        for _ in range(260):
+        for _ in range(backlog):
             flush.zero_()
         trainer.step(*dev_in)
     torch.cuda.synchronize()

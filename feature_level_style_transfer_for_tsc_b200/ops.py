@@ -20,7 +20,7 @@ from . import _lib as L
 #   "simt_bf16" : the CUDA-core kernels fed the SAME bf16 operands as the tensor-core engine -- not a
 #                 product mode: it is the bit-faithful checker of the tcgen05 kernels used by tests.
 _TC_READY = ("conv", "wgrad", "gram")   # families whose tcgen05 kernel exists
-_CFG = {"conv": L.ENGINE_TCGEN05, "wgrad": L.ENGINE_TCGEN05, "gram": L.ENGINE_SIMT, "op_dtype": L.TSC_BF16,
+_CFG = {"conv": L.ENGINE_TCGEN05, "wgrad": L.ENGINE_TCGEN05, "gram": L.ENGINE_TCGEN05, "op_dtype": L.TSC_BF16,
         "name": "tcgen05"}
 
 

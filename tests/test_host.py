@@ -139,3 +139,17 @@ def test_cdan_mirror_interface():
     assert C_DAN.calc_coeff(1, 1.0, 0.0, 100.0, 20.0) == widgets.calc_coeff(1, 1.0, 0.0, 100.0, 20.0)
     with pytest.raises(RuntimeError):
         C_DAN.CDAN(torch.zeros(2, 3, 4), torch.zeros(2, 3, 4), torch.zeros(2, 3), torch.zeros(2, 3), ad, rl)
+
+
+def test_default_engine_is_the_tensor_core_path_for_every_family():
+    """A process that never calls set_engine must still run conv, wgrad AND the Gram loss on tcgen05 (a default that left
+    the Gram family on the SIMT checker went unnoticed in round 1 because bench.py always calls set_engine)."""
+    import importlib
+    import feature_level_style_transfer_for_tsc_b200.ops as ops
+    fresh = importlib.reload(ops)
+    try:
+        L = fresh.L
+        assert [fresh.get_engine(f) for f in ("conv", "wgrad", "gram")] == [L.ENGINE_TCGEN05] * 3
+        assert fresh.engine_name() == "tcgen05" and fresh.op_dtype() == L.TSC_BF16
+    finally:
+        importlib.reload(ops)
