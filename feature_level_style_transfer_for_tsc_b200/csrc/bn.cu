@@ -418,69 +418,38 @@ __device__ __forceinline__ void block_sum8(float (&v)[8], float* sh /*[8][8]*/) 
 // running statistics (momentum, unbiased variance -- torch semantics).
 __device__ __forceinline__ void bn_branch_coeffs(const tsc_bn_branch& br, int ch, int C, int Cp, int n_part, int ltiles, int L,
                                                  bool writer, float* coef_s, float* sh) {
-    float mean[8], var[8];
+    // Warp j of the block owns channel j of the chunk: its lanes stride over the per-CTA (mean, M2) pairs, merge them
+    // with Chan's update and finish with a butterfly -- one round of global loads and one barrier per branch (the block
+    // used to make two passes over the partials with three block-wide reductions: half of the kernel's time at cfg2
+    // size, profiles/README.md session 3).  Lane 0's merge order is fixed, so the result is deterministic.
+    (void)sh;
+    const int j = threadIdx.x >> 5, lane = threadIdx.x & 31, c = ch * 8 + j;
+    float m = 0.f, v = 1.f;
     if (br.stat_partial) {
         const float2* part = reinterpret_cast<const float2*>(br.stat_partial);
-        float sn = 0.f, sm[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) sm[j] = 0.f;
-        for (int i = threadIdx.x; i < n_part; i += BF_THREADS) {
-            const float n = (float)min(128, L - (i % ltiles) * 128);
-            sn += n;
-            const float2* p = part + (size_t)i * Cp + ch * 8;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) sm[j] = fmaf(n, p[j].x, sm[j]);
+        float n = 0.f, mu = 0.f, q = 0.f;
+        for (int i = lane; i < n_part; i += 32) {
+            const float ni = (float)min(128, L - (i % ltiles) * 128);
+            const float2 pr = part[(size_t)i * Cp + c];
+            welford_merge(n, mu, q, ni, pr.x, pr.y);
         }
-        float tmp[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) tmp[j] = sm[j];
-        block_sum8(tmp, sh);
-        float nn[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) nn[j] = j == 0 ? sn : 0.f;
-        block_sum8(nn, sh);
-        const float N = nn[0];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) mean[j] = tmp[j] / N;
-        float q[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) q[j] = 0.f;
-        for (int i = threadIdx.x; i < n_part; i += BF_THREADS) {
-            const float n = (float)min(128, L - (i % ltiles) * 128);
-            const float2* p = part + (size_t)i * Cp + ch * 8;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float d = p[j].x - mean[j];
-                q[j] += p[j].y + n * d * d;
-            }
+        for (int o = 16; o > 0; o >>= 1) {
+            const float nb = __shfl_xor_sync(0xffffffffu, n, o), mb = __shfl_xor_sync(0xffffffffu, mu, o);
+            const float qb = __shfl_xor_sync(0xffffffffu, q, o);
+            welford_merge(n, mu, q, nb, mb, qb);
         }
-        block_sum8(q, sh);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) var[j] = q[j] / N;
-        if (writer && threadIdx.x < 8) {
-            const int j = threadIdx.x, c = ch * 8 + j;
-            if (c < C && br.running_mean && br.momentum > 0.f) {
-                float m = 0.f, v = 0.f;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) { if (k == j) { m = mean[k]; v = q[k]; } }
-                br.running_mean[c] = (1.f - br.momentum) * br.running_mean[c] + br.momentum * m;
-                br.running_var[c] = (1.f - br.momentum) * br.running_var[c] + br.momentum * (v / fmaxf(N - 1.f, 1.f));
-            }
+        m = mu;
+        v = q / n;
+        if (writer && lane == 0 && c < C && br.running_mean && br.momentum > 0.f) {
+            br.running_mean[c] = (1.f - br.momentum) * br.running_mean[c] + br.momentum * mu;
+            br.running_var[c] = (1.f - br.momentum) * br.running_var[c] + br.momentum * (q / fmaxf(n - 1.f, 1.f));
         }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = ch * 8 + j;
-            mean[j] = c < C ? br.running_mean[c] : 0.f;
-            var[j] = c < C ? br.running_var[c] : 1.f;
-        }
+    } else if (c < C) {
+        m = br.running_mean[c];
+        v = br.running_var[c];
     }
-    __syncthreads();
-    if (threadIdx.x < 8) {
-        const int j = threadIdx.x, c = ch * 8 + j;
-        float m = 0.f, v = 1.f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { if (k == j) { m = mean[k]; v = var[k]; } }
+    if (lane == 0) {
         float invstd = 0.f, sc = 0.f, shf = 0.f;
         if (c < C) {
             invstd = 1.f / sqrtf(v + br.eps);
@@ -663,16 +632,22 @@ __global__ void __launch_bounds__(BF_THREADS) bn_bwd_apply_fused_kernel(const fl
     pdl_wait();
     const int ch = blockIdx.x, sp = blockIdx.y, Cp = Cpc * 8;
     float s1[8], s2[8];
+    {
+        // warp w sums the (S1, S2) partials of channel w of the chunk (fixed order), one barrier
+        const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const float2* part = reinterpret_cast<const float2*>(a.red_partial) + ch * 8 + w;
+        float a1 = 0.f, a2 = 0.f;
+        for (int i = lane; i < n_part; i += 32) {
+            const float2 pr = part[(size_t)i * Cp];
+            a1 += pr.x; a2 += pr.y;
+        }
+        a1 = warp_sum(a1);
+        a2 = warp_sum(a2);
+        if (lane == 0) { sh[w] = a1; sh[8 + w] = a2; }
+        __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-    const float2* part = reinterpret_cast<const float2*>(a.red_partial);
-    for (int i = threadIdx.x; i < n_part; i += BF_THREADS) {
-        const float2* p = part + (size_t)i * Cp + ch * 8;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { s1[j] += p[j].x; s2[j] += p[j].y; }
+        for (int j = 0; j < 8; ++j) { s1[j] = sh[j]; s2[j] = sh[8 + j]; }
     }
-    block_sum8(s1, sh);
-    block_sum8(s2, sh);
     float mean[8], invstd[8], g[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {

@@ -315,6 +315,8 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const __grid_constant__
     extern __shared__ float wsm[];                    // [8][16][Kmax]
     __shared__ PackTaps pt;
     __shared__ int scratch[2 * TSC_MAX_TAPS + 1];
+    __shared__ short s_tap[TSC_MAX_TAPS];             // s(t): the load loop indexes it per element -- from the constant bank
+                                                      // a warp's 31 distinct taps serialise (the kernel's hot spot in round 1)
     const tsc_pack_layer& ly = batch.layer[blockIdx.y];
     const int Cin = ly.Cin, Cout = ly.Cout, Kmax = ly.Kmax;
     const int np_f = (Cout + 15) & ~15, cin_p = (Cin + 15) & ~15;
@@ -323,7 +325,8 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const __grid_constant__
     if ((int)blockIdx.x >= n_cc * n_kp) return;
     const int cc = blockIdx.x / n_kp, kp = blockIdx.x % n_kp;
     const int co0 = cc * 8, ci0 = kp * 16;
-    pack_build_taps(ly, &pt, scratch);       // geometry only: overlaps the tail of the previous kernel
+    if ((int)threadIdx.x < Kmax) s_tap[threadIdx.x] = ly.s_of_tap[threadIdx.x];
+    pack_build_taps(ly, &pt, scratch);       // geometry only: overlaps the tail of the previous kernel (ends with a barrier)
     pdl_wait();
     // ---- load (and mask in place) ----
     float* W = ly.W;
@@ -334,7 +337,7 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const __grid_constant__
         float v = 0.f;
         if (co < Cout && ci < Cin) {
             float* p = W + ((size_t)co * Cin + ci) * Kmax + t;
-            if (co >= ly.s_of_tap[t]) v = *p;
+            if (co >= s_tap[t]) v = *p;
             else if (ly.zero_masked) *p = 0.f;
         }
         wsm[e] = v;
