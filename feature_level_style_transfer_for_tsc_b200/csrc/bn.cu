@@ -563,14 +563,19 @@ __global__ void __launch_bounds__(BF_THREADS) bn_apply_pooled_kernel(const tsc_b
 
 // Top of a stack: the incoming gradient is NCL fp32.  d = dout * [z > 0] (z = scale*y + shift [+ second branch]) is
 // written as c8 fp32 and the per-block partial sums (S1, S2) of each branch go to red_partial[S][Cp][2].
-__global__ void __launch_bounds__(BF_THREADS) bn_bwd_top_kernel(const float* __restrict__ dout, const tsc_bn_bwd_branch a,
-                                                                 const tsc_bn_bwd_branch b2, int two, int relu,
+// TWO is a template parameter: the two-branch form keeps 8 more coefficient vectors live (141 registers, one block per SM,
+// four waves at cfg2 size); each form is bounded to two blocks per SM.
+template <bool TWO>
+__global__ void __launch_bounds__(BF_THREADS, 2) bn_bwd_top_kernel(const float* __restrict__ dout, const tsc_bn_bwd_branch a,
+                                                                    const tsc_bn_bwd_branch b2, int two_unused, int relu,
                                                                  float* __restrict__ d_c8, int B, int C, int Cpc, int L,
                                                                  int S, int pooled) {
     __shared__ float sh[64];
     pdl_trigger();
     pdl_wait();
     const int ch = blockIdx.x, sp = blockIdx.y, Cp = Cpc * 8;
+    constexpr bool two = TWO;
+    (void)two_unused;
     float mean[8], invstd[8], sc[8], sf[8], mean2[8], invstd2[8], sc2[8], sf2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -735,7 +740,7 @@ int tsc_bn_bwd_top(const float* dout_ncl, const tsc_bn_bwd_branch* a, const tsc_
     TSC_REQUIRE(B > 0 && C > 0 && L > 0, "bad shape [%d,%d,%d]", B, C, L);
     const int Cpc = pad16(C) / 8, S = bn_splits(B, Cpc, L);
     const tsc_bn_bwd_branch bb = b ? *b : *a;
-    launch_pdl(bn_bwd_top_kernel, dim3(Cpc, S), dim3(BF_THREADS), 0, (cudaStream_t)stream, dout_ncl, *a, bb, (int)(b != nullptr), relu, d_c8,
+    launch_pdl(b ? bn_bwd_top_kernel<true> : bn_bwd_top_kernel<false>, dim3(Cpc, S), dim3(BF_THREADS), 0, (cudaStream_t)stream, dout_ncl, *a, bb, (int)(b != nullptr), relu, d_c8,
                B, C, Cpc, L, S, 0);
     TSC_LAUNCH_CHECK();
     return 0;
@@ -747,7 +752,7 @@ int tsc_bn_bwd_top_pooled(const float* dpooled, const tsc_bn_bwd_branch* a, int 
     TSC_REQUIRE(dpooled && a && a->y_c8 && a->coef && a->red_partial && d_c8, "NULL argument");
     TSC_REQUIRE(B > 0 && C > 0 && L > 0, "bad shape [%d,%d,%d]", B, C, L);
     const int Cpc = pad16(C) / 8, S = bn_splits(B, Cpc, L);
-    launch_pdl(bn_bwd_top_kernel, dim3(Cpc, S), dim3(BF_THREADS), 0, (cudaStream_t)stream, dpooled, *a, *a, 0, relu, d_c8, B, C, Cpc, L, S, 1);
+    launch_pdl(bn_bwd_top_kernel<false>, dim3(Cpc, S), dim3(BF_THREADS), 0, (cudaStream_t)stream, dpooled, *a, *a, 0, relu, d_c8, B, C, Cpc, L, S, 1);
     TSC_LAUNCH_CHECK();
     return 0;
 }
