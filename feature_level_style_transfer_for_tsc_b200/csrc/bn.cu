@@ -2,15 +2,19 @@
 // All HBM-bound: one thread moves one 32 B row of 8 channels; a warp moves 1 KB contiguous.
 // Reference semantics: OS_CNN/OS_CNN.py:65,72-74,165,176-180; formulas SURVEY appendix A2.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace tsc {
 
 static constexpr int BN_THREADS = 256;
 
-// number of row-splits per channel chunk so that the grid is a couple of waves of 148 SMs
-static int bn_splits(int B, int Cpc, int L) {
+// number of row-splits per channel chunk so that the grid is exactly ONE wave of `per_sm` resident blocks on each of the
+// 148 SMs (rounded down: these kernels are latency-bound, and a grid of 600 blocks on 592 slots ran a second wave of
+// eight blocks that doubled the kernel's time -- profiles/README.md, session 3)
+static int bn_splits(int B, int Cpc, int L, int per_sm = 4) {
     const long long rows = (long long)B * L;
-    int s = cdiv(148 * 4, Cpc);
+    static const bool legacy = [] { const char* e = getenv("TSC_BN_LEGACY_SPLITS"); return e && e[0] == '1'; }();   // A/B knob
+    int s = legacy ? cdiv(148 * 4, Cpc) : (148 * per_sm) / Cpc;
     const int max_s = (int)((rows + BN_THREADS - 1) / BN_THREADS);   // at least one row per thread
     if (s > max_s) s = max_s;
     if (s < 1) s = 1;
@@ -701,7 +705,10 @@ __global__ void __launch_bounds__(BF_THREADS) bn_bwd_apply_fused_kernel(const fl
 
 extern "C" {
 
-int tsc_bn_fused_splits(int B, int C, int L) { return tsc::bn_splits(B, tsc::pad16(C) / 8, L); }
+static constexpr int BWD_TOP_PER_SM = 2;        // __launch_bounds__ of bn_bwd_top_kernel
+static constexpr int BWD_APPLY_PER_SM = 3;      // bn_bwd_apply_fused_kernel: 80 registers x 256 threads
+
+int tsc_bn_fused_splits(int B, int C, int L) { return tsc::bn_splits(B, tsc::pad16(C) / 8, L, BWD_TOP_PER_SM); }
 
 int tsc_bn_apply_fused(const tsc_bn_branch* a, const tsc_bn_branch* b, int n_part, int relu, void* out, int out_kind, int B,
                        int C, int L, tsc_stream_t stream) {
@@ -738,7 +745,7 @@ int tsc_bn_bwd_top(const float* dout_ncl, const tsc_bn_bwd_branch* a, const tsc_
     TSC_REQUIRE(dout_ncl && a && a->y_c8 && a->coef && a->red_partial && d_c8, "NULL argument");
     TSC_REQUIRE(!b || (b->y_c8 && b->coef && b->red_partial), "second branch incomplete");
     TSC_REQUIRE(B > 0 && C > 0 && L > 0, "bad shape [%d,%d,%d]", B, C, L);
-    const int Cpc = pad16(C) / 8, S = bn_splits(B, Cpc, L);
+    const int Cpc = pad16(C) / 8, S = bn_splits(B, Cpc, L, BWD_TOP_PER_SM);
     const tsc_bn_bwd_branch bb = b ? *b : *a;
     launch_pdl(b ? bn_bwd_top_kernel<true> : bn_bwd_top_kernel<false>, dim3(Cpc, S), dim3(BF_THREADS), 0, (cudaStream_t)stream, dout_ncl, *a, bb, (int)(b != nullptr), relu, d_c8,
                B, C, Cpc, L, S, 0);
@@ -751,7 +758,7 @@ int tsc_bn_bwd_top_pooled(const float* dpooled, const tsc_bn_bwd_branch* a, int 
     using namespace tsc;
     TSC_REQUIRE(dpooled && a && a->y_c8 && a->coef && a->red_partial && d_c8, "NULL argument");
     TSC_REQUIRE(B > 0 && C > 0 && L > 0, "bad shape [%d,%d,%d]", B, C, L);
-    const int Cpc = pad16(C) / 8, S = bn_splits(B, Cpc, L);
+    const int Cpc = pad16(C) / 8, S = bn_splits(B, Cpc, L, BWD_TOP_PER_SM);
     launch_pdl(bn_bwd_top_kernel<false>, dim3(Cpc, S), dim3(BF_THREADS), 0, (cudaStream_t)stream, dpooled, *a, *a, 0, relu, d_c8, B, C, Cpc, L, S, 1);
     TSC_LAUNCH_CHECK();
     return 0;
@@ -763,7 +770,7 @@ int tsc_bn_bwd_apply_fused(const float* d_c8, const tsc_bn_bwd_branch* a, int n_
     TSC_REQUIRE(d_c8 && a && a->coef && a->red_partial && a->gamma && dy_c8, "NULL argument");
     TSC_REQUIRE(!a->training || a->y_c8, "training-mode backward needs y");
     TSC_REQUIRE(B > 0 && C > 0 && L > 0 && n_part > 0, "bad shape [%d,%d,%d] n_part=%d", B, C, L, n_part);
-    const int Cpc = pad16(C) / 8, S = bn_splits(B, Cpc, L);
+    const int Cpc = pad16(C) / 8, S = bn_splits(B, Cpc, L, BWD_APPLY_PER_SM);
     cudaStream_t cs = (cudaStream_t)stream;
     dim3 grid(Cpc, S);
     if (dy_dtype == TSC_BF16)
