@@ -337,8 +337,10 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const __grid_constant__
         float v = 0.f;
         if (co < Cout && ci < Cin) {
             float* p = W + ((size_t)co * Cin + ci) * Kmax + t;
-            if (co >= s_tap[t]) v = *p;
-            else if (ly.zero_masked) *p = 0.f;
+            const float w = *p;                          // the whole slab row is read: coalesced, no divergent loads
+            if (co >= s_tap[t]) v = w;
+            else if (ly.zero_masked && w != 0.f) *p = 0.f;   // masked taps stay zero once masked (their gradient is an
+                                                             // exact zero): after the first step nothing is stored
         }
         wsm[e] = v;
     }
