@@ -231,7 +231,9 @@ __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __res
     float* o = dW + ((size_t)co * Cin + ci) * Kmax + t_base;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        if (t_base + j < Kmax) o[j] = accumulate ? o[j] + acc[j] : acc[j];
+        if (t_base + j >= Kmax) continue;
+        if (!accumulate) o[j] = acc[j];                 // masked taps: the exact zero
+        else if (src[j]) o[j] += acc[j];                // accumulate: a masked tap adds nothing, leave it untouched
     }
 }
 
