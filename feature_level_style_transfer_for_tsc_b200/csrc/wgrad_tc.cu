@@ -32,6 +32,18 @@ static constexpr int WG_MAX_ITEMS = 192;
 static constexpr int WG_HDR = 256;
 static constexpr int WG_STAGES = 2;
 static constexpr int WG_TMEM_COLS = 256;     // half of TMEM: CTAs of two independent launches can be co-resident
+static constexpr int WG_SMEM_HALF = 113 * 1024;
+
+// TMEM columns of a CTA = accumulators (taps) per work item x padded in channels.  Half of TMEM when two CTAs can share
+// an SM; all of it when the shared-memory ring of the shape rules that out anyway (Cin > 128: the 144 -> 72 bank of the
+// classifier then stages one (dY, X) tile pair per THREE taps instead of per tap -- it was the slowest launch of the
+// cfg2 step, 115 us, profiles/README.md session 3).
+static inline int wg_stage_bytes(int cinp, int NT) { return 16 * WG_LT * 16 + (cinp / 8) * ((WG_LT + NT - 1 + 7) & ~7) * 16; }
+static inline int wg_tmem_cols(int cinp) {
+    const int nt_half = WG_TMEM_COLS / cinp;
+    if (nt_half >= 1 && WG_HDR + WG_STAGES * wg_stage_bytes(cinp, nt_half) <= WG_SMEM_HALF) return WG_TMEM_COLS;
+    return 512;
+}
 
 struct WgItem { short m0, t0, nt, pad; };
 struct WgItems { int n; WgItem it[WG_MAX_ITEMS]; };
@@ -50,6 +62,7 @@ struct WgParams {
     int S;              // position splits
     int NT;             // accumulators (taps) per item
     int stage_bytes;
+    int tmem_cols;      // 256 or 512 (wg_tmem_cols)
     long long* tl;      // optional phase timeline of CTA (0,0) (tsc_debug_set_timeline), NULL in production
 };
 
@@ -78,7 +91,7 @@ oswgrad_tc_kernel(const __grid_constant__ WgItems items, const WgParams p) {
         mbar_init(acc_full, 2);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, WG_TMEM_COLS);
+    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -173,7 +186,7 @@ oswgrad_tc_kernel(const __grid_constant__ WgItems items, const WgParams p) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, WG_TMEM_COLS);
+    if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     if (warp == 1 && lane == 0) WTL(7);
 }
 
@@ -246,7 +259,7 @@ static int wgrad_tc_items(int Cin, int Cout, int Kmax, const int* s_of_tap, tc::
                           int* m_split) {
     using namespace tc;
     const int np = pad16(Cout), cinp = pad16(Cin);
-    const int NT = tc::WG_TMEM_COLS / cinp;
+    const int NT = tc::wg_tmem_cols(cinp) / cinp;
     const int MT = np > 128 ? 2 : 1;
     *m_split = MT == 2 ? np - 128 : 0;
     items->n = 0;
@@ -274,14 +287,14 @@ static int wgrad_tc_items(int Cin, int Cout, int Kmax, const int* s_of_tap, tc::
 
 // upper bound on the number of work items without the tap table: 2 tiles x ceil(Kmax / NT)
 static int wgrad_tc_max_items(int Cin, int Cout, int Kmax) {
-    const int cinp = pad16(Cin), NT = tc::WG_TMEM_COLS / cinp, MT = pad16(Cout) > 128 ? 2 : 1;
+    const int cinp = pad16(Cin), NT = tc::wg_tmem_cols(cinp) / cinp, MT = pad16(Cout) > 128 ? 2 : 1;
     return MT * cdiv(Kmax, NT);
 }
 
 int wgrad_tc_splits(int B, int L, int Cin, int Cout, int Kmax) {
     const int items = wgrad_tc_max_items(Cin, Cout, Kmax);
     const int ntile = B * cdiv(L, tc::WG_LT);
-    int s = cdiv(148, items);
+    int s = 148 / items;          // rounded down: one CTA per SM, a 155-CTA grid runs a second wave
     if (s > ntile) s = ntile;
     if (s > 32) s = 32;
     if (s < 1) s = 1;
@@ -289,7 +302,7 @@ int wgrad_tc_splits(int B, int L, int Cin, int Cout, int Kmax) {
 }
 
 size_t wgrad_tc_workspace_bytes(int B, int L, int Cin, int Cout, int Kmax) {
-    const int cinp = pad16(Cin), NT = tc::WG_TMEM_COLS / cinp;
+    const int cinp = pad16(Cin), NT = tc::wg_tmem_cols(cinp) / cinp;
     return (size_t)wgrad_tc_splits(B, L, Cin, Cout, Kmax) * wgrad_tc_max_items(Cin, Cout, Kmax) * NT * cinp * 128 * sizeof(float);
 }
 
@@ -303,7 +316,8 @@ int oswgrad_tc(const void* dy, const void* x, int dtype, float* dW, void* worksp
     int m_split = 0;
     if (wgrad_tc_items(Cin, Cout, Kmax, s_of_tap, &items, &lk, &m_split) != 0) return -1;
     const int np = pad16(Cout), cinp = pad16(Cin);
-    const int NT = tc::WG_TMEM_COLS / cinp;
+    p.tmem_cols = wg_tmem_cols(cinp);
+    const int NT = p.tmem_cols / cinp;
     p.part = (float*)workspace;
     p.B = B; p.L = L; p.ltiles = cdiv(L, WG_LT);
     p.taps = Kmax; p.pad_left = (Kmax - 1) / 2;
@@ -312,7 +326,7 @@ int oswgrad_tc(const void* dy, const void* x, int dtype, float* dW, void* worksp
     p.S = wgrad_tc_splits(B, L, Cin, Cout, Kmax);
     p.NT = NT;
     p.tl = g_wg_timeline;
-    p.stage_bytes = 16 * WG_LT * 16 + p.kcx * p.RX * 16;
+    p.stage_bytes = wg_stage_bytes(cinp, NT);
     const int smem = WG_HDR + WG_STAGES * p.stage_bytes;
     TSC_REQUIRE(smem <= 227 * 1024, "wgrad shape needs %d B of shared memory: unsupported", smem);
     p.dy = (const __nv_bfloat16*)dy;
