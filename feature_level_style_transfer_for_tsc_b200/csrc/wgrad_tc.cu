@@ -22,6 +22,7 @@
 // float atomics), writes the exact zeros of the masked taps and can accumulate into dW (flat gradient bucket).
 // Replaces cuDNN/oneDNN wgrad of OS_CNN/OS_CNN.py:71.
 #include "tc_common.cuh"
+#include <algorithm>
 
 namespace tsc {
 namespace tc {
@@ -291,19 +292,28 @@ static int wgrad_tc_max_items(int Cin, int Cout, int Kmax) {
     return MT * cdiv(Kmax, NT);
 }
 
-int wgrad_tc_splits(int B, int L, int Cin, int Cout, int Kmax) {
-    const int items = wgrad_tc_max_items(Cin, Cout, Kmax);
+// position splits for `items` work items: one CTA per SM, a single wave (rounded down), at most 32 splits
+static int wgrad_tc_splits_for(int items, int B, int L) {
     const int ntile = B * cdiv(L, tc::WG_LT);
-    int s = 148 / items;          // rounded down: one CTA per SM, a 155-CTA grid runs a second wave
+    int s = 148 / items;
     if (s > ntile) s = ntile;
     if (s > 32) s = 32;
     if (s < 1) s = 1;
     return s;
 }
 
+int wgrad_tc_splits(int B, int L, int Cin, int Cout, int Kmax) {
+    return wgrad_tc_splits_for(wgrad_tc_max_items(Cin, Cout, Kmax), B, L);
+}
+
+// The launch sizes its splits from the ACTUAL number of work items (masked taps of the low channel tile drop out: 15
+// items instead of the bound of 22 for the 72 -> 228 bank), so the workspace is sized for the most CTA-private blocks
+// any launch can write: max(148, items) of them.
 size_t wgrad_tc_workspace_bytes(int B, int L, int Cin, int Cout, int Kmax) {
     const int cinp = pad16(Cin), NT = tc::wg_tmem_cols(cinp) / cinp;
-    return (size_t)wgrad_tc_splits(B, L, Cin, Cout, Kmax) * wgrad_tc_max_items(Cin, Cout, Kmax) * NT * cinp * 128 * sizeof(float);
+    const int blocks = std::max(148, wgrad_tc_max_items(Cin, Cout, Kmax));
+    (void)B; (void)L;
+    return (size_t)blocks * NT * cinp * 128 * sizeof(float);
 }
 
 int oswgrad_tc(const void* dy, const void* x, int dtype, float* dW, void* workspace, int accumulate, int B, int L, int Cin,
@@ -323,7 +333,7 @@ int oswgrad_tc(const void* dy, const void* x, int dtype, float* dW, void* worksp
     p.taps = Kmax; p.pad_left = (Kmax - 1) / 2;
     p.np = np; p.kcx = cinp / 8;
     p.RX = (WG_LT + NT - 1 + 7) & ~7;
-    p.S = wgrad_tc_splits(B, L, Cin, Cout, Kmax);
+    p.S = wgrad_tc_splits_for(items.n, B, L);
     p.NT = NT;
     p.tl = g_wg_timeline;
     p.stage_bytes = wg_stage_bytes(cinp, NT);
