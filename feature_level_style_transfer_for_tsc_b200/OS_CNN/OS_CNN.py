@@ -68,7 +68,7 @@ def defer_batch_counters(on: bool):
     return got
 
 
-def _bn_layer_spec(geom, bn, relu, zero_masked=True):
+def _bn_layer_spec(geom, bn, relu, zero_masked=True, dense_wgrad=False):
     """LayerSpec for one conv+BN pair; advances ``num_batches_tracked`` like nn.BatchNorm1d.forward."""
     use_batch_stats = bn.training or bn.running_mean is None
     momentum = 0.0
@@ -79,7 +79,8 @@ def _bn_layer_spec(geom, bn, relu, zero_masked=True):
             bn.num_batches_tracked.add_(1)
         momentum = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked.item())
     return LayerSpec(geom=geom, relu=relu, training=use_batch_stats, momentum=float(momentum), eps=float(bn.eps),
-                     running_mean=bn.running_mean, running_var=bn.running_var, zero_masked=zero_masked)
+                     running_mean=bn.running_mean, running_var=bn.running_var, zero_masked=zero_masked,
+                     dense_wgrad=bool(dense_wgrad))
 
 
 def _bn_params(conv, bn):
@@ -91,7 +92,8 @@ def _bn_params(conv, bn):
 def _run_stack(layers, x, shortcut=None, final_relu=False, pooled=False):
     specs, params = [], []
     for layer in layers:
-        specs.append(_bn_layer_spec(layer.geometry, layer.bn, layer.relu_or_not_at_last_layer))
+        specs.append(_bn_layer_spec(layer.geometry, layer.bn, layer.relu_or_not_at_last_layer,
+                                    dense_wgrad=getattr(layer, "dense_wgrad", False)))
         params += _bn_params(layer.conv1d, layer.bn)
     sc_spec = None
     if shortcut is not None:
@@ -111,7 +113,13 @@ def _run_stack(layers, x, shortcut=None, final_relu=False, pooled=False):
 
 class build_layer_with_layer_parameter(nn.Module):
     """One OS layer: mask*W -> zero pad -> Conv1d(Cin, sum Cout, Kmax) -> BatchNorm1d -> optional ReLU
-    (reference lines 46-77)."""
+    (reference lines 46-77).
+
+    ``dense_wgrad`` (beyond the reference surface; default from ``TSC_DENSE_WGRAD``, off): when true this layer's
+    ``conv1d.weight.grad`` is the reference's unmasked gradient (non-zero on masked taps) instead of
+    ``grad * mask``; ``functional.dense_wgrad()`` switches it per backward call."""
+
+    dense_wgrad = os.environ.get("TSC_DENSE_WGRAD", "0") == "1"
 
     def __init__(self, layer_parameters, relu_or_not_at_last_layer=True, with_nvidia=True):
         super(build_layer_with_layer_parameter, self).__init__()

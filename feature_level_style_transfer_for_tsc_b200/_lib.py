@@ -73,6 +73,14 @@ class BNBwdBranch(ctypes.Structure):
 
 
 _bp, _bbp = ctypes.POINTER(BNBranch), ctypes.POINTER(BNBwdBranch)
+MAX_LIST, MAX_CLASSES, MAX_VOTERS = 32, 64, 8
+
+
+class TensorList(ctypes.Structure):
+    """tsc_tensor_list"""
+    _fields_ = [("p", ctypes.c_void_p * MAX_LIST), ("n", ctypes.c_longlong * MAX_LIST), ("count", ctypes.c_int),
+                ("pad_", ctypes.c_int)]
+
 
 # name -> (restype, argtypes); must list every symbol declared in include/tsc_b200.h
 SIGNATURES = {
@@ -116,6 +124,10 @@ SIGNATURES = {
     "tsc_cdan_fuse_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p]),
     "tsc_cdan_distance_fwd": (_i, [_p, _p, _p, _p, _i, _p]),
     "tsc_cdan_distance_bwd": (_i, [_p, _p, _p, _p, _i, _p]),
+    "tsc_multi_l2norm_workspace_bytes": (_sz, [_i]),
+    "tsc_multi_l2norm": (_i, [ctypes.POINTER(TensorList), _p, _p, _p]),
+    "tsc_class_precision": (_i, [_p, _p, _p, _p, _p, _i, _i, _p]),
+    "tsc_entropy_vote": (_i, [_p, _p, _p, _p, _i, _i, _i, _f, _f, _p]),
     "tsc_debug_read_and_clear_watchdog": (_i, [_ip]),
     "tsc_debug_set_timeline": (_i, [_p]),
 }

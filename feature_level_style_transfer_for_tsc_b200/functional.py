@@ -35,6 +35,7 @@ class LayerSpec:
     running_mean: Optional[torch.Tensor]
     running_var: Optional[torch.Tensor]
     zero_masked: bool = True
+    dense_wgrad: bool = False   # weight gradient over ALL taps (the reference's unmasked ``.grad``) instead of grad*mask
 
 
 @dataclass
@@ -69,6 +70,35 @@ def set_direct_grads(on: bool) -> None:
 
 def direct_grads() -> bool:
     return _DIRECT_GRADS
+
+
+_DENSE_WGRAD = False
+
+
+class dense_wgrad:
+    """Context manager / switch: while on, every ``os_stack`` backward returns the weight gradient of the *unmasked* big
+    Conv1d -- non-zero on the masked taps, exactly what the reference's autograd produces (OS_CNN.py:68-71) --
+    instead of ``grad * mask``.  GradNorm needs it: its per-loss norms ``torch.norm(w_i * g)`` run over the whole
+    ``.grad`` tensors of ``return_last_layer().parameters()`` (train_and_test.py:683-690).  Read at *backward* time, so
+    ``with dense_wgrad(): torch.autograd.grad(loss_i, block.parameters(), retain_graph=True)`` works on a graph that was
+    built outside the context.  Costs the dense/live ratio of the bank (2.2x for cfg2's 72->228 layer) in the wgrad kernel."""
+
+    def __init__(self, on: bool = True):
+        self.on = bool(on)
+
+    def __enter__(self):
+        global _DENSE_WGRAD
+        self.prev, _DENSE_WGRAD = _DENSE_WGRAD, self.on
+        return self
+
+    def __exit__(self, *exc):
+        global _DENSE_WGRAD
+        _DENSE_WGRAD = self.prev
+        return False
+
+
+def _wgrad_geom(ls: "LayerSpec"):
+    return ls.geom.dense_twin() if (ls.dense_wgrad or _DENSE_WGRAD) else ls.geom
 
 
 _AUX_STREAMS = {}
@@ -196,7 +226,7 @@ def _fused_backward(spec: StackSpec, sv: "_Saved", params, dout: torch.Tensor, x
         d = ops.bn_bwd_top(dout, a_top, b_top, spec.final_relu)
         b_top.dgamma, b_top.dbeta, b_top.dbias = param_grad_targets(4 * nl, sc.geom.cout, sc.training)
         dy_r = ops.bn_bwd_apply_fused(d, b_top, S_top, sc.geom.cout, dt, direct)
-        wgrad(4 * nl, sc.geom, dy_r, sv.x_ops[0])
+        wgrad(4 * nl, _wgrad_geom(sc), dy_r, sv.x_ops[0])
         if x_requires_grad:
             dx_short = ops.osconv(eng, L.DIR_DGRAD, sc.geom, dy_r, sv.wd_r, None)
     elif spec.pooled:
@@ -210,7 +240,7 @@ def _fused_backward(spec: StackSpec, sv: "_Saved", params, dout: torch.Tensor, x
         g = ls.geom
         cur.dgamma, cur.dbeta, cur.dbias = param_grad_targets(4 * i, g.cout, ls.training)
         dy = ops.bn_bwd_apply_fused(d, cur, n_part, g.cout, dt, direct)
-        wgrad(4 * i, g, dy, sv.x_ops[i])
+        wgrad(4 * i, _wgrad_geom(ls), dy, sv.x_ops[i])
         if i > 0:
             below = spec.layers[i - 1]
             co = sv.coeffs[i - 1]
@@ -321,7 +351,7 @@ class OSStackFunction(torch.autograd.Function):
             grads[4 * nl + 2] = s2[:C]
             grads[4 * nl + 3] = s1[:C]
             grads[4 * nl + 1] = zero_bias[:C] if sc.training else (gr * sv.co_r.invstd[:C] * s1[:C])
-            grads[4 * nl + 0] = ops.oswgrad(spec.wgrad_engine, sc.geom, dy_r, sv.x_ops[0])
+            grads[4 * nl + 0] = ops.oswgrad(spec.wgrad_engine, _wgrad_geom(sc), dy_r, sv.x_ops[0])
             if ctx.x_requires_grad:
                 dx_short = ops.osconv(eng, L.DIR_DGRAD, sc.geom, dy_r, sv.wd_r, None)
         else:
@@ -343,7 +373,7 @@ class OSStackFunction(torch.autograd.Function):
             grads[4 * i + 3] = s1[:C]
             # d(bias) = sum dY: identically 0 behind a train-mode BN, gamma*invstd*S1 behind an eval-mode BN
             grads[4 * i + 1] = zero_bias[:C] if ls.training else (gamma * co.invstd[:C] * s1[:C])
-            grads[4 * i + 0] = ops.oswgrad(spec.wgrad_engine, g, dy, sv.x_ops[i])
+            grads[4 * i + 0] = ops.oswgrad(spec.wgrad_engine, _wgrad_geom(ls), dy, sv.x_ops[i])
             if i > 0 or ctx.x_requires_grad:
                 dz = ops.osconv(eng, L.DIR_DGRAD, g, dy, sv.wd[i], None)
         dx = None

@@ -125,6 +125,13 @@ class BankGeometry:
             self._plans[key] = host.to(device)
         return self._plans[key]
 
+    def dense_twin(self) -> "BankGeometry":
+        """The same bank with every tap live for every channel: the geometry of the reference's *unmasked* weight gradient
+        (``W.grad`` of the big Conv1d is dense, OS_CNN.py:68-71 -- SURVEY F4), used when ``dense_wgrad`` is on."""
+        if getattr(self, "_dense", None) is None:
+            self._dense = self if all(v == 0 for v in self.s_of_tap) else dense_geometry(self.cin, self.cout, self.kmax)
+        return self._dense
+
     def live_macs_per_position(self) -> int:
         return self.cin * sum(h - l for l, h in zip(self.lo, self.hi))
 
@@ -582,6 +589,54 @@ def cdan_distance_bwd(dloss, saved, B: int):
     L.check(L.load().tsc_cdan_distance_bwd(_ptr(dloss), _ptr(saved), _ptr(du), _ptr(dcritic), B, _stream()),
             "tsc_cdan_distance_bwd")
     return du, dcritic
+
+
+def multi_l2norm(tensors: Sequence[torch.Tensor]) -> torch.Tensor:
+    """[||t_0||, ..., ||t_{n-1}||, sum of them] (fp32, device) for up to L.MAX_LIST fp32 CUDA tensors, two launches."""
+    if not 1 <= len(tensors) <= L.MAX_LIST:
+        raise RuntimeError(f"multi_l2norm takes 1..{L.MAX_LIST} tensors, got {len(tensors)}")
+    lst = L.TensorList()
+    lst.count = len(tensors)
+    keep = []
+    for i, t in enumerate(tensors):
+        t = _req(t.detach(), name=f"tensor {i}") if t.is_contiguous() else _req(t.detach().contiguous(), name=f"tensor {i}")
+        keep.append(t)
+        lst.p[i], lst.n[i] = t.data_ptr(), t.numel()
+    dev = keep[0].device
+    norms = torch.empty(len(tensors) + 1, device=dev, dtype=torch.float32)
+    ws = torch.empty(int(L.load().tsc_multi_l2norm_workspace_bytes(len(tensors))) // 4 + 4, device=dev, dtype=torch.float32)
+    L.check(L.load().tsc_multi_l2norm(ctypes.byref(lst), _ptr(norms), _ptr(ws), _stream()), "tsc_multi_l2norm")
+    return norms
+
+
+def class_precision(logits: torch.Tensor, labels: Optional[torch.Tensor] = None):
+    """(pred [N] int32, counts [2, K] int32, precision [K] fp64) of multi_source_voting.py:296-311."""
+    _req(logits, name="logits")
+    N, K = logits.shape
+    if labels is not None:
+        _req(labels, torch.int64, "labels")
+        if labels.numel() != N:
+            raise RuntimeError(f"{labels.numel()} labels for {N} rows")
+    pred = torch.empty(N, device=logits.device, dtype=torch.int32)
+    counts = torch.empty((2, K), device=logits.device, dtype=torch.int32)
+    prec = torch.empty(K, device=logits.device, dtype=torch.float64)
+    L.check(L.load().tsc_class_precision(_ptr(logits), _ptr(labels), _ptr(pred), _ptr(counts), _ptr(prec), N, K, _stream()),
+            "tsc_class_precision")
+    return pred, counts, prec
+
+
+def entropy_vote(logits: torch.Tensor, precision: torch.Tensor, entropy_gain: float = 120.0, weight_base: float = 9.0):
+    """logits [M, N, K] fp32, precision [M, K] fp64 -> (score [N, K] fp32, pred [N] int32); multi_source_voting.py:357-407."""
+    _req(logits, name="logits")
+    _req(precision, torch.float64, "precision")
+    M, N, K = logits.shape
+    if tuple(precision.shape) != (M, K):
+        raise RuntimeError(f"precision {tuple(precision.shape)} != {(M, K)}")
+    score = torch.empty((N, K), device=logits.device, dtype=torch.float32)
+    pred = torch.empty(N, device=logits.device, dtype=torch.int32)
+    L.check(L.load().tsc_entropy_vote(_ptr(logits), _ptr(precision), _ptr(score), _ptr(pred), M, N, K, float(entropy_gain),
+                                      float(weight_base), _stream()), "tsc_entropy_vote")
+    return score, pred
 
 
 def read_watchdog() -> int:

@@ -38,6 +38,9 @@ extern "C" {
 #define TSC_MAX_TAPS 96          /* largest supported Kmax (reference caps it at 89, train_and_test.py:40) */
 #define TSC_MAX_CHANNELS 256     /* largest padded channel count of one OS layer (reference: <= 228) */
 #define TSC_MAX_OPT_GROUPS 32    /* parameter groups of one tsc_rmsprop_step call */
+#define TSC_MAX_LIST 32          /* tensors of one tsc_multi_l2norm call */
+#define TSC_MAX_CLASSES 64       /* classes of the voting kernels */
+#define TSC_MAX_VOTERS 8         /* models of one tsc_entropy_vote call */
 
 typedef void* tsc_stream_t;      /* cudaStream_t */
 
@@ -265,6 +268,31 @@ int tsc_rmsprop_step(float* params, const float* grads, float* square_avg, long 
 int tsc_rmsprop_step_clamped(float* params, const float* grads, float* square_avg, long long n,
                              const long long* group_end, const float* group_lr, const float* group_clamp, int ngroups,
                              float alpha, float eps, float grad_scale, tsc_stream_t stream);
+
+/* ---- callers either side of the path --------------------------------------------------------
+ * GradNorm (train_and_test.py:683-690): per loss, sum over the shared block's parameter tensors of
+ * torch.norm(w_i * g_p) = |w_i| * ||g_p||.  tsc_multi_l2norm writes norms[i] = ||tensor i||_2 for i < count and
+ * norms[count] = their sum (fixed summation order, no float atomics); workspace from the query function. */
+typedef struct tsc_tensor_list {
+    const float* p[TSC_MAX_LIST];  /* device pointers, fp32, 4-byte aligned (16-byte aligned tensors take the vector path) */
+    long long n[TSC_MAX_LIST];     /* elements */
+    int count;
+    int pad_;
+} tsc_tensor_list;
+size_t tsc_multi_l2norm_workspace_bytes(int count);
+int tsc_multi_l2norm(const tsc_tensor_list* list, float* norms, float* workspace, tsc_stream_t stream);
+/* Multi-source voting (multi_source_voting.py:281-311 and the accuracy of utils.py:27-183).
+ * logits [N,K] fp32, labels [N] int64 (or NULL) -> pred [N] int32 (first maximum, numpy.argmax; nullable),
+ * counts [2K] int32 = (#predicted as k, #predicted as k and labelled k), precision [K] fp64 = correct / predicted,
+ * 0 for a class never predicted (nullable). */
+int tsc_class_precision(const float* logits, const long long* labels, int* pred, int* counts, double* precision,
+                        int N, int K, tsc_stream_t stream);
+/* multi_source_voting.py:357-407: logits [M,N,K] of M models, precision [M,K] from tsc_class_precision on the training
+ * split.  w_m = precision_m / mean_m(precision) (NaN -> 0); per model p = softmax(logits), H = entropy(p),
+ * score += p * (1 + entropy_gain * exp(-H)) * weight_base ^ w_m  (the reference: gain 120, base 9); pred = argmax.
+ * score [N,K] fp32, pred [N] int32. */
+int tsc_entropy_vote(const float* logits, const double* precision, float* score, int* pred, int M, int N, int K,
+                     float entropy_gain, float weight_base, tsc_stream_t stream);
 
 /* ---- debugging aid: the tcgen05 kernels bound every mbarrier wait; a timed-out wait stores a
  * non-zero code here (device word, read back by the caller when it wants to). */

@@ -112,9 +112,123 @@ def make_cdan_golden():
             "iter_num_after": float(ad.iter_num)}
 
 
+def _ref_lines(rel_path, first, last):
+    """Source lines [first, last] (1-based, inclusive) of a reference file, dedented -- executed, never stored."""
+    import textwrap
+    with open(os.path.join(REF, rel_path), encoding="utf-8") as f:
+        lines = f.readlines()
+    return textwrap.dedent("".join(lines[first - 1:last]))
+
+
+def make_voting_golden():
+    """Runs the reference script's own lines (multi_source_voting.py:294-307 per model, 358-367, 406-424) on seeded
+    logits of three models; class 4 is never predicted by any model (the 0/0 -> nan_to_num branch)."""
+    from scipy.stats import entropy
+    from sklearn.metrics import accuracy_score
+    rng = np.random.default_rng(17)
+    K, n_train, n_test = 5, 90, 61
+    label_list_train = rng.integers(0, K - 1, n_train).astype(np.float64)      # np.concatenate of y.numpy() onto float64
+    label_list = rng.integers(0, K - 1, n_test).astype(np.float64)
+    ns = {"np": np, "entropy": entropy, "accuracy_score": accuracy_score, "target_num_class": K,
+          "label_list_train": label_list_train, "label_list": label_list}
+    out = {"label_list_train": label_list_train, "label_list": label_list}
+    src_prec = _ref_lines("multi_source_voting.py", 294, 307)
+    for m in (1, 2, 3):
+        tr = (rng.standard_normal((n_train, K)) * 2.0).astype(np.float32)
+        tr[np.arange(n_train), label_list_train.astype(int)] += 1.5 * (m / 3.0)     # models of different quality
+        tr[:, K - 1] = -30.0                                                         # never the argmax
+        te = (rng.standard_normal((n_test, K)) * 2.0).astype(np.float32)
+        te[np.arange(n_test), label_list.astype(int)] += 1.0
+        te[:, K - 1] -= 4.0
+        out[f"train_logits{m}"], out[f"test_logits{m}"] = tr.copy(), te.copy()
+        ns[f"results_of_train{m}"] = tr.copy()
+        ns[f"results_of_probs{m}"] = te.copy()
+        exec(src_prec.replace("results_of_train1", f"results_of_train{m}").replace("weight_for_1", f"weight_for_{m}"), ns)
+        out[f"precision{m}"] = np.array(ns[f"weight_for_{m}"], dtype=np.float64)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        exec(_ref_lines("multi_source_voting.py", 358, 367), ns)
+    for m in (1, 2, 3):
+        out[f"weight{m}"] = np.asarray(ns[f"weight_{m}"], dtype=np.float64)
+    exec(_ref_lines("multi_source_voting.py", 406, 424), ns)
+    out["score"] = np.asarray(ns["result_final"])
+    out["predict"] = np.asarray(ns["predict_list"])
+    out["acc"] = np.float64(ns["acc"])
+    np.savez_compressed(os.path.join(OUT, "voting_small.npz"), **out)
+    return out
+
+
+def make_gradnorm_golden():
+    """Executes train_and_test.py:500-511 (GradNorm weights, their Adam optimizers) once and :646-766 (loss stacking,
+    first backward, per-loss norms over return_last_layer().parameters(), weight gradient, graph-clearing second
+    backward, optimizer steps, renormalisation, WGAN clamps) for two consecutive batches over the reference's modules."""
+    ref_os, ref_sb = import_reference()
+    from oracle import os_cnn as O
+    from oracle import grad_norm as GN
+    lpl = ref_sb.generate_layer_parameter_list(1, 7, [216, 2160], 3)           # the "small" bank: widths 20 / 30 / 40
+    cf = O.feature_channels(lpl)
+    lpl_cls = ref_os.layer_parameter_list_input_change(lpl, cf)
+    K, B, C, Ln, style_weight = 4, 6, 3, 32, 1.0e3
+    torch.manual_seed(5)
+    fe_t = ref_os.OS_CNN_res(lpl); cl_t = ref_os.OS_CNN(lpl_cls, K)
+    fe_s = ref_os.OS_CNN_res(lpl); cl_s = ref_os.OS_CNN(lpl_cls, K)
+    mods = (fe_t, cl_t, fe_s, cl_s)
+    names = ("fe_t", "cl_t", "fe_s", "cl_s")
+    out = {}
+    for nm, m in zip(names, mods):
+        m.train()
+        out.update({f"init/{nm}/{k}": v.detach().numpy().copy() for k, v in m.state_dict().items()})
+    ad_net = torch.nn.Linear(4, 3)               # only their parameters are touched (the WGAN clamps, :763-766)
+    feature_discriminator_s = torch.nn.Linear(4, 3)
+    dummy = torch.nn.Parameter(torch.zeros(1))
+    ns = {"torch": torch, "nn": torch.nn, "np": np, "with_nvidia": False,
+          "target_feature_extraction_module": fe_t, "source_feature_extraction_module": fe_s,
+          "ad_net": ad_net, "feature_discriminator_s": feature_discriminator_s,
+          "optimizer_list": [torch.optim.RMSprop(fe_t.parameters(), lr=0.001), torch.optim.RMSprop(cl_t.parameters(), lr=0.003),
+                             torch.optim.RMSprop(fe_s.parameters(), lr=0.001), torch.optim.RMSprop(cl_s.parameters(), lr=0.003)],
+          "optimizer_sl_cpc": torch.optim.Adam([dummy], lr=0.002)}
+    exec(_ref_lines("train_and_test.py", 500, 511), ns)
+    body = _ref_lines("train_and_test.py", 646, 766)
+    g = torch.Generator().manual_seed(23)
+    for b in range(2):
+        xt = torch.randn(B, C, Ln, generator=g); yt = torch.randint(0, K, (B,), generator=g)
+        xs = torch.randn(B, C, Ln, generator=g); ys = torch.randint(0, K, (B,), generator=g)
+        losses = GN.named_losses(mods, xt, yt, xs, ys, style_weight)
+        out.update({f"b{b}/xt": xt.numpy(), f"b{b}/yt": yt.numpy(), f"b{b}/xs": xs.numpy(), f"b{b}/ys": ys.numpy()})
+        out.update({f"b{b}/loss/{k}": np.float64(v.item()) for k, v in losses.items()})
+        out[f"b{b}/weights_t_before"] = ns["weights_grad_norm_t"].detach().numpy().copy()
+        out[f"b{b}/weights_s_before"] = ns["weights_grad_norm_s"].detach().numpy().copy()
+        ns.update(losses)
+        ns["cur_epoch"] = 0
+        exec(body, ns)
+        for side in ("t", "s"):
+            out[f"b{b}/norms_{side}"] = ns[f"norms_{side}_stack"].detach().numpy().copy()
+            out[f"b{b}/target_{side}"] = ns[f"constant_term_{side}"].detach().numpy().copy()
+            out[f"b{b}/grad_w_{side}"] = ns[f"grad_for_weight_{side}"].detach().numpy().copy()
+            out[f"b{b}/weights_{side}_after"] = ns[f"weights_grad_norm_{side}"].detach().numpy().copy()
+            out[f"b{b}/initial_{side}"] = np.asarray(ns[f"initial_loss_{side}"]).copy()
+        for nm, m in zip(names, mods):
+            out.update({f"b{b}/grad/{nm}/{k}": p.grad.detach().numpy().copy() for k, p in m.named_parameters()})
+            # the state every module is in after this batch: RMSprop's first update is sign-like, so rounding-level
+            # gradients (conv biases in front of a BatchNorm) move by O(lr) -- a test of batch b+1 starts from here
+            out.update({f"b{b}/after/{nm}/{k}": v.detach().numpy().copy() for k, v in m.state_dict().items()
+                        if "num_batches" not in k})
+    out["meta"] = np.array(json.dumps({"lpl": lpl, "lpl_cls": lpl_cls, "n_class": K, "B": B, "C": C, "L": Ln,
+                                       "style_weight": style_weight, "seed": 5, "cur_epoch": 0}))
+    np.savez_compressed(os.path.join(OUT, "gradnorm_small.npz"), **out)
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     sys.path.insert(0, os.path.dirname(HERE))
+    if len(sys.argv) > 1 and sys.argv[1] == "--drivers":       # only the 8f-row vectors (leaves the other files untouched)
+        make_voting_golden()
+        make_gradnorm_golden()
+        for fn in ("voting_small.npz", "gradnorm_small.npz"):
+            print(f"  {fn}: {os.path.getsize(os.path.join(OUT, fn))} bytes")
+        return
     ref_os, ref_sb = import_reference()
     from oracle import os_cnn as O
 
@@ -191,6 +305,8 @@ def main():
 
     # ---- C-DAN consumer (C_DAN.py + widgets.AdversarialNetworkforCDAN), small shapes -----------
     tables["cdan_small"] = make_cdan_golden()
+    make_voting_golden()
+    make_gradnorm_golden()
 
     with open(os.path.join(OUT, "tables.json"), "w") as f:
         json.dump(tables, f, indent=1, sort_keys=True)

@@ -189,12 +189,22 @@ def init_classifier(lpl: List[LayerParams], n_class: int) -> "OrderedDict[str, t
 # --------------------------------------------------------------------------------------
 # forward  (OS_CNN/OS_CNN.py:67-77, 101-110, 155-180, 207-217)
 # --------------------------------------------------------------------------------------
+DENSE_WGRAD = False     # True: d/dW as the reference's autograd returns it, see masked_conv
+
+
 def masked_conv(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, layer: LayerParams) -> torch.Tensor:
-    """OS_CNN.py:68-71: W*mask, ConstantPad1d((Kmax-1)//2, Kmax//2), Conv1d."""
+    """OS_CNN.py:68-71: W*mask, ConstantPad1d((Kmax-1)//2, Kmax//2), Conv1d.
+
+    The reference masks ``weight.data`` (outside autograd) and convolves with the parameter itself, so its ``W.grad``
+    is the unmasked dense gradient -- non-zero on masked taps.  By default this restatement differentiates
+    through the mask (``grad * mask``, what the parity tests compare); with ``DENSE_WGRAD`` the value is still
+    ``W * mask`` but the gradient passes straight to ``W``, which is what GradNorm's norms see
+    (train_and_test.py:683-690)."""
     g = bank_geometry(layer)
     mask = torch.from_numpy(build_mask(layer)).to(w.dtype)
     xp = F.pad(x, (g["pad_l"], g["pad_r"]))
-    return F.conv1d(xp, w * mask, b)
+    wm = w + (w * mask - w).detach() if DENSE_WGRAD else w * mask
+    return F.conv1d(xp, wm, b)
 
 
 def batch_norm(y: torch.Tensor, sd: Dict[str, torch.Tensor], prefix: str, training: bool,
