@@ -1,0 +1,245 @@
+"""GPU parity of the 8f rows: the dense weight gradient, the GradNorm joint-stage driver, the evaluation helpers
+and the multi-source vote -- against the vectors the reference's own lines produced (tests/golden/gradnorm_small.npz,
+voting_small.npz) and against the oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, as_lpl, rel_err
+from oracle import grad_norm as GN
+from oracle import os_cnn as O
+from oracle import voting as V
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def T():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import feature_level_style_transfer_for_tsc_b200 as pkg
+    pkg._lib.load()
+    return pkg
+
+
+@pytest.fixture(scope="module")
+def voting():
+    return np.load(os.path.join(GOLDEN, "voting_small.npz"))
+
+
+@pytest.fixture(scope="module")
+def gradnorm():
+    return np.load(os.path.join(GOLDEN, "gradnorm_small.npz"))
+
+
+def test_multi_l2norm_matches_torch(T):
+    g = torch.Generator(device="cuda").manual_seed(3)
+    big = torch.randn(1 << 20, device="cuda", generator=g)
+    tensors = [torch.randn(228, 72, 31, device="cuda", generator=g), torch.randn(7, device="cuda", generator=g),
+               big[1:1001],                                         # 4-byte aligned only: the scalar path
+               torch.zeros(5, device="cuda"), torch.randn(1, device="cuda", generator=g),
+               torch.randn(144, 3, device="cuda", generator=g).t()]      # non-contiguous: copied by the wrapper
+    out = T.ops.multi_l2norm(tensors).cpu().numpy()
+    ref = np.array([float(torch.linalg.vector_norm(t.double())) for t in tensors])
+    assert out.shape == (len(tensors) + 1,)
+    assert rel_err(out[:-1], ref) < 2e-6
+    assert abs(out[-1] - ref.sum()) < 2e-6 * ref.sum()
+    again = T.ops.multi_l2norm(tensors).cpu().numpy()
+    assert np.array_equal(out, again)                                # fixed summation order
+    with pytest.raises(RuntimeError):
+        T.ops.multi_l2norm([])
+    with pytest.raises(RuntimeError):
+        T.ops.multi_l2norm([torch.zeros(3)])                         # CPU tensor: no fallback
+
+
+def test_class_precision_and_vote_match_the_reference_script(T, voting):
+    K = voting["train_logits1"].shape[1]
+    labels_tr = torch.from_numpy(voting["label_list_train"].astype(np.int64)).cuda()
+    precs = []
+    for m in (1, 2, 3):
+        lg = torch.from_numpy(voting[f"train_logits{m}"]).cuda()
+        pred, counts, prec = T.ops.class_precision(lg, labels_tr)
+        assert np.array_equal(pred.cpu().numpy(), np.argmax(voting[f"train_logits{m}"], axis=1))      # bit-exact argmax
+        assert np.array_equal(prec.cpu().numpy(), voting[f"precision{m}"])                              # bit-exact (ints, one division)
+        assert int(counts[0].sum()) == lg.shape[0]
+        precs.append(prec)
+    tests = [torch.from_numpy(voting[f"test_logits{m}"]).cuda() for m in (1, 2, 3)]
+    from feature_level_style_transfer_for_tsc_b200 import multi_source_voting as MV
+    score, pred = MV.entropy_vote(tests, precs)
+    assert rel_err(score.cpu(), voting["score"]) < 1e-5             # fp32 softmax / entropy: expf, logf vs numpy's
+    assert np.array_equal(pred.cpu().numpy(), voting["predict"])
+    labels_te = torch.from_numpy(voting["label_list"].astype(np.int64)).cuda()
+    _, counts, _ = T.ops.class_precision(score, labels_te)
+    assert int(counts[1].sum()) / labels_te.numel() == float(voting["acc"])
+    # ties: the first maximum wins, as numpy.argmax
+    tie = torch.tensor([[1.0, 3.0, 3.0], [2.0, 2.0, 1.0]], device="cuda")
+    assert T.ops.class_precision(tie)[0].tolist() == [1, 0]
+    with pytest.raises(RuntimeError):
+        T.ops.class_precision(torch.zeros(4, 65, device="cuda"))     # more classes than the kernel supports
+
+
+def build_gradnorm_modules(T, gradnorm, meta, state="init", b=None):
+    from feature_level_style_transfer_for_tsc_b200.OS_CNN.OS_CNN import OS_CNN, OS_CNN_res
+    lpl, lpl_c = as_lpl(meta["lpl"]), as_lpl(meta["lpl_cls"])
+    torch.manual_seed(meta["seed"])
+    fe_t = OS_CNN_res(lpl); cl_t = OS_CNN(lpl_c, meta["n_class"])
+    fe_s = OS_CNN_res(lpl); cl_s = OS_CNN(lpl_c, meta["n_class"])
+    mods = (fe_t, cl_t, fe_s, cl_s)
+    for nm, m in zip(("fe_t", "cl_t", "fe_s", "cl_s"), mods):
+        for k, v in m.state_dict().items():
+            if "num_batches" not in k:
+                assert np.array_equal(v.numpy(), gradnorm[f"init/{nm}/{k}"]), (nm, k)      # same seed, same RNG stream (A5)
+        m.cuda().train()
+    return mods
+
+
+def sync_state(mods, gradnorm, b):
+    with torch.no_grad():
+        for nm, m in zip(("fe_t", "cl_t", "fe_s", "cl_s"), mods):
+            for k, v in m.state_dict().items():
+                if "num_batches" not in k:
+                    v.copy_(torch.from_numpy(gradnorm[f"b{b}/after/{nm}/{k}"]))
+
+
+# fp32 engine: the arithmetic is pinned tightly.  bf16 tensor-core engine: the balanced losses include a Gram style loss (a
+# difference of nearly equal Gram matrices, x 1e3) and gradients that pass a BatchNorm backward behind an average pool
+# (one bf16 ulp is amplified ~100x), so only aggregate bounds are meaningful there; every kernel involved is
+# checked op-level on identical inputs in tests/test_gpu_kernels.py.
+@pytest.mark.parametrize("engine,tol_norm,tol_grad,tol_w", [("simt", 2e-4, 1e-3, 1e-5), ("tcgen05", 0.15, 0.3, 1e-4)])
+def test_gradnorm_joint_stage_driver(T, gradnorm, engine, tol_norm, tol_grad, tol_w):
+    """Two consecutive batches of train_and_test.py:646-766 on the CUDA modules: per-loss norms over the last block (dense
+    weight gradients), GradNorm targets, weight gradients, balanced weights after Adam + renormalisation, and the
+    parameter gradients the optimizers see (= grad(total) + grad(remainder))."""
+    from feature_level_style_transfer_for_tsc_b200 import grad_norm as D
+    from feature_level_style_transfer_for_tsc_b200 import functional as TF
+    T.set_engine(engine)
+    meta = json.loads(str(gradnorm["meta"]))
+    mods = build_gradnorm_modules(T, gradnorm, meta)
+    names = ("fe_t", "cl_t", "fe_s", "cl_s")
+    opts = [torch.optim.RMSprop(m.parameters(), lr=lr) for m, lr in zip(mods, (0.001, 0.003, 0.001, 0.003))]
+    critic = torch.nn.Linear(4, 3).cuda()
+    drv = D.JointStageDriver(mods[0].return_last_layer(), mods[2].return_last_layer(), opts, clamps=[(critic, 0.0005)])
+    masks = {i: O.build_mask(as_lpl(meta["lpl"])[i]) for i in range(3)}
+    for b in range(2):
+        if b > 0:
+            sync_state(mods, gradnorm, b - 1)         # see tests/test_oracle_drivers.py: RMSprop's first step is sign-like
+        xt, yt = torch.from_numpy(gradnorm[f"b{b}/xt"]).cuda(), torch.from_numpy(gradnorm[f"b{b}/yt"]).cuda()
+        xs, ys = torch.from_numpy(gradnorm[f"b{b}/xs"]).cuda(), torch.from_numpy(gradnorm[f"b{b}/ys"]).cuda()
+        assert rel_err(drv.t.weights.detach().cpu(), gradnorm[f"b{b}/weights_t_before"]) < 1e-5
+        losses = GN.named_losses(mods, xt, yt, xs, ys, meta["style_weight"], adain=TF.adain, gram_style_loss=TF.gram_style_loss)
+        for k, v in losses.items():
+            ref = float(gradnorm[f"b{b}/loss/{k}"])
+            assert abs(float(v.detach()) - ref) < tol_norm * max(0.05, abs(ref)), k
+        info = drv.step(losses, meta["cur_epoch"])
+        torch.cuda.synchronize()
+        assert T.ops.read_watchdog() == 0
+        for side in ("t", "s"):
+            assert rel_err(info[f"norms_{side}"], gradnorm[f"b{b}/norms_{side}"]) < tol_norm, (b, side)
+            assert rel_err(info[f"target_{side}"], gradnorm[f"b{b}/target_{side}"]) < tol_norm, (b, side)
+            assert rel_err(info[f"grad_w_{side}"], gradnorm[f"b{b}/grad_w_{side}"]) < tol_norm, (b, side)
+            w = getattr(drv, side).weights.detach().cpu().numpy()
+            assert rel_err(w, gradnorm[f"b{b}/weights_{side}_after"]) < tol_w, (b, side)
+            assert abs(w.sum() - (7.0 if side == "t" else 8.0)) < 1e-5
+        assert rel_err(drv.t.initial, gradnorm[f"b{b}/initial_t"]) < tol_norm
+        # what the optimizers saw: the main backward runs with masked gradients (grad * mask, exact zeros elsewhere)
+        for nm, m in zip(names, mods):
+            for k, p in m.named_parameters():
+                ref = gradnorm[f"b{b}/grad/{nm}/{k}"]
+                g = p.grad.cpu().numpy()
+                if k.endswith("conv1d.weight") and "res" not in k:
+                    i = int(k.split(".conv1d")[0].split(".")[-1])
+                    mask = masks[i] if nm.startswith("fe") else O.build_mask(as_lpl(meta["lpl_cls"])[i])
+                    assert np.abs(g * (1 - mask)).max() == 0.0
+                    ref = ref * mask
+                if k.endswith("conv1d.bias"):
+                    continue                                          # ~0 behind a BatchNorm (rounding noise in the reference)
+                err = np.linalg.norm((g - ref).ravel()) / max(np.linalg.norm(ref.ravel()), 1e-12)
+                assert err < tol_grad or np.abs(ref).max() < 1e-6, (b, nm, k, err)
+        assert float(critic.weight.abs().max()) <= 0.0005 + 1e-9      # WGAN clamp (:763-766)
+
+
+@pytest.mark.parametrize("engine,tol", [("simt", 3e-4), ("tcgen05", 0.1)])
+def test_dense_wgrad_reproduces_the_reference_masked_tap_gradients(T, gradnorm, engine, tol):
+    """F4: with dense_wgrad the kernel-bank gradient equals the reference's autograd result on EVERY tap."""
+    from feature_level_style_transfer_for_tsc_b200 import functional as TF
+    T.set_engine(engine)
+    meta = json.loads(str(gradnorm["meta"]))
+    mods = build_gradnorm_modules(T, gradnorm, meta)
+    xt, yt = torch.from_numpy(gradnorm["b0/xt"]).cuda(), torch.from_numpy(gradnorm["b0/yt"]).cuda()
+    xs, ys = torch.from_numpy(gradnorm["b0/xs"]).cuda(), torch.from_numpy(gradnorm["b0/ys"]).cuda()
+    losses = GN.named_losses(mods, xt, yt, xs, ys, meta["style_weight"], adain=TF.adain, gram_style_loss=TF.gram_style_loss)
+    c = GN.remainder_coefficients(0)
+    remainder = sum(ci * losses[k] for ci, k in zip(c, GN.REMAINDER))
+    total = (2 * losses["target_nf_loss"] + 5 * losses["target_classification_loss"] + 2 * losses["source_nf_loss"]
+             + 2 * losses["source_classification_loss"] + 4 * losses["s2t2s_classification_loss"] + 2 * remainder)
+    block = mods[0].return_last_layer()
+    with TF.dense_wgrad():
+        grads = torch.autograd.grad(total, list(block.parameters()), retain_graph=True)
+    for (k, _), g in zip(block.named_parameters(), grads):
+        ref = gradnorm[f"b0/grad/fe_t/net_1.net.{k}"]
+        if k.endswith("conv1d.bias"):
+            continue
+        err = np.linalg.norm((g.cpu().numpy() - ref).ravel()) / np.linalg.norm(ref.ravel())
+        assert err < tol * 3, (k, err)
+        if k.endswith("conv1d.weight"):
+            i = int(k.split(".")[1])
+            mask = O.build_mask(as_lpl(meta["lpl"])[i])
+            off = (1 - mask).astype(bool)
+            if off.any():
+                ref_off = ref[off]
+                assert np.abs(ref_off).max() > 1e-5                    # the reference's "garbage" is really there
+                e2 = np.linalg.norm(g.cpu().numpy()[off] - ref_off) / np.linalg.norm(ref_off)
+                assert e2 < tol * 3, (k, e2)
+    # without the switch the same graph gives exact zeros on the masked taps
+    grads0 = torch.autograd.grad(total, list(block.parameters()))
+    for (k, _), g in zip(block.named_parameters(), grads0):
+        if k.endswith("conv1d.weight"):
+            mask = O.build_mask(as_lpl(meta["lpl"])[int(k.split(".")[1])])
+            assert np.abs(g.cpu().numpy() * (1 - mask)).max() == 0.0
+
+
+def test_eval_helpers_and_vote_end_to_end(T, tables, small_pair, tmp_path, monkeypatch):
+    """utils.eval_* and multi_source_voting.vote over the CUDA modules in eval mode: the logits are the golden eval logits of
+    the reference modules, the vote equals the oracle's vote over the same logits."""
+    from feature_level_style_transfer_for_tsc_b200 import multi_source_voting as MV
+    from feature_level_style_transfer_for_tsc_b200 import utils as U
+    from feature_level_style_transfer_for_tsc_b200.OS_CNN.OS_CNN import OS_CNN, OS_CNN_res
+    T.set_engine("simt")
+    monkeypatch.chdir(tmp_path)
+    meta = tables["small"]
+    lpl_e, lpl_c = as_lpl(meta["lpl_ext"]), as_lpl(meta["lpl_cls"])
+    out = small_pair["out"]
+    chains = []
+    for j in range(3):
+        torch.manual_seed(meta["seed"] + j)
+        fe, cl = OS_CNN_res(lpl_e).cuda().eval(), OS_CNN(lpl_c, meta["n_class"]).cuda().eval()
+        chains.append([fe, cl])
+    x, y = torch.from_numpy(out["x"]), torch.from_numpy(out["y"])
+    loader = [(x[:4], y[:4]), (x[4:], y[4:])]                          # ragged last batch
+    # model 0 = the golden model in its *initial* state: eval BN with fresh running statistics
+    lg0, lab = MV.collect_logits(chains[0], loader)
+    sd_fe = {k: torch.from_numpy(v.copy()) for k, v in small_pair["init_fe"].items()}
+    sd_cl = {k: torch.from_numpy(v.copy()) for k, v in small_pair["init_cl"].items()}
+    ref_lg = O.classifier_forward(sd_cl, lpl_c, O.extractor_forward(sd_fe, lpl_e, x, training=False), training=False)[0]
+    assert rel_err(lg0.cpu(), ref_lg.detach()) < 2e-4
+    assert np.array_equal(lab.cpu().numpy(), out["y"])
+    acc = U.eval_model_testdata(chains[0][0], chains[0][1], loader, 3)
+    assert acc == V.accuracy(lg0.cpu().numpy(), out["y"])
+    assert "epoch_num:3 accuracy_for_test:" in open("numpy_saved_with_accuracy/the_log.txt").read()
+    assert U.eval_target_model_being_pretrained(chains[0][0], chains[0][1], loader, 0, whether_test=True) == acc
+    with pytest.raises(RuntimeError):
+        U.loader_accuracy(chains[0], loader, with_nvidia=False)
+    pred, acc_v, score = MV.vote(chains, loader, loader)
+    logits = [MV.collect_logits(c, loader)[0].cpu().numpy() for c in chains]
+    precs = [V.class_precision(l, out["y"], meta["n_class"]) for l in logits]
+    ref_score, ref_pred = V.entropy_vote(logits, V.normalized_weights(precs))
+    assert rel_err(score.cpu(), ref_score) < 1e-5
+    assert np.array_equal(pred.cpu().numpy(), ref_pred)
+    assert acc_v == float(np.mean(ref_pred == out["y"]))
+    U.save_target_classification_modules(chains[0][0], chains[0][1], 2)
+    ck = torch.load("train_log/epoch_2.tar")
+    assert set(ck) == {"epoch", "feature_extraction_state_dict", "classification_state_dict"}
+    assert list(ck["feature_extraction_state_dict"].keys()) == list(small_pair["init_fe"].keys())
