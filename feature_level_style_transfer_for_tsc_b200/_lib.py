@@ -39,7 +39,10 @@ class ConvEpilogue(ctypes.Structure):
     """tsc_conv_epilogue of include/tsc_b200.h (device pointers; all nullable)."""
     _fields_ = [("stat_partial", ctypes.c_void_p), ("mask_y", ctypes.c_void_p), ("mask_scale", ctypes.c_void_p),
                 ("mask_shift", ctypes.c_void_p), ("mask_mean", ctypes.c_void_p), ("mask_invstd", ctypes.c_void_p),
-                ("red_partial", ctypes.c_void_p)]
+                ("red_partial", ctypes.c_void_p), ("affine_scale", ctypes.c_void_p), ("affine_shift", ctypes.c_void_p),
+                ("residual", ctypes.c_void_p), ("affine_out", ctypes.c_void_p), ("affine_out_kind", ctypes.c_int),
+                ("affine_relu", ctypes.c_int), ("bn_gamma", ctypes.c_void_p), ("bn_beta", ctypes.c_void_p),
+                ("bn_mean", ctypes.c_void_p), ("bn_var", ctypes.c_void_p), ("bn_eps", ctypes.c_float)]
 
 
 _ep = ctypes.POINTER(ConvEpilogue)

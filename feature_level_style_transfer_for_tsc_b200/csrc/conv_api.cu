@@ -39,11 +39,11 @@ int tsc_osconv(int engine, int direction, const void* x, int dtype, const void* 
                float* y, const tsc_conv_epilogue* epilogue, int B, int L, int Cin, int Cout, int Kmax,
                const int* s_of_tap, tsc_stream_t stream) {
     using namespace tsc;
-    TSC_REQUIRE(x && w && y, "NULL tensor");
+    TSC_REQUIRE(x && w && (y || (epilogue && epilogue->affine_out && direction == TSC_DIR_FWD)), "NULL tensor");
     TSC_REQUIRE(B > 0 && L > 0, "bad shape B=%d L=%d", B, L);
     TSC_REQUIRE(dtype == TSC_F32 || dtype == TSC_BF16, "bad dtype %d", dtype);
     if (engine == TSC_ENGINE_SIMT) {
-        TSC_REQUIRE(!epilogue || (!epilogue->stat_partial && !epilogue->red_partial),
+        TSC_REQUIRE(!epilogue || (!epilogue->stat_partial && !epilogue->red_partial && !epilogue->affine_out),
                     "fused epilogues exist on the tcgen05 engine only");
         return osconv_simt(direction, x, dtype, w, bias, y, B, L, Cin, Cout, Kmax, s_of_tap, (cudaStream_t)stream);
     }

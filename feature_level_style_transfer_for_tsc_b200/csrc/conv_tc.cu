@@ -52,6 +52,13 @@ struct ConvTcParams {
     const float* mask_mean;    //        yhat = (y - mean) * invstd
     const float* mask_invstd;
     float* red_partial;        // DGRAD: [n_cta][np] float2 (S1, S2) partial sums over the CTA's valid rows
+    // FWD, inference: z = act(aff_scale * (acc + bias) + aff_shift [+ aff_res]) written to aff_out (kind aff_kind) instead of y
+    const float* aff_scale;    //        ready-made coefficients, or NULL: derived in the prologue from the BatchNorm tensors below
+    const float* aff_shift;
+    const float* bn_gamma; const float* bn_beta; const float* bn_mean; const float* bn_var; float bn_eps;
+    const float* aff_res;      //        c8 fp32 [B][np/8][L][8] added before the activation (the shortcut branch), or NULL
+    void* aff_out;
+    int aff_kind, aff_relu;
     int nbias, B, L, ltiles;
     int np;
     int Rp;            // halo rows in shared memory (multiple of 8)
@@ -119,7 +126,10 @@ __device__ __forceinline__ float warp_colsum32(float* v, int lane) {
     return v[0];
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// AFF: the inference instantiation (eval-mode BatchNorm folded into the epilogue).  A separate instantiation so that the
+// training kernel keeps its register budget (125 per thread: two CTAs of different launches share an SM).
+template <bool AFF>
+__global__ void __launch_bounds__(TC_THREADS, AFF ? 2 : 1)
 osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const ConvTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);            // [8]
@@ -169,6 +179,20 @@ osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const ConvTcParams p)
                 bias_s[3 * np + c] = __ldg(p.mask_invstd + c);
             } else {
                 bias_s[c] = (p.bias && c < p.nbias) ? __ldg(p.bias + c) : 0.f;
+                if (AFF) {
+                    if (p.aff_scale) {
+                        bias_s[np + c] = __ldg(p.aff_scale + c);
+                        bias_s[2 * np + c] = __ldg(p.aff_shift + c);
+                    } else if (c < p.nbias) {
+                        // eval-mode BatchNorm1d (OS_CNN.py:72 in .eval()): the arithmetic of bn_eval_coeffs_kernel
+                        const float sc = __ldg(p.bn_gamma + c) * (1.f / sqrtf(__ldg(p.bn_var + c) + p.bn_eps));
+                        bias_s[np + c] = sc;
+                        bias_s[2 * np + c] = __ldg(p.bn_beta + c) - __ldg(p.bn_mean + c) * sc;
+                    } else {
+                        bias_s[np + c] = 0.f;
+                        bias_s[2 * np + c] = 0.f;
+                    }
+                }
             }
         }
     }
@@ -292,6 +316,7 @@ osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const ConvTcParams p)
         float* ybase = p.y + row_off;
         const bool do_stat = p.stat_partial != nullptr;
         const bool do_red = p.red_partial != nullptr;
+        constexpr bool do_aff = AFF;
         const float* mbase = do_red ? p.mask_y + row_off : nullptr;
         // one thread polls the accumulator barrier; the other 127 sleep in a named barrier instead of spinning on
         // mbarrier.try_wait next to the MMA issuer
@@ -350,7 +375,73 @@ osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const ConvTcParams p)
                     }
                 }
             }
-            if (valid) {
+            if (do_aff) {
+                // inference: eval-mode BatchNorm (+ shortcut branch) (+ ReLU) applied to the accumulators; the pre-BN y
+                // never reaches HBM and the next layer's operand is written directly
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    if (g < ng) {
+                        float rv[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) rv[j] = 0.f;
+                        if (p.aff_res && valid) {
+                            const float* src = p.aff_res + row_off + (size_t)((c0 >> 3) + g) * chunk_stride;
+                            const float4 a0 = __ldg(reinterpret_cast<const float4*>(src));
+                            const float4 a1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+                            rv[0] = a0.x; rv[1] = a0.y; rv[2] = a0.z; rv[3] = a0.w; rv[4] = a1.x; rv[5] = a1.y; rv[6] = a1.z; rv[7] = a1.w;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int c = c0 + g * 8 + j;
+                            float z = fmaf(v[g * 8 + j], bias_s[np + c], bias_s[2 * np + c]) + rv[j];
+                            if (p.aff_relu) z = fmaxf(z, 0.f);
+                            v[g * 8 + j] = z;
+                        }
+                    }
+                }
+                if (p.aff_kind == TSC_OUT_C8_BF16) {
+                    __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(p.aff_out) + row_off;
+                    if (valid) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            if (g < ng) {
+                                uint4 raw;
+                                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
+                                *reinterpret_cast<uint4*>(ob + (size_t)((c0 >> 3) + g) * chunk_stride) = raw;
+                            }
+                        }
+                    }
+                } else if (p.aff_kind == TSC_OUT_C8_F32) {
+                    float* of = reinterpret_cast<float*>(p.aff_out) + row_off;
+                    if (valid) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            if (g < ng) {
+                                float* d0 = of + (size_t)((c0 >> 3) + g) * chunk_stride;
+                                *reinterpret_cast<float4*>(d0) = make_float4(v[g * 8], v[g * 8 + 1], v[g * 8 + 2], v[g * 8 + 3]);
+                                *reinterpret_cast<float4*>(d0 + 4) = make_float4(v[g * 8 + 4], v[g * 8 + 5], v[g * 8 + 6], v[g * 8 + 7]);
+                            }
+                        }
+                    }
+                } else if (p.aff_kind == TSC_OUT_NCL_F32) {
+                    // [B][Cout][L]: the 32 lanes of a warp are 32 consecutive positions of one channel (128 B per store)
+                    float* on = reinterpret_cast<float*>(p.aff_out) + (size_t)b * p.nbias * p.L + (valid ? l : 0);
+                    if (valid) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (i < ng * 8 && c0 + i < p.nbias) on[(size_t)(c0 + i) * p.L] = v[i];
+                    }
+                } else {
+                    // TSC_OUT_POOLED (one CTA per sample, L <= 128): column sums over this warp's valid rows
+                    float s1[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) s1[i] = valid ? v[i] : 0.f;
+                    const float a = warp_colsum32(s1, lane);
+                    if (c0 + lane < np) wstat[q * np + c0 + lane] = make_float2(a, 0.f);
+                }
+            } else if (valid && p.y) {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     if (g < ng) {
@@ -391,7 +482,16 @@ osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const ConvTcParams p)
                 if (c0 + lane < np) wstat[q * np + c0 + lane] = make_float2(mean_l, c);
             }
         }
-        if (do_stat || do_red) {
+        if (do_aff && p.aff_kind == TSC_OUT_POOLED) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const float inv_l = 1.f / (float)p.L;
+            for (int c = threadIdx.x - 64; c < p.nbias; c += 128) {
+                float a = 0.f;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) a += wstat[w * np + c].x;
+                reinterpret_cast<float*>(p.aff_out)[(size_t)b * p.nbias + c] = a * inv_l;      // AdaptiveAvgPool1d(1)
+            }
+        } else if (do_stat || do_red) {
             asm volatile("bar.sync 1, 128;" ::: "memory");             // the four epilogue warps
             const int rows_cta = min(128, p.L - l0);
             for (int c = threadIdx.x - 64; c < np; c += 128) {
@@ -587,6 +687,21 @@ int osconv_tc(int direction, const void* x, int dtype, const void* w, const void
     if (epi) {
         if (fwd) {
             p.stat_partial = epi->stat_partial;
+            if (epi->affine_out) {
+                TSC_REQUIRE((epi->affine_scale && epi->affine_shift) || (epi->bn_gamma && epi->bn_beta && epi->bn_mean && epi->bn_var),
+                            "affine epilogue needs (scale, shift) or (gamma, beta, running mean, running var)");
+                TSC_REQUIRE(!epi->stat_partial, "affine epilogue (inference) and BatchNorm statistics (training) exclude each other");
+                TSC_REQUIRE(epi->affine_out_kind == TSC_OUT_C8_BF16 || epi->affine_out_kind == TSC_OUT_C8_F32 ||
+                            epi->affine_out_kind == TSC_OUT_NCL_F32 || epi->affine_out_kind == TSC_OUT_POOLED,
+                            "bad affine_out_kind %d", epi->affine_out_kind);
+                TSC_REQUIRE(epi->affine_out_kind != TSC_OUT_POOLED || L <= 128,
+                            "the pooled inference epilogue needs L <= 128 (one CTA per sample), got %d", L);
+                p.aff_scale = epi->affine_scale; p.aff_shift = epi->affine_scale ? epi->affine_shift : nullptr;
+                p.bn_gamma = epi->bn_gamma; p.bn_beta = epi->bn_beta; p.bn_mean = epi->bn_mean; p.bn_var = epi->bn_var;
+                p.bn_eps = epi->bn_eps;
+                p.aff_res = epi->residual;
+                p.aff_out = epi->affine_out; p.aff_kind = epi->affine_out_kind; p.aff_relu = epi->affine_relu ? 1 : 0;
+            }
         } else if (epi->red_partial) {
             TSC_REQUIRE(epi->mask_y && epi->mask_mean && epi->mask_invstd, "dgrad reduction needs mask_y, mask_mean, mask_invstd");
             TSC_REQUIRE(!epi->mask_scale || epi->mask_shift, "mask_scale needs mask_shift");
@@ -627,11 +742,16 @@ int osconv_tc(int direction, const void* x, int dtype, const void* w, const void
     const int smem = p.off_stages + ns * slot;
     static bool attr_set = false;          // once per process: opt in to the full 227 KB of dynamic shared memory
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(osconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(osconv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(osconv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         attr_set = true;
     }
-    { cudaError_t le = launch_pdl(osconv_tc_kernel, dim3(B * p.ltiles), dim3(TC_THREADS), (size_t)smem, cs, xmap, p); if (le != cudaSuccess) { set_error("osconv launch: %s", cudaGetErrorString(le)); return (int)le; } }
+    {
+        cudaError_t le = p.aff_out ? launch_pdl(osconv_tc_kernel<true>, dim3(B * p.ltiles), dim3(TC_THREADS), (size_t)smem, cs, xmap, p)
+                                   : launch_pdl(osconv_tc_kernel<false>, dim3(B * p.ltiles), dim3(TC_THREADS), (size_t)smem, cs, xmap, p);
+        if (le != cudaSuccess) { set_error("osconv launch: %s", cudaGetErrorString(le)); return (int)le; }
+    }
     TSC_LAUNCH_CHECK();
     return 0;
 }

@@ -167,6 +167,49 @@ def _fused_forward(spec: StackSpec, sv: "_Saved", x: torch.Tensor, params, need_
     return out
 
 
+def _inference_forward(spec: StackSpec, x: torch.Tensor, params):
+    """Forward-only pass with every BatchNorm in eval mode (utils.eval_*, multi_source_voting): the
+    running-statistics affine, the ReLU, the shortcut add and the pooling are the convolution's epilogue, so a stack is
+    ncl_to_c8 + one pack launch + one convolution per layer (which derives the BatchNorm coefficients in its prologue); no
+    pre-BN tensor reaches HBM."""
+    eng, dt = spec.engine, spec.op_dtype
+    B, _, Ln = x.shape
+    nl = len(spec.layers)
+    h = x0 = ops.ncl_to_c8(x, dt)
+    jobs = [(ls.geom, params[4 * i], ls.zero_masked, False) for i, ls in enumerate(spec.layers)]
+    if spec.shortcut is not None:
+        jobs.append((spec.shortcut.geom, params[4 * nl], False, False))
+    packs = ops.pack_weights_multi(jobs, dt)
+
+    def coeffs(ls, k):
+        return (params[k + 2], params[k + 3], ls.running_mean, ls.running_var, ls.eps)
+
+    out = None
+    for i, ls in enumerate(spec.layers):
+        co = coeffs(ls, 4 * i)
+        bias = params[4 * i + 1]
+        wf = packs[i][0]
+        if i < nl - 1:
+            h = ops.osconv(eng, L.DIR_FWD, ls.geom, h, wf, bias, affine=(co, ls.relu, L.OUT_C8_BF16, None))
+        elif spec.shortcut is None:
+            if spec.pooled and Ln > 128:      # the pooled epilogue owns one sample per CTA: longer series take two kernels
+                y = ops.osconv(eng, L.DIR_FWD, ls.geom, h, wf, bias)
+                out = ops.bn_apply_fused(ops.BNLayerFwd(y, None, params[4 * i + 2], params[4 * i + 3], ls.running_mean,
+                                                        ls.running_var, 0.0, ls.eps,
+                                                        torch.empty((4, ls.geom.cout_p), device=x.device, dtype=torch.float32)),
+                                         None, ls.geom.cout, ls.relu, L.OUT_POOLED)
+            else:
+                out = ops.osconv(eng, L.DIR_FWD, ls.geom, h, wf, bias,
+                                 affine=(co, ls.relu, L.OUT_POOLED if spec.pooled else L.OUT_NCL_F32, None))
+        else:
+            sc = spec.shortcut
+            co_r = coeffs(sc, 4 * nl)
+            r = ops.osconv(eng, L.DIR_FWD, sc.geom, x0, packs[nl][0], params[4 * nl + 1],
+                           affine=(co_r, False, L.OUT_C8_F32, None))
+            out = ops.osconv(eng, L.DIR_FWD, ls.geom, h, wf, bias, affine=(co, spec.final_relu, L.OUT_NCL_F32, r))
+    return out
+
+
 def _fused_backward(spec: StackSpec, sv: "_Saved", params, dout: torch.Tensor, x_requires_grad: bool):
     eng, dt = spec.engine, spec.op_dtype
     nl = len(spec.layers)
@@ -384,7 +427,18 @@ class OSStackFunction(torch.autograd.Function):
         return (None, dx, *grads)
 
 
+INFERENCE_PATH = True      # debugging switch: False sends forward-only eval calls through the training kernels
+
+
 def os_stack(spec: StackSpec, x: torch.Tensor, params: List[torch.Tensor]) -> torch.Tensor:
+    no_graph = not torch.is_grad_enabled() or not (x.requires_grad or any(p.requires_grad for p in params))
+    if (INFERENCE_PATH and no_graph and FUSED_PATH and spec.engine == L.ENGINE_TCGEN05 and spec.op_dtype == L.TSC_BF16
+            and not any(ls.training for ls in spec.layers) and not (spec.shortcut is not None and spec.shortcut.training)):
+        ops._req(x, name="input")
+        if x.shape[1] != spec.layers[0].geom.cin:
+            raise RuntimeError(f"input has {x.shape[1]} channels, the first OS layer expects {spec.layers[0].geom.cin}")
+        with torch.no_grad():
+            return _inference_forward(spec, x, list(params))
     return OSStackFunction.apply(spec, x, *params)
 
 

@@ -16,7 +16,7 @@ from typing import List, Sequence, Tuple
 import torch
 
 from . import ops
-from .utils import predict_logits
+from .utils import GraphedPredictor
 
 ENTROPY_GAIN = 120.0       # multi_source_voting.py:387
 WEIGHT_BASE = 9.0          # :387 np.power(9, weight)
@@ -25,10 +25,11 @@ WEIGHT_BASE = 9.0          # :387 np.power(9, weight)
 def collect_logits(modules, dataloader) -> Tuple[torch.Tensor, torch.Tensor]:
     """(logits [N, K] fp32, labels [N] int64), both on the device, for a loader of (x, y) batches (:281-293)."""
     outs, labels = [], []
+    predict = GraphedPredictor(modules)
     with torch.no_grad():
         for _, (x, y) in enumerate(dataloader):
             x = x.float().cuda()
-            outs.append(predict_logits(modules, x))
+            outs.append(predict(x).clone())                          # the predictor's output buffer is reused
             labels.append(y.to(device=x.device, dtype=torch.int64))
     return torch.cat(outs).contiguous(), torch.cat(labels).contiguous()
 

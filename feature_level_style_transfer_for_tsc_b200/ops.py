@@ -262,8 +262,12 @@ def n_conv_ctas(B: int, Ln: int) -> int:
 
 def osconv(engine: int, direction: int, g: BankGeometry, x8: torch.Tensor, w_packed: torch.Tensor,
            bias: Optional[torch.Tensor], stat_partial: Optional[torch.Tensor] = None, mask=None,
-           red_partial: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """mask = (y_c8, scale|None, shift|None, mean, invstd) of the layer below (dgrad with red_partial only)."""
+           red_partial: Optional[torch.Tensor] = None, affine=None) -> torch.Tensor:
+    """mask = (y_c8, scale|None, shift|None, mean, invstd) of the layer below (dgrad with red_partial only).
+    affine = (coef, relu, out_kind, residual_c8_f32 | None): the inference epilogue of the tcgen05 engine (forward only) --
+    returns act(scale * (conv + bias) + shift [+ residual]) in layout ``out_kind``; the pre-BN y is not written.  ``coef`` is
+    (scale, shift) with Cout_p entries each, or (gamma, beta, running_mean, running_var, eps): eval-mode BatchNorm, the
+    coefficients are then derived in the kernel's prologue."""
     dt = L.TSC_BF16 if x8.dtype == torch.bfloat16 else L.TSC_F32
     _req(x8, torch_dtype(dt), "x_c8")
     _req(w_packed, torch_dtype(dt), "w_packed")
@@ -274,8 +278,39 @@ def osconv(engine: int, direction: int, g: BankGeometry, x8: torch.Tensor, w_pac
         raise RuntimeError(f"x_c8 has {kc * 8} padded channels, expected {cin_side}")
     if bias is not None:
         _req(bias, name="bias")
-    y = torch.empty((B, cout_side // 8, Ln, 8), device=x8.device, dtype=torch.float32)
     plan = g.plan(direction, x8.device) if engine == L.ENGINE_TCGEN05 else None
+    if affine is not None:
+        if direction != L.DIR_FWD or engine != L.ENGINE_TCGEN05 or stat_partial is not None:
+            raise RuntimeError("the affine (inference) epilogue exists for the forward tcgen05 convolution only")
+        coef, relu, out_kind, residual = affine
+        for t in coef[:4]:
+            _req(t, name="affine coefficient")
+            if t.numel() < (g.cout_p if len(coef) == 2 else g.cout):
+                raise RuntimeError("affine coefficient tensor is too short")
+        if out_kind == L.OUT_NCL_F32:
+            out = torch.empty((B, g.cout, Ln), device=x8.device, dtype=torch.float32)
+        elif out_kind == L.OUT_POOLED:
+            out = torch.empty((B, g.cout), device=x8.device, dtype=torch.float32)
+        else:
+            out = torch.empty((B, cout_side // 8, Ln, 8), device=x8.device,
+                              dtype=torch.bfloat16 if out_kind == L.OUT_C8_BF16 else torch.float32)
+        epi = L.ConvEpilogue()
+        if len(coef) == 2:
+            epi.affine_scale, epi.affine_shift = coef[0].data_ptr(), coef[1].data_ptr()
+        else:
+            epi.bn_gamma, epi.bn_beta, epi.bn_mean, epi.bn_var = (t.data_ptr() for t in coef[:4])
+            epi.bn_eps = float(coef[4])
+        epi.affine_out = out.data_ptr()
+        epi.affine_out_kind, epi.affine_relu = int(out_kind), 1 if relu else 0
+        if residual is not None:
+            _req(residual, name="residual")
+            if tuple(residual.shape) != (B, cout_side // 8, Ln, 8):
+                raise RuntimeError(f"residual shape {tuple(residual.shape)} != {(B, cout_side // 8, Ln, 8)}")
+            epi.residual = residual.data_ptr()
+        L.check(L.load().tsc_osconv(engine, direction, _ptr(x8), dt, _ptr(w_packed), _ptr(plan), _ptr(bias), None,
+                                    ctypes.byref(epi), B, Ln, g.cin, g.cout, g.kmax, g.s_arr, _stream()), "tsc_osconv")
+        return out
+    y = torch.empty((B, cout_side // 8, Ln, 8), device=x8.device, dtype=torch.float32)
     epi = None
     if stat_partial is not None or red_partial is not None:
         epi = L.ConvEpilogue()

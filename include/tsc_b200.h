@@ -122,6 +122,25 @@ typedef struct tsc_conv_epilogue {
     const float* mask_mean;
     const float* mask_invstd;
     float* red_partial;
+    /* FWD, inference (eval-mode BatchNorm folded into the convolution): when affine_out != NULL the kernel writes
+     *   z = act(affine_scale[c] * (acc + bias[c]) + affine_shift[c] [+ residual])
+     * with (scale, shift) [Cout_p] from tsc_bn_eval_coeffs, or -- affine_scale NULL -- derived in the kernel's prologue from
+     * the BatchNorm tensors themselves (bn_gamma, bn_beta, bn_mean = running_mean, bn_var = running_var, [Cout] each, bn_eps):
+     * scale = gamma / sqrt(var + eps), shift = beta - mean * scale, i.e. no launch besides the convolution,
+     * to affine_out in layout affine_out_kind (TSC_OUT_C8_BF16: the next layer's operand; TSC_OUT_C8_F32; TSC_OUT_NCL_F32:
+     * the module boundary; TSC_OUT_POOLED: mean over L, [B, Cout], L <= 128 only) and y_c8 may be NULL (not written).
+     * residual: c8 fp32 [B][Cout_p/8][L][8] or NULL (the shortcut branch of Res_OS_layer, OS_CNN.py:176-180). */
+    const float* affine_scale;
+    const float* affine_shift;
+    const float* residual;
+    void* affine_out;
+    int affine_out_kind;
+    int affine_relu;
+    const float* bn_gamma;
+    const float* bn_beta;
+    const float* bn_mean;
+    const float* bn_var;
+    float bn_eps;
 } tsc_conv_epilogue;
 size_t tsc_osconv_plan_bytes(int direction, int Cin, int Cout, int Kmax, const int* s_of_tap);
 int tsc_osconv_plan_build(int direction, int Cin, int Cout, int Kmax, const int* s_of_tap, void* host_plan);

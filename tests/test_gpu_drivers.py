@@ -243,3 +243,54 @@ def test_eval_helpers_and_vote_end_to_end(T, tables, small_pair, tmp_path, monke
     ck = torch.load("train_log/epoch_2.tar")
     assert set(ck) == {"epoch", "feature_extraction_state_dict", "classification_state_dict"}
     assert list(ck["feature_extraction_state_dict"].keys()) == list(small_pair["init_fe"].keys())
+
+
+@pytest.mark.parametrize("C,Ln,B,K", [(3, 32, 6, 4), (9, 128, 16, 6), (1, 160, 4, 3), (3, 400, 3, 5)])
+def test_inference_path_equals_the_training_kernels_in_eval_mode(T, C, Ln, B, K):
+    """Forward-only eval calls fold BatchNorm / ReLU / shortcut / pooling into the convolution epilogue: same numbers as the
+    conv -> bn_apply kernels of the training path (bf16 operands in both; a rounding flip of an intermediate is the only
+    difference), and within the tensor-core tolerance of the fp32 oracle.  L = 160 / 400 take the two-kernel pooled tail
+    (more than one CTA per sample) and a ragged last tile."""
+    from feature_level_style_transfer_for_tsc_b200 import functional as TF
+    from feature_level_style_transfer_for_tsc_b200.OS_CNN.OS_CNN import OS_CNN, OS_CNN_res
+    T.set_engine("tcgen05")
+    lpl_e, lpl_c = O.trainer_layer_lists(C, Ln) if Ln >= 100 else (as_lpl([[(C, 4, 1), (C, 4, 2), (C, 4, 3)],
+                                                                           [(12, 6, 1), (12, 6, 2), (12, 6, 3)],
+                                                                           [(18, 10, 1), (18, 10, 2)]]), None)
+    if lpl_c is None:
+        lpl_c = O.layer_parameter_list_input_change(lpl_e, O.feature_channels(lpl_e))
+    torch.manual_seed(2)
+    fe, cl = OS_CNN_res(lpl_e).cuda(), OS_CNN(lpl_c, K).cuda()
+    x, _ = O.synthetic_batch(B, C, Ln, K, 3)
+    xd = x.cuda()
+    fe.train(); cl.train()
+    with torch.no_grad():                      # a few training-mode passes give the running statistics real values
+        for _ in range(3):
+            cl(fe(xd))
+    sd_fe = {k: v.detach().cpu().clone() for k, v in fe.state_dict().items()}
+    sd_cl = {k: v.detach().cpu().clone() for k, v in cl.state_dict().items()}
+    fe.eval(); cl.eval()
+    with torch.no_grad():
+        feat = fe(xd)
+        logits, pooled = cl(feat)
+        TF.INFERENCE_PATH = False
+        try:
+            feat0 = fe(xd)
+            logits0, pooled0 = cl(feat0)
+        finally:
+            TF.INFERENCE_PATH = True
+    torch.cuda.synchronize()
+    assert T.ops.read_watchdog() == 0
+    assert feat.shape == feat0.shape and logits.shape == (B, K) and pooled.shape == pooled0.shape
+    assert rel_err(feat.cpu(), feat0.cpu()) < 5e-3
+    assert rel_err(pooled.cpu(), pooled0.cpu()) < 5e-3
+    assert rel_err(logits.cpu(), logits0.cpu()) < 5e-3
+    ref_feat = O.extractor_forward(sd_fe, lpl_e, x, training=False)
+    ref_logits, ref_pooled = O.classifier_forward(sd_cl, lpl_c, ref_feat, training=False)
+    assert rel_err(feat.cpu(), ref_feat) < 2e-2                                # tcgen05 engine: bf16 operands, 1e-2 class
+    assert rel_err(pooled.cpu(), ref_pooled) < 2e-2
+    assert rel_err(logits.cpu(), ref_logits) < 2e-2
+    # with autograd on and parameters that require grad the same call must build a graph (the joint stage's eval-BN
+    # classifier call, train_and_test.py:584-586): not the inference path
+    out = cl(feat.requires_grad_(True))[0]
+    assert out.requires_grad
