@@ -73,7 +73,7 @@ __device__ __forceinline__ int row_argmax(const float* __restrict__ r, int K) {
     float bv = r[0];
     for (int k = 1; k < K; ++k) {
         const float v = r[k];
-        if (v > bv || (bv != bv && v == v)) { bv = v; best = k; }      // first maximum; NaN never wins over a number
+        if (v > bv || (v != v && bv == bv)) { bv = v; best = k; }      // first maximum; like numpy.argmax the first NaN wins
     }
     return best;
 }

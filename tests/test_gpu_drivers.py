@@ -294,3 +294,60 @@ def test_inference_path_equals_the_training_kernels_in_eval_mode(T, C, Ln, B, K)
     # classifier call, train_and_test.py:584-586): not the inference path
     out = cl(feat.requires_grad_(True))[0]
     assert out.requires_grad
+
+
+def test_driver_kernels_edge_cases(T):
+    """Smallest and largest supported shapes, degenerate rows, and the numpy corner cases the reference inherits
+    (softmax without max subtraction overflows to NaN for logits > 88; numpy.argmax returns the first NaN)."""
+    from feature_level_style_transfer_for_tsc_b200 import multi_source_voting as MV
+    g = torch.Generator().manual_seed(9)
+    # one series, one class, one model
+    lg = torch.zeros(1, 1)
+    pred, counts, prec = T.ops.class_precision(lg.cuda(), torch.zeros(1, dtype=torch.int64).cuda())
+    assert pred.tolist() == [0] and counts.tolist() == [[1], [1]] and prec.tolist() == [1.0]
+    score, p = MV.entropy_vote([lg.cuda()], [prec])
+    ref_s, ref_p = V.entropy_vote([lg.numpy()], V.normalized_weights([prec.cpu().numpy()]))
+    assert rel_err(score.cpu(), ref_s) < 1e-6 and p.tolist() == ref_p.tolist()
+    # the largest shape: 64 classes, 8 models, a ragged number of rows; uniform rows (maximum entropy) and a one-hot row
+    N, K, M = 1000 + 37, 64, 8
+    logits = [torch.randn(N, K, generator=g) * 3 for _ in range(M)]
+    logits[0][5] = 0.0
+    logits[1][6] = -40.0
+    logits[1][6, 17] = 40.0
+    labels = torch.randint(0, K, (N,), generator=g)
+    precs = [T.ops.class_precision(l.cuda(), labels.cuda())[2] for l in logits]
+    for l, pr in zip(logits, precs):
+        assert np.array_equal(pr.cpu().numpy(), V.class_precision(l.numpy(), labels.numpy(), K))
+    score, p = MV.entropy_vote([l.cuda() for l in logits], precs)
+    ref_s, ref_p = V.entropy_vote([l.numpy() for l in logits], V.normalized_weights([pr.cpu().numpy() for pr in precs]))
+    assert rel_err(score.cpu(), ref_s) < 1e-5
+    assert np.array_equal(p.cpu().numpy(), ref_p)
+    # exp overflow: inf / inf = NaN in the reference's softmax; numpy.argmax picks the first NaN -- so does the kernel
+    over = torch.tensor([[1.0, 100.0, 2.0], [0.5, 0.1, 0.2]])
+    one = torch.ones(3, dtype=torch.float64).cuda()
+    score, p = MV.entropy_vote([over.cuda()], [one])
+    with np.errstate(all="ignore"):
+        ref_s, ref_p = V.entropy_vote([over.numpy()], np.ones((1, 3)))
+    assert np.isnan(ref_s[0]).any() and p.tolist() == ref_p.tolist()
+    assert np.array_equal(np.isnan(score.cpu().numpy()), np.isnan(ref_s))
+    assert T.ops.class_precision(torch.tensor([[0.0, float("nan"), 5.0]]).cuda())[0].tolist() == [1]
+    with pytest.raises(RuntimeError):
+        MV.entropy_vote([lg.cuda()] * 9, [prec] * 9)                 # more models than TSC_MAX_VOTERS
+    # 32 tensors in one norm call, one of them empty
+    ts = [torch.randn(17 * (i + 1), device="cuda") for i in range(31)] + [torch.empty(0, device="cuda")]
+    out = T.ops.multi_l2norm(ts).cpu().numpy()
+    ref = np.array([float(torch.linalg.vector_norm(t.double())) for t in ts])
+    assert rel_err(out[:-1], ref) < 2e-6 and out[31] == 0.0
+    with pytest.raises(RuntimeError):
+        T.ops.multi_l2norm(ts + ts[:1])
+    # a single series through the inference path
+    from feature_level_style_transfer_for_tsc_b200.OS_CNN.OS_CNN import OS_CNN, OS_CNN_res
+    T.set_engine("tcgen05")
+    lpl_e, lpl_c = O.trainer_layer_lists(9, 128)
+    torch.manual_seed(4)
+    fe, cl = OS_CNN_res(lpl_e).cuda().eval(), OS_CNN(lpl_c, 6).cuda().eval()
+    x, _ = O.synthetic_batch(3, 9, 128, 6, 0)
+    with torch.no_grad():
+        all3 = cl(fe(x.cuda()))[0]
+        one_ = cl(fe(x[1:2].cuda()))[0]
+    assert torch.equal(all3[1:2], one_)                              # eval mode: no coupling across the batch, bit for bit
