@@ -73,7 +73,11 @@ def main():
         part = torch.empty(ops.n_conv_ctas(B, Ln), g.cout_p, 2, device=dev)
         flops = 2.0 * B * Ln * g.live_macs_per_position()
         reps = 5 if B * Ln >= 1 << 19 else 20
+        gamma, beta = torch.ones(g.cout, device=dev), torch.zeros(g.cout, device=dev)
+        rmean, rvar = torch.zeros(g.cout, device=dev), torch.ones(g.cout, device=dev)
+        aff = ((gamma, beta, rmean, rvar, 1e-5), True, L.OUT_C8_BF16, None)
         for name, fn in (("osconv fwd (+BN partial statistics)", lambda: ops.osconv(L.ENGINE_TCGEN05, L.DIR_FWD, g, x8, wf, bias, stat_partial=part)),
+                         ("osconv fwd inference (eval BN + ReLU epilogue, bf16 out)", lambda: ops.osconv(L.ENGINE_TCGEN05, L.DIR_FWD, g, x8, wf, bias, affine=aff)),
                          ("osconv dgrad", lambda: ops.osconv(L.ENGINE_TCGEN05, L.DIR_DGRAD, g, dy8, wd, None)),
                          ("oswgrad (+ordered reduce)", lambda: ops.oswgrad(L.ENGINE_TCGEN05, g, dy8, x8))):
             t = timed(fn, reps)
