@@ -76,9 +76,11 @@ struct ConvTcParams {
                        // tcgen05 fence after every stage wait (the pre-session-3 behaviour)
 };
 
-#define TL(i) do { if (p.tl && blockIdx.x == 0) p.tl[i] = clock64(); } while (0)
+// DBG is the kernel's template flag: the production instantiation carries no timeline / experiment code at all (the MMA
+// issuer is bound by its own instruction count -- ncu source page, profiles/README.md session 4)
+#define TL(i) do { if (DBG && p.tl && blockIdx.x == 0) p.tl[i] = clock64(); } while (0)
 // per-stage samples of CTA 0 (debug timeline only): slot k of weight stage i, for the first 48 stages
-#define TLS(i, k) do { if (p.tl && blockIdx.x == 0 && (i) < 48) p.tl[8 + (i) * 8 + (k)] = clock64(); } while (0)
+#define TLS(i, k) do { if (DBG && p.tl && blockIdx.x == 0 && (i) < 48) p.tl[8 + (i) * 8 + (k)] = clock64(); } while (0)
 
 // 32 lanes x 32 bit, 32 consecutive columns
 __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, float* v) {
@@ -128,7 +130,7 @@ __device__ __forceinline__ float warp_colsum32(float* v, int lane) {
 
 // AFF: the inference instantiation (eval-mode BatchNorm folded into the epilogue).  A separate instantiation so that the
 // training kernel keeps its register budget (125 per thread: two CTAs of different launches share an SM).
-template <bool AFF>
+template <bool AFF, bool DBG>
 __global__ void __launch_bounds__(TC_THREADS, AFF ? 2 : 1)
 osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const ConvTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -216,7 +218,7 @@ osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const ConvTcParams p)
                 TLS(i, 4);
                 mbar_wait(&empty[s], ph ^ 1u, dead, 1);
                 TLS(i, 5);
-                if (p.debug & 4) { mbar_arrive(&full[s]); if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; } continue; }
+                if (DBG && (p.debug & 4)) { mbar_arrive(&full[s]); if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; } continue; }
                 mbar_arrive_expect_tx(&full[s], e.y);
                 bulk_load(stages + (size_t)s * (p.stage_bytes + ZERO_BLOCK_BYTES), reinterpret_cast<const uint8_t*>(p.w) + (size_t)e.x * 16,
                           e.y, &full[s]);
@@ -263,42 +265,52 @@ osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const ConvTcParams p)
         uint32_t s = 0, ph = 0, acc = 0;
         int stage_i = 0;
         uint4 e0 = mm[0], e1 = mm[1], e2 = mm[2], e3 = mm[3];
-        uint32_t fl = gflag[0];
-        for (int g = 0; g < n_grp; ++g) {
-            const int gn = min(g + 1, n_grp - 1);
-            const uint4* nx = mm + (size_t)gn * MMA_GROUP;
-            const uint4 f0 = nx[0], f1 = nx[1], f2 = nx[2], f3 = nx[3];
-            const uint32_t fln = gflag[gn];
-            if (fl & 1u) {
-                if (lane == 0) TLS(stage_i, 0);
-                // The stage's bytes were written by the async proxy and published through the mbarrier's complete_tx:
-                // tcgen05.mma may read them without a tcgen05 fence (the fence is for ordering against other threads'
-                // tcgen05 operations).  With the fence here the issuer paid ~240 cycles per already-complete stage.
-                if (!mbar_test_wait(&full[s], ph)) mbar_wait(&full[s], ph, dead, 3);
-                __syncwarp();     // lanes leave the polling loop at different times: reconverge before the elect
-                if (p.debug & 8) tc_fence_after();
-                if (g == 0 && lane == 0) TL(3);
-                if (lane == 0) TLS(stage_i, 1);
-            }
-            const bool last = (fl & 2u) != 0;
-            if (p.debug & 2) {
-                if (last && elect_one()) tc_commit(&empty[s]);
-            } else if (elect_one()) {
-                umma_bf16(e0.w, ((uint64_t)desc_hi << 32) | e0.x, ((uint64_t)desc_hi << 32) | e0.y, e0.z, acc);
-                umma_bf16(e1.w, ((uint64_t)desc_hi << 32) | e1.x, ((uint64_t)desc_hi << 32) | e1.y, e1.z, 1u);
-                umma_bf16(e2.w, ((uint64_t)desc_hi << 32) | e2.x, ((uint64_t)desc_hi << 32) | e2.y, e2.z, 1u);
-                umma_bf16(e3.w, ((uint64_t)desc_hi << 32) | e3.x, ((uint64_t)desc_hi << 32) | e3.y, e3.z, 1u);
-                if (last) tc_commit(&empty[s]);      // frees the stage when these MMAs have read it
-            }
-            acc = 1;
-            if (last) {
-                if (lane == 0) TLS(stage_i, 2);
-                ++stage_i;
-                if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; }
-            }
-            e0 = f0; e1 = f1; e2 = f2; e3 = f3;
-            fl = fln;
+        uint4 f0, f1, f2, f3;
+        uint32_t fl = gflag[0], fln;
+        // One issue group: prefetch the next group's entries (the read past the last group lands in the flag bytes / the
+        // activation tile: in bounds, never issued), wait for the group's weight stage if it opens one, issue, commit.
+        // The loop is unrolled by two with the register sets swapped, so the prefetched entries are never copied: the
+        // issuing warp is bound by its own instruction count (118 warp instructions per group before, ncu source page).
+#define TSC_ISSUE_GROUP(E0, E1, E2, E3, FL, N0, N1, N2, N3, FLN, G)                                                  \
+        {                                                                                                            \
+            const uint4* nx = mm + (size_t)((G) + 1) * MMA_GROUP;                                                    \
+            N0 = nx[0]; N1 = nx[1]; N2 = nx[2]; N3 = nx[3];                                                          \
+            FLN = gflag[(G) + 1];                                                                                    \
+            if (FL & 1u) {                                                                                           \
+                if (lane == 0) TLS(stage_i, 0);                                                                      \
+                /* The stage's bytes were written by the async proxy and published through the mbarrier's complete_tx: \
+                   tcgen05.mma may read them without a tcgen05 fence (with the fence the issuer paid ~240 cycles per   \
+                   already-complete stage). */                                                                       \
+                if (!mbar_test_wait(&full[s], ph)) mbar_wait(&full[s], ph, dead, 3);                                 \
+                __syncwarp();     /* lanes leave the polling loop at different times: reconverge before the elect */ \
+                if (DBG && (p.debug & 8)) tc_fence_after();                                                          \
+                if ((G) == 0 && lane == 0) TL(3);                                                                    \
+                if (lane == 0) TLS(stage_i, 1);                                                                      \
+            }                                                                                                        \
+            const bool last = (FL & 2u) != 0;                                                                        \
+            if (DBG && (p.debug & 2)) {                                                                              \
+                if (last && elect_one()) tc_commit(&empty[s]);                                                       \
+            } else if (elect_one()) {                                                                                \
+                umma_bf16(E0.w, ((uint64_t)desc_hi << 32) | E0.x, ((uint64_t)desc_hi << 32) | E0.y, E0.z, acc);      \
+                umma_bf16(E1.w, ((uint64_t)desc_hi << 32) | E1.x, ((uint64_t)desc_hi << 32) | E1.y, E1.z, 1u);       \
+                umma_bf16(E2.w, ((uint64_t)desc_hi << 32) | E2.x, ((uint64_t)desc_hi << 32) | E2.y, E2.z, 1u);       \
+                umma_bf16(E3.w, ((uint64_t)desc_hi << 32) | E3.x, ((uint64_t)desc_hi << 32) | E3.y, E3.z, 1u);       \
+                if (last) tc_commit(&empty[s]);      /* frees the stage when these MMAs have read it */               \
+            }                                                                                                        \
+            acc = 1;                                                                                                 \
+            if (last) {                                                                                              \
+                if (lane == 0) TLS(stage_i, 2);                                                                      \
+                if (DBG) ++stage_i;                                                                                  \
+                if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; }                                                      \
+            }                                                                                                        \
         }
+        int g = 0;
+        for (; g + 1 < n_grp; g += 2) {
+            TSC_ISSUE_GROUP(e0, e1, e2, e3, fl, f0, f1, f2, f3, fln, g)
+            TSC_ISSUE_GROUP(f0, f1, f2, f3, fln, e0, e1, e2, e3, fl, g + 1)
+        }
+        if (g < n_grp) TSC_ISSUE_GROUP(e0, e1, e2, e3, fl, f0, f1, f2, f3, fln, g)
+#undef TSC_ISSUE_GROUP
         __syncwarp();
         if (elect_one()) tc_commit(acc_full);
         pdl_trigger();            // the next kernel of the stream may start its prologue while the epilogue runs
@@ -742,14 +754,21 @@ int osconv_tc(int direction, const void* x, int dtype, const void* w, const void
     const int smem = p.off_stages + ns * slot;
     static bool attr_set = false;          // once per process: opt in to the full 227 KB of dynamic shared memory
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(osconv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(osconv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(osconv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(osconv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(osconv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(osconv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         attr_set = true;
     }
     {
-        cudaError_t le = p.aff_out ? launch_pdl(osconv_tc_kernel<true>, dim3(B * p.ltiles), dim3(TC_THREADS), (size_t)smem, cs, xmap, p)
-                                   : launch_pdl(osconv_tc_kernel<false>, dim3(B * p.ltiles), dim3(TC_THREADS), (size_t)smem, cs, xmap, p);
+        // the instrumented instantiation only when a timeline buffer or an experiment knob is set
+        const bool dbg = p.tl != nullptr || p.debug != 0;
+        const dim3 grid(B * p.ltiles), block(TC_THREADS);
+        cudaError_t le = p.aff_out ? (dbg ? launch_pdl(osconv_tc_kernel<true, true>, grid, block, (size_t)smem, cs, xmap, p)
+                                          : launch_pdl(osconv_tc_kernel<true, false>, grid, block, (size_t)smem, cs, xmap, p))
+                                   : (dbg ? launch_pdl(osconv_tc_kernel<false, true>, grid, block, (size_t)smem, cs, xmap, p)
+                                          : launch_pdl(osconv_tc_kernel<false, false>, grid, block, (size_t)smem, cs, xmap, p));
         if (le != cudaSuccess) { set_error("osconv launch: %s", cudaGetErrorString(le)); return (int)le; }
     }
     TSC_LAUNCH_CHECK();
