@@ -150,6 +150,16 @@ osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const ConvTcParams p)
     const int b = blockIdx.x / p.ltiles, l0 = (blockIdx.x % p.ltiles) * 128;
     const int np = p.np;
 
+    // experiment (TSC_CONV_DEBUG & 16, instrumented instantiation only): every CTA records %globaltimer at entry and exit and
+    // its SM id at tl[1024 + 4 * blockIdx.x ..] -- where a launch's wall time goes beyond the lifetime of one CTA
+    if (DBG && (p.debug & 16) && p.tl && threadIdx.x == 0) {
+        unsigned long long t; unsigned int sm;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        p.tl[1024 + 4 * blockIdx.x] = (long long)t;
+        p.tl[1024 + 4 * blockIdx.x + 2] = (long long)sm;
+        p.tl[1024 + 4 * blockIdx.x + 3] = clock64();
+    }
     if (warp == 0 && lane == 0) {
         TL(0);
         tma_prefetch_desc(&xmap);
@@ -533,6 +543,12 @@ osconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const ConvTcParams p)
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     if (warp == 1 && lane == 0) TL(7);
+    if (DBG && (p.debug & 16) && p.tl && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.tl[1024 + 4 * blockIdx.x + 1] = (long long)t;
+        p.tl[1024 + 4 * blockIdx.x + 3] = clock64() - p.tl[1024 + 4 * blockIdx.x + 3];
+    }
 }
 
 EncodeTiledFn get_encode_tiled() {
