@@ -38,6 +38,12 @@ WORKLOAD3 = ("cfg3: 3 source domains (C,L)=(1,128),(3,256),(9,128) + 1 target (9
 STYLE_WEIGHT = 1.0
 
 
+def step_config(workload: str, series_per_gpu: int):
+    """`config` of the JSON line: workload keys only, identical in both arms (the driver compares them)."""
+    return dict(workload=workload, series_per_step_per_gpu=series_per_gpu,
+                l2="flushed between timed steps (256 MiB write, outside the per-step events)")
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -109,17 +115,128 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 20))
-    value, dt, cores, threads = cpu_step_rate(steps, max(1, min(args.warmup, 2)))
+    # one step = one full cfg2 step of the oracle port (about 0.25 s on 16 cores): --steps / --warmup are honoured as given
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    value, dt, cores, threads = cpu_step_rate(steps, warmup)
     sample = f"{steps} full cfg2 steps (B=128 per domain) of the oracle port on {threads} torch CPU threads"
     line = dict(metric=METRIC, value=value, unit=UNIT, impl="reference", n_gpus=args.gpus, steps=steps,
-                warmup=max(1, min(args.warmup, 2)), ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak",
+                warmup=warmup, ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload=WORKLOAD, series_per_step_per_gpu=2 * CFG["B"], engine="cpu oracle port (torch/oneDNN fp32)",
-                            parallelism="rank 0 only"),
+                config=step_config(WORKLOAD, 2 * CFG["B"]),
+                run=dict(engine="cpu oracle port (torch/oneDNN fp32)", parallelism="rank 0 only"),
                 cpu_baseline=dict(value=value, unit=UNIT, cores=threads, kind="port", sample=sample),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
+
+
+
+def measure_tf32_peak(torch, n=8192, reps=6):
+    """cuBLAS TF32 matmul throughput on this box (burst, best of `reps`), measured the way MEASURED_PEAKS.json measures
+    the bf16 peak -- the denominator of the Gram kernels' tensor roofline (kind::tf32)."""
+    a = torch.randn(n, n, device="cuda")
+    b = torch.randn(n, n, device="cuda")
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        for _ in range(2):
+            torch.matmul(a, b)
+        best = float("inf")
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def time_cold(torch, fn, flush, reps=8):
+    """mean device ms of fn() with the L2 flushed before every launch (events on the launching stream)."""
+    for _ in range(3):
+        fn()
+    evs = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in evs)
+    return ts[len(ts) // 2]
+
+
+def style_rooflines(torch, ops, L, peaks, tf32_peak, flush):
+    """HBM roofline of the statistics / AdaIN kernels (north_star (b)) and tensor roofline of the Gram kernels (c), at the
+    cfg2 shape and at the sweep shape [1024, 144, 1024]; every launch timed alone, L2 flushed before it (cold operands)."""
+    hbm, gram = [], []
+    for (B, C, Ln) in ((128, 144, 128), (1024, 144, 1024)):
+        n = B * C * Ln
+        c = torch.randn(B, C, Ln, device="cuda")
+        st = torch.randn(B, C, Ln, device="cuda")
+        dy = torch.randn(B, C, Ln, device="cuda")
+        _, stats = ops.adain_fwd(c, st, 1e-5)
+        for name, fn, nbytes in (("rowstats_welford", lambda: ops.rowstats(c), 4.0 * n),
+                                 ("adain_fwd", lambda: ops.adain_fwd(c, st, 1e-5), 12.0 * n),
+                                 ("adain_bwd", lambda: ops.adain_bwd(dy, c, st, stats), 20.0 * n)):
+            ms = time_cold(torch, fn, flush)
+            gbs = nbytes / (ms * 1e-3) / 1e9
+            hbm.append(dict(kernel=name, shape=[B, C, Ln], bound="hbm", us=round(ms * 1e3, 2), achieved=round(gbs, 1),
+                            peak=peaks["hbm"], unit="GB/s", frac=round(gbs / peaks["hbm"], 3), algorithmic_bytes=nbytes))
+        eng = L.ENGINE_TCGEN05
+        _, D = ops.gram_loss_fwd(eng, c, st)
+        one = torch.ones((), device="cuda")
+        flops = 2.0 * 2 * B * C * C * Ln
+        for name, fn in (("gram_loss_fwd", lambda: ops.gram_loss_fwd(eng, c, st)),
+                         ("gram_loss_bwd", lambda: ops.gram_loss_bwd(eng, D, c, st, one))):
+            ms = time_cold(torch, fn, flush)
+            tf = flops / (ms * 1e-3) / 1e12
+            gram.append(dict(kernel=name, shape=[B, C, Ln], bound="tensor", us=round(ms * 1e3, 2), achieved=round(tf, 1),
+                             peak=round(tf32_peak, 1), unit="TFLOP/s", frac=round(tf / tf32_peak, 3), algorithmic_flops=flops,
+                             peak_source="cuBLAS TF32 8192^3 measured in this run (kind::tf32; the forward issues 3 MMAs per "
+                                         "algorithmic one: hi*hi + hi*lo + lo*hi)"))
+        del c, st, dy, stats, D
+    return hbm, gram
+
+
+def gpu_eager_baseline(torch, steps=10, warmup=3):
+    """The GPU bar (SURVEY 8d / BASELINE.md section 4): the oracle port of the cfg2 step -- the reference's own operator
+    sequence in plain PyTorch -- run eagerly on cuda:0 (cuDNN convolutions with torch's default TF32, cuBLAS, ATen
+    element-wise kernels), timed with CUDA events after this repo's timed regions.  A reported baseline, like cpu_baseline."""
+    from oracle import os_cnn as OO
+    from oracle import step as OS
+    ms = OS.ModelSet(CFG["C"], CFG["L"], CFG["K"], CFG["C"], CFG["L"], CFG["K"], seed=0)
+    for name in ("fe_t", "cl_t", "fe_s", "du", "cl_s"):
+        sd = getattr(ms, name)
+        for k in list(sd.keys()):
+            sd[k] = sd[k].cuda()
+    xt, yt = [t.cuda() for t in OO.synthetic_batch(CFG["B"], CFG["C"], CFG["L"], CFG["K"], 0)]
+    xs, ys = [t.cuda() for t in OO.synthetic_batch(CFG["B"], CFG["C"], CFG["L"], CFG["K"], 1)]
+
+    def one():
+        ms.set_requires_grad()
+        out = OS.step_forward(ms, xt, yt, xs, ys, STYLE_WEIGHT, training=True)
+        out["loss"].backward()
+        OS.rmsprop_update(ms)
+
+    for _ in range(warmup):
+        one()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one()
+    e1.record()
+    torch.cuda.synchronize()
+    dt = e0.elapsed_time(e1) * 1e-3 / steps
+    return dict(value=2 * CFG["B"] / dt, unit=UNIT, ms_per_step=dt * 1e3, steps=steps,
+                what="oracle port of the cfg2 step in eager PyTorch on cuda:0: cuDNN convolutions (TF32, torch default), "
+                     "cuBLAS fp32, ATen element-wise kernels, one optimizer loop over the tensors; host launch latency included "
+                     "(that is how the reference runs)")
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -304,7 +421,7 @@ def run_ours(args):
     import feature_level_style_transfer_for_tsc_b200 as T
     from feature_level_style_transfer_for_tsc_b200 import ops
     from feature_level_style_transfer_for_tsc_b200.train_step import StyleTransferModelSet, Trainer
-    from oracle import os_cnn as O                      # synthetic input generator only (SURVEY 8d definition)
+    from feature_level_style_transfer_for_tsc_b200 import data as O      # synthetic input generator (SURVEY 8d definition)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -445,8 +562,27 @@ def run_ours(args):
     kern = {k: dict(ms_per_step=round(v["ms_per_step"], 4), launches=v["launches_per_step"],
                     tflops=(round(v["tflops"], 2) if v["tflops"] else None),
                     gbs=(round(v["gbs"], 1) if v["gbs"] else None)) for k, v in sorted(table.items(), key=lambda kv: -kv[1]["ms"])}
+    extra = {}
     if args.engine == "tcgen05":
-        roof = conv_roofline(torch, ops, T._lib, conv_calls, peaks)
+        iso = conv_roofline(torch, ops, T._lib, conv_calls, peaks)
+        # headline = the kernel INSIDE the step: algorithmic FLOPs of the step's conv launches / their summed event time in
+        # the instrumented single-stream pass, against the sustained bf16 peak (a kernel timed inside a long step)
+        d = table.get("osconv[tc]")
+        ach = d["tflops"] if d and d["tflops"] else 0.0
+        roof = dict(kernel=iso["kernel"], bound="tensor", achieved=ach, peak=peaks["bf16_sustained"], unit="TFLOP/s",
+                    frac=ach / peaks["bf16_sustained"], traffic=iso["traffic"], traffic_note=iso["traffic_note"],
+                    peak_source=peaks["source"] + " bf16 sustained (kernel timed inside the step)",
+                    timing="CUDA events around every conv launch of 3 instrumented eager steps on one stream (device time, GPU "
+                           "kept busy ahead of the host); FLOPs = live-tap 2*B*L*Cin*sum(out_g*k_g) per launch",
+                    algorithmic_flops_per_step=iso["algorithmic_flops_per_step"],
+                    device_ms_per_step=(d["ms_per_step"] if d else None), launches_per_step=(d["launches_per_step"] if d else None),
+                    isolated=dict(achieved=iso["achieved"], peak=iso["peak"], frac=iso["frac"], peak_source=iso["peak_source"],
+                                  device_ms_per_step=iso["device_ms_per_step"], launches=iso["launches"],
+                                  note="each distinct launch replayed 20x back to back in a CUDA graph, operands L2-warm"))
+        if world == 1 and not args.no_extra:
+            tf32_peak = measure_tf32_peak(torch)
+            hbm, gram = style_rooflines(torch, ops, T._lib, peaks, tf32_peak, flush)
+            extra = dict(roofline_hbm=hbm, roofline_gram=gram, tf32_peak_tflops=round(tf32_peak, 1))
     else:
         d = table.get("osconv", dict(tflops=0.0))
         roof = dict(kernel="osconv_simt_kernel (fp32 CUDA cores; not the product engine)", bound="tensor",
@@ -460,14 +596,16 @@ def run_ours(args):
     line = dict(metric=METRIC, value=series / t_dev, unit=UNIT, n_gpus=world, steps=args.steps,
                 warmup=max(args.warmup, 3), ms_per_step=t_dev / args.steps * 1e3, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="bf16" if args.engine == "tcgen05" else "f32", data="synthetic",
-                config=dict(workload=WORKLOAD3 if cfg3 else WORKLOAD4 if cfg4 else WORKLOAD, series_per_step_per_gpu=series_per_gpu, engine=args.engine, parallelism=f"dp{world}",
-                            cuda_graph=not args.no_graph,
-                            l2="flushed between timed steps (256 MiB write, outside the per-step events)"),
+                config=step_config(WORKLOAD3 if cfg3 else WORKLOAD4 if cfg4 else WORKLOAD, series_per_gpu),
+                run=dict(engine=args.engine, parallelism=f"dp{world}", cuda_graph=not args.no_graph),
                 e2e=dict(value=series / t_e2e, unit=UNIT, h2d_bytes_per_step=h2d_bytes * world, d2h_bytes_per_step=4 * world,
                          ms_per_step=t_e2e / args.steps * 1e3),
                 gpu_launches=int(launches), clocks=clocks.summary(), roofline=roof, kernels=kern)
     if cpu:
         line["cpu_baseline"] = cpu
+    line.update(extra)
+    if world == 1 and not args.no_extra and not cfg4 and not cfg3:
+        line["gpu_eager_baseline"] = gpu_eager_baseline(torch)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -481,6 +619,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--engine", default="tcgen05", choices=["tcgen05", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the statistics / AdaIN / Gram rooflines, the TF32 peak and the eager-PyTorch GPU baseline")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4"],
                     help="cfg2 = the headline step (default); cfg3 = multi-source transfer with the C-DAN loss; "
                          "cfg4 = long-series OS-CNN forward + backward (both secondary)")

@@ -1,31 +1,28 @@
-"""Conditional-adversarial (C-DAN) consumer of the transferred features -- drop-in mirror of the reference's
-``C_DAN.py`` (same names and call signatures: ``RandomLayer``, ``Entropy``, ``grl_hook``, ``calc_coeff``, ``CDAN``)
+"""Conditional-adversarial (C-DAN) consumer of the transferred features -- the reference's ``C_DAN.py`` surface that the
+trainer uses (``RandomLayer([Cf*L, K])`` and ``CDAN(...)``, train_and_test.py:74-76,590-594) on this repository's kernels,
 for BASELINE configuration 3.
 
-``CDAN(...)`` with a two-view ``RandomLayer`` (the only form the trainer uses, train_and_test.py:74-76,590-591) runs
+``CDAN(...)`` runs
 
-    y0 = [flatten(target feature); flatten(generated feature)] @ R0      cuBLAS (plain dense GEMM, [2B, C*L] x [C*L, 1024])
+    y0 = [flatten(target feature); flatten(generated feature)] @ R0      random projection, [2B, C*L] x [C*L, 1024]
     fusion, u = tsc_cdan_fuse_fwd(y0, logits, R1)                         softmax, p @ R1, scale, product, entropy weights
-    out = critic(fusion)                                                  three Linear layers (cuBLAS), ONE pass over 2B rows
+    out = critic(fusion)                                                  three Linear layers, ONE pass over 2B rows
     loss = tsc_cdan_distance_fwd(u, out)
 
 and the matching two backward kernels, which also apply the reference's three gradient reversals (the hooks of
-C_DAN.py:68-69 and widgets.py:121-122) with coefficients read from a small device buffer -- no host synchronisation
-(the reference's ``.item()`` at C_DAN.py:72,75 becomes a detached device sum), so the whole loss is CUDA-graph
-capturable.  Every other call shape (any number of views, ``random_layer=None``) takes the generic route below, which
-is the reference's sequence of torch operators on CUDA tensors.  There is no CPU path.
+C_DAN.py:68-71 and widgets.py:121-122) with coefficients read from a small device buffer -- no host synchronisation
+(the reference's ``.item()`` at C_DAN.py:75,77 becomes a detached device sum), so the whole loss is CUDA-graph
+capturable.  The only call shape is the trainer's: a two-view ``RandomLayer`` (feature, class logits).  Anything else --
+``random_layer=None`` (the outer-product form, C_DAN.py:55-59), more views, CPU tensors -- raises: there is no
+alternate route.
 """
 import math
 
-import numpy as np
 import torch
 import torch.nn as nn
 
 from . import ops
 from .widgets import AdversarialNetworkforCDAN
-
-
-FUSED = True          # debugging switch: False sends every call through the generic torch-operator route
 
 
 class RandomLayer(nn.Module):
@@ -52,28 +49,8 @@ class RandomLayer(nn.Module):
         return math.pow(float(self.output_dim), 1.0 / self.input_num)
 
     def forward(self, input_list):
-        return_list = [torch.mm(input_list[i], self.random_matrix[i]) for i in range(self.input_num)]
-        return_tensor = return_list[0] / self.scale_div
-        for single in return_list[1:]:
-            return_tensor = torch.mul(return_tensor, single)
-        return return_tensor
-
-
-def Entropy(input_):
-    """-sum p log(p + 1e-5) over dim 1 of already soft-maxed rows (reference lines 32-37)."""
-    epsilon = 1e-5
-    entropy = -input_ * torch.log(input_ + epsilon)
-    return torch.sum(entropy, dim=1)
-
-
-def grl_hook(coeff):
-    def fun1(grad):
-        return -coeff * grad.clone()
-    return fun1
-
-
-def calc_coeff(iter_num, high=1.0, low=0.0, alpha=100.0, max_iter=50.0):
-    return float(2.0 * (high - low) / (1.0 + np.exp(-alpha * iter_num / max_iter)) - (high - low) + low)
+        raise RuntimeError("RandomLayer is evaluated inside CDAN(...): the projection, the class-probability product and the "
+                           "entropy weights are one fused kernel chain (no stand-alone torch route)")
 
 
 class _RandomProjectPair(torch.autograd.Function):
@@ -145,30 +122,11 @@ def CDAN(input_target, input_g_from_source, prob_target, prob_g_from_source, ad_
         raise RuntimeError("CDAN needs CUDA tensors: the tsc_b200 path has no CPU fallback")
     input_target = torch.flatten(input_target, 1)
     input_g_from_source = torch.flatten(input_g_from_source, 1)
-    if (FUSED and random_layer is not None and random_layer.input_num == 2 and prob_target.shape[1] <= 32
-            and input_target.shape == input_g_from_source.shape and random_layer.output_dim <= 8192):
-        return _cdan_fused(input_target, input_g_from_source, prob_target, prob_g_from_source, ad_net, random_layer)
-    prob_target = torch.nn.functional.softmax(prob_target, dim=1)
-    prob_g_from_source = torch.nn.functional.softmax(prob_g_from_source, dim=1)
-    if random_layer is None:
-        fusion_target = torch.bmm(prob_target.unsqueeze(2), input_target.unsqueeze(1))
-        target_out = ad_net(fusion_target.view(-1, input_target.size(1) * prob_target.size(1)))
-        fusion_source = torch.bmm(prob_g_from_source.unsqueeze(2), input_g_from_source.unsqueeze(1))
-        g_source_out = ad_net(fusion_source.view(-1, input_g_from_source.size(1) * prob_g_from_source.size(1)))
-    else:
-        fusion_target = random_layer.forward([input_target, prob_target])
-        target_out = ad_net(fusion_target.view(-1, fusion_target.size(1)))
-        fusion_source = random_layer.forward([input_g_from_source, prob_g_from_source])
-        g_source_out = ad_net(fusion_source.view(-1, fusion_source.size(1)))
-    entropy_target = Entropy(prob_target)
-    entropy_g_from_source = Entropy(prob_g_from_source)
-    coeff = ad_net.coeff
-    entropy_target.register_hook(grl_hook(coeff))
-    entropy_g_from_source.register_hook(grl_hook(coeff))
-    weight_target = 1.0 + torch.exp(-entropy_target)
-    weight_g_from_source = 1.0 + torch.exp(-entropy_g_from_source)
-    weight_target = weight_target / torch.sum(weight_target).detach()
-    weight_g_from_source = weight_g_from_source / torch.sum(weight_g_from_source).detach()
-    distance_target = torch.sum(weight_target * target_out)
-    distance_g_from_source = torch.sum(weight_g_from_source * g_source_out)
-    return distance_target - distance_g_from_source
+    if random_layer is None or random_layer.input_num != 2:
+        raise RuntimeError("CDAN: only the trainer's call shape is built -- a RandomLayer over (feature, class logits), "
+                           "train_and_test.py:76,594")
+    if prob_target.shape[1] > 32 or random_layer.output_dim > 8192 or input_target.shape != input_g_from_source.shape:
+        raise RuntimeError(f"CDAN: unsupported shape (classes {prob_target.shape[1]} > 32, projection width "
+                           f"{random_layer.output_dim} > 8192, or feature shapes {tuple(input_target.shape)} != "
+                           f"{tuple(input_g_from_source.shape)})")
+    return _cdan_fused(input_target, input_g_from_source, prob_target, prob_g_from_source, ad_net, random_layer)

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <mutex>
 #include "../../include/tsc_b200.h"
 
 namespace tsc {
@@ -52,6 +53,18 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// One-time, thread-safe opt-in of a kernel to the full 227 KB of dynamic shared memory (function attributes are process
+// state: this is the only host-side state the launch wrappers keep besides the geometry caches, both behind a lock).
+struct OnceAttr {
+    std::once_flag flag;
+    cudaError_t err = cudaSuccess;
+};
+template <typename F>
+static inline cudaError_t run_once(OnceAttr& o, F&& f) {
+    std::call_once(o.flag, [&] { o.err = f(); });
+    return o.err;
 }
 
 static inline int pad16(int c) { return (c + 15) & ~15; }

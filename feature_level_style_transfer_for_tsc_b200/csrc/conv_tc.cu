@@ -768,14 +768,16 @@ int osconv_tc(int direction, const void* x, int dtype, const void* w, const void
     CUtensorMap xmap;
     if (make_c8_map(&xmap, x, B, p.kc, L, p.Rp, p.kc) != 0) return -1;
     const int smem = p.off_stages + ns * slot;
-    static bool attr_set = false;          // once per process: opt in to the full 227 KB of dynamic shared memory
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(osconv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(osconv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(osconv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(osconv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    static OnceAttr attr_once;             // once per process: opt in to the full 227 KB of dynamic shared memory
+    {
+        const cudaError_t e = run_once(attr_once, [] {
+            cudaError_t r = cudaFuncSetAttribute(osconv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(osconv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(osconv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(osconv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            return r;
+        });
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-        attr_set = true;
     }
     {
         // the instrumented instantiation only when a timeline buffer or an experiment knob is set

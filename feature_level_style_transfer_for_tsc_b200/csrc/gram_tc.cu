@@ -451,12 +451,14 @@ int gram_fwd_tc(const float* a, const float* s, float* D, float* loss, float* ws
     p.inv_cl = 1.f / ((float)C * (float)L);
     p.tl = g_gram_timeline;
     const int smem = GR_HDR + ns * stage_bytes;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gram_fwd_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(gram_fwd_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    static OnceAttr attr_once;
+    {
+        const cudaError_t e = run_once(attr_once, [] {
+            cudaError_t r = cudaFuncSetAttribute(gram_fwd_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(gram_fwd_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            return r;
+        });
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-        attr_set = true;
     }
     if (C * (GR_KC / 4) <= 5 * 128)
         gram_fwd_tc_kernel<5><<<B, GR_THREADS, smem, cs>>>(p);
@@ -483,11 +485,12 @@ int gram_bwd_tc(const float* D, const float* a, const float* s, const float* dlo
     p.NS = ns;
     p.tmem_cols = p.Rp / 128 == 1 ? 256 : 512;
     const int smem = GR_HDR + ns * stage_bytes;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gram_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    static OnceAttr attr_once;
+    {
+        const cudaError_t e = run_once(attr_once, [] {
+            return cudaFuncSetAttribute(gram_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        });
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-        attr_set = true;
     }
     gram_bwd_tc_kernel<<<dim3(B, cdiv(L, 128)), GR_THREADS, smem, cs>>>(p);
     TSC_LAUNCH_CHECK();

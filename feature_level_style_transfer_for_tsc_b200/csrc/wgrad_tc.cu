@@ -341,11 +341,12 @@ int oswgrad_tc(const void* dy, const void* x, int dtype, float* dW, void* worksp
     TSC_REQUIRE(smem <= 227 * 1024, "wgrad shape needs %d B of shared memory: unsupported", smem);
     p.dy = (const __nv_bfloat16*)dy;
     p.x = (const __nv_bfloat16*)x;
-    static bool attr_set = false;          // once per process: opt in to the full 227 KB of dynamic shared memory
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(oswgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    static OnceAttr attr_once;             // once per process: opt in to the full 227 KB of dynamic shared memory
+    {
+        const cudaError_t e = run_once(attr_once, [] {
+            return cudaFuncSetAttribute(oswgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        });
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-        attr_set = true;
     }
     { cudaError_t le = launch_pdl(oswgrad_tc_kernel, dim3(items.n, p.S), dim3(WG_THREADS), (size_t)smem, cs, items, p); if (le != cudaSuccess) { set_error("oswgrad launch: %s", cudaGetErrorString(le)); return (int)le; } }
     TSC_LAUNCH_CHECK();

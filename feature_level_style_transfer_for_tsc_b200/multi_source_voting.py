@@ -16,7 +16,7 @@ from typing import List, Sequence, Tuple
 import torch
 
 from . import ops
-from .utils import GraphedPredictor
+from .utils import _predictor_for
 
 ENTROPY_GAIN = 120.0       # multi_source_voting.py:387
 WEIGHT_BASE = 9.0          # :387 np.power(9, weight)
@@ -25,7 +25,7 @@ WEIGHT_BASE = 9.0          # :387 np.power(9, weight)
 def collect_logits(modules, dataloader) -> Tuple[torch.Tensor, torch.Tensor]:
     """(logits [N, K] fp32, labels [N] int64), both on the device, for a loader of (x, y) batches (:281-293)."""
     outs, labels = [], []
-    predict = GraphedPredictor(modules)
+    predict = _predictor_for(list(modules))
     with torch.no_grad():
         for _, (x, y) in enumerate(dataloader):
             x = x.float().cuda()

@@ -296,6 +296,12 @@ class Trainer:
             dist.broadcast(self.flat.flat_p, src=src, group=self.group)
             for t in self.model.buffers():
                 dist.broadcast(t.data, src=src, group=self.group)
+            # RandomLayer keeps its projections as a plain tensor list (as the reference does, C_DAN.py:15): neither
+            # parameters nor buffers, but every rank must train the shared critic against the SAME projections
+            for m in self.model.modules():
+                if isinstance(m, RandomLayer):
+                    for t in m.random_matrix:
+                        dist.broadcast(t, src=src, group=self.group)
 
     def _fwd_bwd(self, *inputs):
         self.flat.zero_grad()
@@ -315,6 +321,16 @@ class Trainer:
             if counters:
                 torch._foreach_add_(counters, 1)          # one launch for every BatchNorm's num_batches_tracked
             out["loss"].backward()
+            # direct_grads: the wgrad / BatchNorm-backward kernels of the side branches wrote into the flat bucket on their
+            # own streams and reported None to autograd -- order the all-reduce / optimizer behind them explicitly instead
+            # of relying on autograd's end-of-backward leaf-stream synchronisation
+            cur = torch.cuda.current_stream()
+            for m in self.model.modules():
+                st = getattr(m, "_side_stream", None)
+                if st is not None:
+                    cur.wait_stream(st)
+                for st in (getattr(m, "_streams", None) or []):
+                    cur.wait_stream(st)
         finally:
             OSM.defer_batch_counters(False)
             TF.set_direct_grads(prev)

@@ -56,8 +56,10 @@ USE_GRAPHS = True       # replay one CUDA graph per batch shape in the evaluatio
 
 
 class GraphedPredictor:
-    """``predict_logits`` behind one CUDA graph per (batch shape, train/eval mode): an evaluation pass at the reference's
-    loader batch of 20 series is launch-bound when run eagerly.  The graph contains the pack kernel and the convolutions
+    """``predict_logits`` behind one CUDA graph per batch shape, for module chains that are entirely in eval mode: an
+    evaluation pass at the reference's loader batch of 20 series is launch-bound when run eagerly.  A chain with any module
+    in training mode runs eagerly (a captured training-mode pass would replay its warm-up's running-statistics updates,
+    and ``momentum=None`` BatchNorm reads its counter on the host).  The graph contains the pack kernel and the convolutions
     derive the BatchNorm coefficients in their prologue, so it reads the live parameters and running statistics: a
     checkpoint loaded or a training step taken between two calls is seen by the next replay.  The returned logits are a
     static buffer, valid until the next call."""
@@ -68,10 +70,10 @@ class GraphedPredictor:
         self._graphs = {}
 
     def __call__(self, x):
-        if not self.enabled or not x.is_cuda:
+        if not self.enabled or not x.is_cuda or any(m.training for mod in self.modules for m in mod.modules()):
             with torch.no_grad():
                 return predict_logits(self.modules, x)
-        key = (tuple(x.shape), tuple(bool(m.training) for mod in self.modules for m in mod.modules()))
+        key = tuple(x.shape)
         ent = self._graphs.get(key)
         if ent is None:
             static_x = x.clone()
@@ -91,13 +93,27 @@ class GraphedPredictor:
         return static_out
 
 
+_PREDICTORS = {}
+
+
+def _predictor_for(modules) -> GraphedPredictor:
+    """One predictor (and so one set of captured graphs) per module chain, kept across calls: the evaluation helpers
+    run every few epochs on the same modules (train_and_test.py:783-789)."""
+    import weakref
+    key = tuple(id(m) for m in modules)
+    ent = _PREDICTORS.get(key)
+    if ent is None or any(r() is not m for r, m in zip(ent[0], modules)):
+        ent = _PREDICTORS[key] = ([weakref.ref(m) for m in modules], GraphedPredictor(modules))
+    return ent[1]
+
+
 def loader_accuracy(modules, dataloader, with_nvidia=True):
     """accuracy over a loader of (x, y) batches; returns (accuracy, n_series)."""
     if not with_nvidia:
         raise RuntimeError("the tsc_b200 modules have no CPU path (with_nvidia=False)")
     total = None
     n = 0
-    predict = GraphedPredictor(modules)
+    predict = _predictor_for(list(modules))
     with torch.no_grad():
         for _, (x, y) in enumerate(dataloader):
             x = x.float().cuda()

@@ -28,27 +28,24 @@ class DimensionUnification(nn.Module):
         return self.relu2(torch.matmul(conv.weight.squeeze(-1), h) + conv.bias[:, None])
 
 
-def grl_hook(coeff):
-    def fun1(grad):
-        return -coeff * grad.clone()
-    return fun1
-
-
 def calc_coeff(iter_num, high=1.0, low=0.0, alpha=2.0, max_iter=50.0):
-    """reference widgets.py:12-13"""
-    return float(2.0 * (high - low) / (1.0 + np.exp(-alpha * iter_num / max_iter)) - (high - low) + low)
+    """Warm-up of the gradient-reversal strength: a sigmoid ramp from ``low`` (iteration 0) towards ``high``
+    (reference widgets.py:12-13, there with the removed ``np.float``)."""
+    ramp = 2.0 / (1.0 + np.exp(-alpha * iter_num / max_iter)) - 1.0
+    return float(low + (high - low) * ramp)
+
+
+def _reverse_gradient(x, coeff):
+    """Identity forward, ``-coeff * grad`` backward (the reference registers a hook, widgets.py:8-10,121-122)."""
+    if x.requires_grad:
+        x.register_hook(lambda grad: grad * (-coeff))
+    return x
 
 
 def init_weights(m):
-    """reference widgets.py:82-92"""
-    classname = m.__class__.__name__
-    if classname.find('Conv2d') != -1 or classname.find('ConvTranspose2d') != -1:
-        nn.init.kaiming_uniform_(m.weight)
-        nn.init.zeros_(m.bias)
-    elif classname.find('BatchNorm') != -1:
-        nn.init.normal_(m.weight, 1.0, 0.02)
-        nn.init.zeros_(m.bias)
-    elif classname.find('Linear') != -1:
+    """Initialisation of the critic (reference widgets.py:82-92; of its three branches only the ``Linear`` one can
+    fire for ``AdversarialNetworkforCDAN``): Xavier-normal weight, zero bias.  Consumes the RNG like the reference."""
+    if isinstance(m, nn.Linear):
         nn.init.xavier_normal_(m.weight)
         nn.init.zeros_(m.bias)
 
@@ -114,7 +111,4 @@ class AdversarialNetworkforCDAN(nn.Module):
 
     def forward(self, x):
         coeff = self._advance()
-        x = x * 1.0
-        if x.requires_grad:
-            x.register_hook(grl_hook(coeff))
-        return self.critic(x)
+        return self.critic(_reverse_gradient(x * 1.0, coeff))

@@ -11,8 +11,11 @@
  * Conventions (all functions):
  *   - plain pointers and sizes only; every buffer (incl. workspace) is owned by the caller;
  *     device pointers unless the parameter is documented as HOST;
- *   - no allocation, no host synchronisation, no global mutable state: safe to capture in a
- *     CUDA graph, reentrant across streams and threads;
+ *   - no allocation and no host synchronisation: safe to capture in a CUDA graph.  Host-side state
+ *     is limited to (a) one-time kernel attribute opt-ins (std::call_once), (b) per-bank geometry /
+ *     schedule caches behind a mutex, (c) debug hooks that are inert unless switched on explicitly
+ *     (tsc_debug_set_timeline, the TSC_CONV_* environment knobs read once): calls are reentrant
+ *     across streams and threads, on ONE device per process (one process per GPU);
  *   - `stream` is a cudaStream_t passed as void*;
  *   - return 0 = OK; < 0 = bad argument / unsupported shape (text via tsc_last_error(), thread
  *     local); > 0 = a cudaError_t from the launch.  Nothing throws, nothing aborts;
@@ -36,7 +39,10 @@ extern "C" {
 
 #define TSC_VERSION 100
 #define TSC_MAX_TAPS 96          /* largest supported Kmax (reference caps it at 89, train_and_test.py:40) */
-#define TSC_MAX_CHANNELS 256     /* largest padded channel count of one OS layer (reference: <= 228) */
+#define TSC_MAX_CHANNELS 256     /* largest padded channel count of one OS layer = one TMEM accumulator tile.  The reference's
+                                  * layer recipe (train_and_test.py:38-53) gives 228 at L >= 124 but MORE for short series
+                                  * (336 at L = 64, 560 at L = 32): such layers are rejected with an error (documented limit,
+                                  * DESIGN.md section 6) */
 #define TSC_MAX_OPT_GROUPS 32    /* parameter groups of one tsc_rmsprop_step call */
 #define TSC_MAX_LIST 32          /* tensors of one tsc_multi_l2norm call */
 #define TSC_MAX_CLASSES 64       /* classes of the voting kernels */

@@ -192,6 +192,19 @@ def init_classifier(lpl: List[LayerParams], n_class: int) -> "OrderedDict[str, t
 DENSE_WGRAD = False     # True: d/dW as the reference's autograd returns it, see masked_conv
 
 
+_MASKS = {}
+
+
+def _mask_on(layer: LayerParams, like: torch.Tensor) -> torch.Tensor:
+    """The layer's 0/1 mask on ``like``'s device and dtype -- kept, as the reference keeps ``weight_mask`` as a module
+    attribute (OS_CNN.py:55-58), so that the timed baselines do not rebuild it every call."""
+    key = (tuple(map(tuple, layer)), str(like.device), like.dtype)
+    m = _MASKS.get(key)
+    if m is None:
+        m = _MASKS[key] = torch.from_numpy(build_mask(layer)).to(device=like.device, dtype=like.dtype)
+    return m
+
+
 def masked_conv(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, layer: LayerParams) -> torch.Tensor:
     """OS_CNN.py:68-71: W*mask, ConstantPad1d((Kmax-1)//2, Kmax//2), Conv1d.
 
@@ -201,7 +214,7 @@ def masked_conv(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, layer: LayerP
     ``W * mask`` but the gradient passes straight to ``W``, which is what GradNorm's norms see
     (train_and_test.py:683-690)."""
     g = bank_geometry(layer)
-    mask = torch.from_numpy(build_mask(layer)).to(w.dtype)
+    mask = _mask_on(layer, w)
     xp = F.pad(x, (g["pad_l"], g["pad_r"]))
     wm = w + (w * mask - w).detach() if DENSE_WGRAD else w * mask
     return F.conv1d(xp, wm, b)

@@ -33,19 +33,26 @@ def _mirror_from_golden(z, hidden):
     return rl, ad.cuda()
 
 
-@pytest.mark.parametrize("fused", [True, False])
-def test_cdan_matches_the_reference_vectors(T, tables, cdan_small, fused):
+def test_cdan_matches_the_reference_vectors(T, tables, cdan_small):
     """Three consecutive calls (two training-mode, one eval-mode: the reversal schedule moves 0 -> 0.9866 -> ~1) on the
-    reference's seeded inputs: loss, input gradients, critic gradients.  fused=False is the generic (any-view) route."""
+    reference's seeded inputs: loss, input gradients, critic gradients."""
     from feature_level_style_transfer_for_tsc_b200 import C_DAN
     z = cdan_small
     t = tables["cdan_small"]
     rl, ad = _mirror_from_golden(z, t["hidden"])
-    C_DAN.FUSED = fused
-    try:
-        _run_calls(C_DAN, z, t, rl, ad)
-    finally:
-        C_DAN.FUSED = True
+    _run_calls(C_DAN, z, t, rl, ad)
+
+
+def test_cdan_rejects_every_other_call_shape(T):
+    """No alternate route: the outer-product form (random_layer=None) and other view counts raise."""
+    from feature_level_style_transfer_for_tsc_b200 import C_DAN
+    from feature_level_style_transfer_for_tsc_b200.widgets import AdversarialNetworkforCDAN
+    ad = AdversarialNetworkforCDAN(1024, 8).cuda()
+    f, l = torch.zeros(2, 3, 4, device="cuda"), torch.zeros(2, 3, device="cuda")
+    with pytest.raises(RuntimeError):
+        C_DAN.CDAN(f, f, l, l, ad, None)
+    with pytest.raises(RuntimeError):
+        C_DAN.CDAN(f, f, l, l, ad, C_DAN.RandomLayer([12], with_nvidia=False).cuda())
 
 
 def _run_calls(C_DAN, z, t, rl, ad):

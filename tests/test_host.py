@@ -3,6 +3,7 @@ import ctypes
 import os
 import re
 
+import numpy as np
 import pytest
 import torch
 
@@ -136,9 +137,11 @@ def test_cdan_mirror_interface():
     assert list(ad.state_dict()) == ["ad_layer1.weight", "ad_layer1.bias", "ad_layer2.weight", "ad_layer2.bias",
                                      "ad_layer3.weight", "ad_layer3.bias"]
     assert float(ad.ad_layer1.bias.abs().max()) == 0.0 and (ad.iter_num, ad.alpha, ad.max_iter) == (-1, 100.0, 20.0)
-    assert C_DAN.calc_coeff(1, 1.0, 0.0, 100.0, 20.0) == widgets.calc_coeff(1, 1.0, 0.0, 100.0, 20.0)
-    with pytest.raises(RuntimeError):
+    assert abs(widgets.calc_coeff(1, 1.0, 0.0, 100.0, 20.0) - (2.0 / (1.0 + np.exp(-5.0)) - 1.0)) < 1e-15
+    with pytest.raises(RuntimeError):        # no CPU path
         C_DAN.CDAN(torch.zeros(2, 3, 4), torch.zeros(2, 3, 4), torch.zeros(2, 3), torch.zeros(2, 3), ad, rl)
+    with pytest.raises(RuntimeError):        # no stand-alone torch route of the projection
+        rl([torch.zeros(2, 12), torch.zeros(2, 3)])
 
 
 def test_default_engine_is_the_tensor_core_path_for_every_family():
