@@ -192,6 +192,41 @@ def init_classifier(lpl: List[LayerParams], n_class: int) -> "OrderedDict[str, t
 DENSE_WGRAD = False     # True: d/dW as the reference's autograd returns it, see masked_conv
 
 
+OPERAND_ROUND = None    # e.g. torch.bfloat16: emulate an engine that rounds the convolution OPERANDS (see _RoundedConv)
+
+
+def _q(t: torch.Tensor) -> torch.Tensor:
+    return t.to(OPERAND_ROUND).to(t.dtype)
+
+
+class _RoundedConv(torch.autograd.Function):
+    """The masked convolution with its operands rounded to ``OPERAND_ROUND`` at exactly the points where a low-precision
+    tensor-core engine rounds them, everything else (accumulation, BatchNorm, reductions) in the working precision:
+
+      forward : y  = conv(q(x), q(W * mask)) + b
+      backward: dX = dgrad(q(dY), q(W * mask));  dW = wgrad(q(dY), q(x)) * mask;  db = sum dY     (straight-through in q)
+
+    With float64 working precision this isolates the effect of the operand rounding alone: a bf16 engine must agree with
+    it far more closely than with the exact oracle (tests/test_gpu_fullsize.py)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, mask, pad_l, pad_r):
+        xq = F.pad(_q(x), (pad_l, pad_r))
+        wq = _q(w * mask)
+        ctx.save_for_backward(xq, wq, mask)
+        ctx.pads = (pad_l, pad_r, x.shape[-1])
+        return F.conv1d(xq, wq, b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xq, wq, mask = ctx.saved_tensors
+        pad_l, pad_r, L = ctx.pads
+        dyq = _q(dy)
+        dx = torch.nn.grad.conv1d_input(xq.shape, wq, dyq)[..., pad_l:pad_l + L]
+        dw = torch.nn.grad.conv1d_weight(xq, wq.shape, dyq) * mask
+        return dx, dw, dy.sum(dim=(0, 2)), None, None, None
+
+
 _MASKS = {}
 
 
@@ -215,6 +250,8 @@ def masked_conv(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, layer: LayerP
     (train_and_test.py:683-690)."""
     g = bank_geometry(layer)
     mask = _mask_on(layer, w)
+    if OPERAND_ROUND is not None:
+        return _RoundedConv.apply(x, w, b, mask, g["pad_l"], g["pad_r"])
     xp = F.pad(x, (g["pad_l"], g["pad_r"]))
     wm = w + (w * mask - w).detach() if DENSE_WGRAD else w * mask
     return F.conv1d(xp, wm, b)
@@ -259,7 +296,11 @@ def extractor_forward(sd, lpl: List[LayerParams], x: torch.Tensor, training: boo
     for i, layer in enumerate(lpl):
         h = os_layer(h, sd, f"net_1.net.net.{i}.", layer, relu=(i != len(lpl) - 1),
                      training=training, update_running=update_running)
-    r = F.conv1d(x, sd["net_1.res.conv1d.weight"], sd["net_1.res.conv1d.bias"])   # kernel 1, pad (0,0)
+    if OPERAND_ROUND is not None:
+        wr = sd["net_1.res.conv1d.weight"]
+        r = _RoundedConv.apply(x, wr, sd["net_1.res.conv1d.bias"], torch.ones_like(wr), 0, 0)
+    else:
+        r = F.conv1d(x, sd["net_1.res.conv1d.weight"], sd["net_1.res.conv1d.bias"])   # kernel 1, pad (0,0)
     r = batch_norm(r, sd, "net_1.res.bn.", training, update_running)
     return F.relu(r + h)
 
