@@ -1,0 +1,731 @@
+// tcgen05 engine, forward / dgrad, second generation: the omni-scale convolution as a PERSISTENT implicit GEMM.
+//
+//   positions (128 per tile)  -> MMA M   (accumulator rows = TMEM lanes)
+//   output channels (<= 256)  -> MMA N   (the whole channel axis is one accumulator tile in TMEM)
+//   (tap, input channel)      -> MMA K   (16 channels per instruction)
+//
+// What changed against conv_tc.cu (round 1), and why (profiles/README.md, rounds 1-2):
+// * The issuing warp was bound by its own instruction count (~70 SASS instructions per four MMAs: plan entries loaded from
+//   shared memory into vector registers, 17 R2UR per group).  Here the schedule is a table of per-tap RUNS in the kernel
+//   parameter block (constant bank): the whole issue loop runs in the UNIFORM datapath -- LDCU for the run, UIADD3 for the
+//   two descriptor words that change per MMA -- about six uniform instructions per MMA and no R2UR.  For that the warp's
+//   control flow must be provably uniform: every mbarrier wait is a vote (`__all_sync` of try_wait), and nothing a run needs is
+//   modified inside the elected-lane region.
+// * One CTA walks several position tiles (grid = min(tiles, SMs)); the accumulator tile and the activation tile are
+//   double-buffered (2 x <=256 TMEM columns, two shared-memory tiles), so the epilogue of tile i and the TMA load of tile
+//   i+2 overlap the MMAs of tile i+1.  With one tile per CTA (cfg2: 128 tiles) it degenerates to the single-buffered
+//   layout that fits half an SM, so that CTAs of two streams stay co-resident.
+// * No padding MMAs and no plan relocation pass: a weight stage holds whole MMAs of consecutive runs.
+//
+// Unchanged: the c8 activation tile with halo staged by ONE TMA box load (out-of-bounds rows zero-filled = ConstantPad1d,
+// OS_CNN.py:59,70), a tap = "+ t rows" on the A descriptor; the packed bank (live (channel, tap) pairs only) streamed through a
+// ring of shared-memory stages by 1-D bulk copies; per tap the MMA covers the live channel suffix only; the epilogues (bias,
+// BatchNorm partial statistics, dgrad ReLU mask + BatchNorm-backward partial sums, inference affine) of conv_tc.cu.
+// Replaces ConstantPad1d + Conv1d (+ cuDNN dgrad), OS_CNN/OS_CNN.py:70-71; arithmetic SURVEY A1/A2.
+#include "tc_common.cuh"
+#include <stdlib.h>
+#include <string.h>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+namespace tsc {
+namespace tc {
+
+static constexpr int C2_THREADS = 192;
+static constexpr int C2_MAX_RUNS = 352;
+static constexpr int C2_MAX_STAGES = 256;
+static constexpr int C2_STAGE_BYTES = 32 * 1024;
+static constexpr int C2_HDR = 256;
+static constexpr uint32_t RF_FIRST = 1u << 16, RF_LAST = 1u << 17, RF_INIT = 1u << 18;
+
+// One run = consecutive K steps of one tap inside one weight stage.
+//   x: A start (16 B units from the activation tile base) of the first K step
+//   y: B start inside the stage (16 B units) | live channels nt << 16 (= the descriptor's leading-dimension field)
+//   z: instruction descriptor (M = 128, N = nt, bf16 x bf16 -> f32, both K-major)
+//   w: TMEM column [0,9) | K steps << 9 [9,16) | RF_FIRST: opens its weight stage | RF_LAST: closes it | RF_INIT: overwrites
+struct ConvSched {
+    int n_runs, n_stages, stage_bytes, pad;
+    uint4 runs[C2_MAX_RUNS];
+    uint2 stages[C2_MAX_STAGES];      // {source offset in 16 B units, bytes}
+};
+
+struct Conv2Params {
+    const __nv_bfloat16* w;
+    const float* bias;
+    float* y;
+    // fused epilogues (all nullable) -- see tsc_conv_epilogue in include/tsc_b200.h
+    float* stat_partial;       // FWD : [tiles][np] float2 (mean, M2) over the tile's valid rows
+    const float* mask_y;       // DGRAD: pre-BN output of the layer below, c8 fp32 [B][np/8][L][8]
+    const float* mask_scale;   //        z = scale*y + shift; d = dz * [z > 0]   (NULL = no ReLU)
+    const float* mask_shift;
+    const float* mask_mean;    //        yhat = (y - mean) * invstd
+    const float* mask_invstd;
+    float* red_partial;        // DGRAD: [tiles][np] float2 (S1, S2) partial sums over the tile's valid rows
+    const float* aff_scale;    // FWD, inference: z = act(aff_scale * (acc + bias) + aff_shift [+ aff_res]) -> aff_out
+    const float* aff_shift;
+    const float* bn_gamma; const float* bn_beta; const float* bn_mean; const float* bn_var; float bn_eps;
+    const float* aff_res;
+    void* aff_out;
+    int aff_kind, aff_relu;
+    int nbias, B, L, ltiles, n_tiles;
+    int tiles_base, tiles_rem;     // n_tiles = tiles_base * grid + tiles_rem
+    int np;            // padded output channels of this direction
+    int Rp;            // halo rows of the activation tile (multiple of 8)
+    int kc;            // input-channel chunks of 8
+    int pad_left;
+    int NS;            // weight stages in the ring
+    int nx, na;        // activation tiles / accumulator tiles (1 or 2)
+    int acc_stride;    // TMEM columns per accumulator tile
+    int tmem_cols;
+    int off_bias, off_wstat, off_xs, off_stages, x_bytes;
+    long long* tl;     // optional phase timeline of CTA 0 (tsc_debug_set_timeline), NULL in production
+    int debug;         // experiments only (TSC_C2_DEBUG; garbage results): 1 = the producer signals its stages full without copying
+};
+
+#define TL2(i) do { if (p.tl && blockIdx.x == 0) p.tl[i] = clock64(); } while (0)
+
+// warp-uniform bounded wait: all 32 lanes poll and the loop branch is a vote, so the warp's control flow stays uniform
+// (the issue loop then lives in uniform registers).  false = timed out (watchdog).
+__device__ __forceinline__ bool mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1
+    for (uint32_t i = 0; i < (1u << 22); ++i) {
+        if (__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) return true;
+    }
+    return false;
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Column sums over the 32 lanes of a warp for 32 columns held one per register: a transposing butterfly.
+// On return lane j holds the sum over all lanes of v[j] (31 shuffles instead of 160).
+__device__ __forceinline__ float colsum32(float* v, int lane) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int j = 0; j < o; ++j) {
+            const float send = up ? v[j] : v[j + o];
+            const float keep = up ? v[j + o] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    return v[0];
+}
+
+template <bool AFF>
+__global__ void __launch_bounds__(C2_THREADS, AFF ? 2 : 1)
+osconv2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ ConvSched S, const __grid_constant__ Conv2Params p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);            // [8]  weight stage filled
+    uint64_t* empty = full + 8;                                    // [8]  weight stage consumed
+    uint64_t* x_full = empty + 8;                                  // [2]  activation tile landed
+    uint64_t* x_empty = x_full + 2;                                // [2]  ... consumed by the tile's MMAs
+    uint64_t* acc_full = x_empty + 2;                              // [2]  accumulator tile complete
+    uint64_t* acc_empty = acc_full + 2;                            // [2]  ... drained by the epilogue
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    float* bias_s = reinterpret_cast<float*>(smem + p.off_bias);
+    float2* wstat = reinterpret_cast<float2*>(smem + p.off_wstat);  // [4][np]
+    uint8_t* xs = smem + p.off_xs;
+    uint8_t* stages = smem + p.off_stages;
+
+    // the warp index as a shuffle broadcast: ptxas cannot know that threadIdx.x >> 5 is the same in all lanes (it does not know
+    // the block shape), and without that knowledge every role branch is a potentially divergent one -- the issuing warp's votes
+    // get BRA.DIV guards and its loop falls back to vector registers + R2UR (SASS inspected)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const int np = p.np;
+    // tiles of this CTA (tile = blockIdx.x + j * gridDim.x); no division here: the issuing warp's loop bounds must stay in the
+    // uniform datapath
+    const int n_my = p.tiles_base + ((int)blockIdx.x < p.tiles_rem ? 1 : 0);
+    const int slot_bytes = S.stage_bytes;
+
+    if (warp == 0 && lane == 0) {
+        TL2(0);
+        tma_prefetch_desc(&xmap);
+        for (int i = 0; i < p.NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1);
+            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    if (warp >= 2) {
+        pdl_wait();
+        // per-channel epilogue constants -> shared memory: [0] bias | mask scale, [1] mask shift, [2] mean, [3] invstd
+        for (int c = threadIdx.x - 64; c < np; c += 128) {
+            if (p.red_partial) {
+                bias_s[c] = p.mask_scale ? __ldg(p.mask_scale + c) : 0.f;        // no ReLU below: z = 0*y + 1 > 0
+                bias_s[np + c] = p.mask_scale ? __ldg(p.mask_shift + c) : 1.f;
+                bias_s[2 * np + c] = __ldg(p.mask_mean + c);
+                bias_s[3 * np + c] = __ldg(p.mask_invstd + c);
+            } else {
+                bias_s[c] = (p.bias && c < p.nbias) ? __ldg(p.bias + c) : 0.f;
+                if (AFF) {
+                    if (p.aff_scale) {
+                        bias_s[np + c] = __ldg(p.aff_scale + c);
+                        bias_s[2 * np + c] = __ldg(p.aff_shift + c);
+                    } else if (c < p.nbias) {
+                        // eval-mode BatchNorm1d (OS_CNN.py:72 in .eval()): the arithmetic of bn_eval_coeffs_kernel
+                        const float sc = __ldg(p.bn_gamma + c) * (1.f / sqrtf(__ldg(p.bn_var + c) + p.bn_eps));
+                        bias_s[np + c] = sc;
+                        bias_s[2 * np + c] = __ldg(p.bn_beta + c) - __ldg(p.bn_mean + c) * sc;
+                    } else {
+                        bias_s[np + c] = 0.f;
+                        bias_s[2 * np + c] = 0.f;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== copy producer (one thread): activation tiles by TMA, the packed bank by one bulk copy per stage =====
+        if (lane == 0) {
+            bool dead = false;
+            pdl_wait();
+            TL2(1);
+            const int nx = p.nx;
+            auto load_x = [&](int k) {
+                const int xb = k & (nx - 1), use = nx == 2 ? (k >> 1) : k;
+                if (use > 0) mbar_wait(&x_empty[xb], (uint32_t)((use - 1) & 1), dead, 10);
+                const int tile = (int)blockIdx.x + k * (int)gridDim.x;
+                const int b = tile / p.ltiles, l0 = (tile - b * p.ltiles) * 128;
+                mbar_arrive_expect_tx(&x_full[xb], (uint32_t)p.x_bytes);
+                tma_load_4d(xs + (size_t)xb * p.x_bytes, &xmap, 0, l0 - p.pad_left, 0, b, &x_full[xb]);
+            };
+            load_x(0);
+            uint32_t s = 0, ph = 0;
+            const int n_stages = S.n_stages;
+            for (int j = 0; j < n_my; ++j) {
+                if (nx == 2 && j + 1 < n_my) load_x(j + 1);
+                for (int i = 0; i < n_stages; ++i) {
+                    const uint2 e = S.stages[i];
+                    mbar_wait(&empty[s], ph ^ 1u, dead, 1);
+                    if (p.debug & 1) { mbar_arrive(&full[s]); if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; } continue; }
+                    mbar_arrive_expect_tx(&full[s], e.y);
+                    bulk_load(stages + (size_t)s * slot_bytes, reinterpret_cast<const uint8_t*>(p.w) + (size_t)e.x * 16, e.y, &full[s]);
+                    if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; }
+                }
+                if (nx == 1 && j + 1 < n_my) load_x(j + 1);       // a single tile buffer: reload behind the tile's own stages
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: the whole warp walks the run table in lock-step, in uniform registers; one elected lane issues =====
+        bool ok = true;
+        const uint32_t desc_hi = (128u >> 4) | (1u << 14);                        // SBO = 128 B, descriptor version 1
+        const uint32_t xs16 = smem_u32(xs) >> 4;
+        const uint32_t a_lbo = (uint32_t)p.Rp << 16;                               // LBO = Rp * 16 B (the two 8-channel K groups)
+        const uint32_t a_step = 2u * (uint32_t)p.Rp;                               // one K step = two chunks further
+        const uint32_t st16 = smem_u32(stages) >> 4;
+        const uint32_t slot16 = (uint32_t)slot_bytes >> 4;
+        const uint32_t x16 = (uint32_t)p.x_bytes >> 4;
+        const int n_runs = S.n_runs;
+        const int nx = p.nx, na = p.na;
+        uint32_t s = 0, ph = 0;
+        for (int j = 0; j < n_my; ++j) {
+            const uint32_t xb = (uint32_t)j & (uint32_t)(nx - 1), xuse = nx == 2 ? ((uint32_t)j >> 1) : (uint32_t)j;
+            const uint32_t ab = (uint32_t)j & (uint32_t)(na - 1), ause = na == 2 ? ((uint32_t)j >> 1) : (uint32_t)j;
+            ok = mbar_wait_warp(&x_full[xb], xuse & 1u) && ok;
+            if (ause > 0) ok = mbar_wait_warp(&acc_empty[ab], (ause - 1u) & 1u) && ok;
+            tc_fence_after();
+            if (j == 0) TL2(2);                   // (all lanes store: a lane-dependent branch here would cost the loop its uniformity)
+            const uint32_t a_base = (xs16 + xb * x16) | a_lbo;
+            const uint32_t d_base = tmem_base + ab * (uint32_t)p.acc_stride;
+#pragma unroll 1
+            for (int r = 0; r < n_runs; ++r) {
+                const uint4 e = S.runs[r];
+                if (e.w & RF_FIRST) ok = mbar_wait_warp(&full[s], ph) && ok;
+                uint32_t a = a_base + e.x;
+                uint32_t b = (st16 + s * slot16) + e.y;
+                const uint32_t b_step = (e.y >> 16) * 2u;
+                const int ks = (int)((e.w >> 9) & 0x7fu);
+                const uint32_t d = d_base + (e.w & 0x1ffu);
+                const uint32_t accf = (e.w & RF_INIT) ? 0u : 1u;
+                if (elect_one()) {
+#pragma unroll 1
+                    for (int k = 0; k < ks; ++k) {
+                        umma_bf16(d, ((uint64_t)desc_hi << 32) | a, ((uint64_t)desc_hi << 32) | b, e.z, accf);
+                        a += a_step;
+                        b += b_step;
+                    }
+                    if (e.w & RF_LAST) tc_commit(&empty[s]);      // frees the stage when these MMAs have read it
+                }
+                if (e.w & RF_LAST) { if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; } }
+            }
+            if (elect_one()) {
+                tc_commit(&acc_full[ab]);
+                tc_commit(&x_empty[xb]);
+            }
+        }
+        pdl_trigger();            // the next kernel of the stream may start its prologue while the last epilogue runs
+        TL2(4);
+        if (!ok && lane == 0) atomicCAS(&g_watchdog, 0, (3 << 16) | (int)(blockIdx.x & 0xffff));
+    } else {
+        // ===== epilogue: TMEM -> registers -> (+bias | mask | affine) -> global (+ per-tile partial reductions) =====
+        bool dead = false;
+        const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;
+        const int npc = np / 8;
+        const size_t chunk_stride = (size_t)p.L * 8;
+        const bool do_stat = p.stat_partial != nullptr;
+        const bool do_red = p.red_partial != nullptr;
+        constexpr bool do_aff = AFF;
+        const int na = p.na;
+        for (int j = 0; j < n_my; ++j) {
+            const int tile = (int)blockIdx.x + j * (int)gridDim.x;
+            const int b = tile / p.ltiles, l0 = (tile - b * p.ltiles) * 128;
+            const int l = l0 + row;
+            const bool valid = l < p.L;
+            const size_t row_off = ((size_t)b * npc * p.L + (size_t)(valid ? l : 0)) * 8;
+            float* ybase = p.y + row_off;
+            const float* mbase = do_red ? p.mask_y + row_off : nullptr;
+            const int ab = j & (na - 1), ause = na == 2 ? (j >> 1) : j;
+            const uint32_t t_acc = tmem_base + (uint32_t)(ab * p.acc_stride) + ((uint32_t)(q * 32) << 16);
+            // one thread polls the accumulator barrier; the other 127 sleep in a named barrier instead of spinning on
+            // mbarrier.try_wait next to the MMA issuer
+            if (threadIdx.x == 64) mbar_wait(&acc_full[ab], (uint32_t)(ause & 1), dead, 4);
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            tc_fence_after();
+            if (j == 0 && warp == 2 && lane == 0) TL2(5);
+            for (int c0 = 0; c0 < np; c0 += 32) {
+                float v[32];
+                const bool wide = c0 + 32 <= np;          // np is a multiple of 16: the tail chunk is 16 wide
+                if (wide) {
+                    tmem_ld32(t_acc + (uint32_t)c0, v);
+                } else {
+                    tmem_ld_x16(t_acc + (uint32_t)c0, v);
+#pragma unroll
+                    for (int i = 16; i < 32; ++i) v[i] = 0.f;
+                }
+                const int ng = wide ? 4 : 2;              // 8-channel groups in this chunk
+                if (!do_red) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        if (i < ng * 8) {
+                            const float4 bb = *reinterpret_cast<const float4*>(bias_s + c0 + i);
+                            v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
+                        }
+                    }
+                }
+                float yh[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) yh[i] = 0.f;
+                if (do_red) {
+                    // d = dz * [scale*y + shift > 0]; yhat = (y - mean) * invstd of the layer below
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        if (g < ng) {
+                            float yv[8];
+                            if (valid) {
+                                const float* src = mbase + (size_t)((c0 >> 3) + g) * chunk_stride;
+                                const float4 a0 = __ldg(reinterpret_cast<const float4*>(src));
+                                const float4 a1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+                                yv[0] = a0.x; yv[1] = a0.y; yv[2] = a0.z; yv[3] = a0.w; yv[4] = a1.x; yv[5] = a1.y; yv[6] = a1.z; yv[7] = a1.w;
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) yv[k] = 0.f;
+                            }
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const int c = c0 + g * 8 + k;
+                                const float z = fmaf(yv[k], bias_s[c], bias_s[np + c]);
+                                if (!(z > 0.f)) v[g * 8 + k] = 0.f;
+                                yh[g * 8 + k] = (yv[k] - bias_s[2 * np + c]) * bias_s[3 * np + c];
+                            }
+                        }
+                    }
+                }
+                if (do_aff) {
+                    // inference: eval-mode BatchNorm (+ shortcut branch) (+ ReLU) applied to the accumulators; the pre-BN y
+                    // never reaches HBM and the next layer's operand is written directly
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        if (g < ng) {
+                            float rv[8];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) rv[k] = 0.f;
+                            if (p.aff_res && valid) {
+                                const float* src = p.aff_res + row_off + (size_t)((c0 >> 3) + g) * chunk_stride;
+                                const float4 a0 = __ldg(reinterpret_cast<const float4*>(src));
+                                const float4 a1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+                                rv[0] = a0.x; rv[1] = a0.y; rv[2] = a0.z; rv[3] = a0.w; rv[4] = a1.x; rv[5] = a1.y; rv[6] = a1.z; rv[7] = a1.w;
+                            }
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const int c = c0 + g * 8 + k;
+                                float z = fmaf(v[g * 8 + k], bias_s[np + c], bias_s[2 * np + c]) + rv[k];
+                                if (p.aff_relu) z = fmaxf(z, 0.f);
+                                v[g * 8 + k] = z;
+                            }
+                        }
+                    }
+                    if (p.aff_kind == TSC_OUT_C8_BF16) {
+                        __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(p.aff_out) + row_off;
+                        if (valid) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                if (g < ng) {
+                                    uint4 raw;
+                                    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) h2[k] = __floats2bfloat162_rn(v[g * 8 + 2 * k], v[g * 8 + 2 * k + 1]);
+                                    *reinterpret_cast<uint4*>(ob + (size_t)((c0 >> 3) + g) * chunk_stride) = raw;
+                                }
+                            }
+                        }
+                    } else if (p.aff_kind == TSC_OUT_C8_F32) {
+                        float* of = reinterpret_cast<float*>(p.aff_out) + row_off;
+                        if (valid) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                if (g < ng) {
+                                    float* d0 = of + (size_t)((c0 >> 3) + g) * chunk_stride;
+                                    *reinterpret_cast<float4*>(d0) = make_float4(v[g * 8], v[g * 8 + 1], v[g * 8 + 2], v[g * 8 + 3]);
+                                    *reinterpret_cast<float4*>(d0 + 4) = make_float4(v[g * 8 + 4], v[g * 8 + 5], v[g * 8 + 6], v[g * 8 + 7]);
+                                }
+                            }
+                        }
+                    } else if (p.aff_kind == TSC_OUT_NCL_F32) {
+                        // [B][Cout][L]: the 32 lanes of a warp are 32 consecutive positions of one channel (128 B per store)
+                        float* on = reinterpret_cast<float*>(p.aff_out) + (size_t)b * p.nbias * p.L + (valid ? l : 0);
+                        if (valid) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (i < ng * 8 && c0 + i < p.nbias) on[(size_t)(c0 + i) * p.L] = v[i];
+                        }
+                    } else {
+                        // TSC_OUT_POOLED (one tile per sample, L <= 128): column sums over this warp's valid rows
+                        float s1[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) s1[i] = valid ? v[i] : 0.f;
+                        const float a = colsum32(s1, lane);
+                        if (c0 + lane < np) wstat[q * np + c0 + lane] = make_float2(a, 0.f);
+                    }
+                } else if (valid && p.y) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        if (g < ng) {
+                            float* d0 = ybase + (size_t)((c0 >> 3) + g) * chunk_stride;
+                            *reinterpret_cast<float4*>(d0) = make_float4(v[g * 8], v[g * 8 + 1], v[g * 8 + 2], v[g * 8 + 3]);
+                            *reinterpret_cast<float4*>(d0 + 4) = make_float4(v[g * 8 + 4], v[g * 8 + 5], v[g * 8 + 6], v[g * 8 + 7]);
+                        }
+                    }
+                }
+                if (do_red) {
+                    float s1[32], s2[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float x = valid ? v[i] : 0.f;
+                        s1[i] = x;
+                        s2[i] = x * yh[i];
+                    }
+                    const float a = colsum32(s1, lane);
+                    const float c = colsum32(s2, lane);
+                    if (c0 + lane < np) wstat[q * np + c0 + lane] = make_float2(a, c);
+                } else if (do_stat) {
+                    // two-pass per warp: column means first, then the centred sums of squares (no cancellation even when
+                    // |mean| >> std); lane j ends up with (sum, M2) of column c0 + j over this warp's valid rows
+                    const int nw = max(0, min(32, min(128, p.L - l0) - q * 32));
+                    float s1[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) s1[i] = valid ? v[i] : 0.f;
+                    const float a = colsum32(s1, lane);
+                    const float mean_l = nw > 0 ? a / (float)nw : 0.f;
+                    float s2[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float m = __shfl_sync(0xffffffffu, mean_l, i);
+                        const float dlt = valid ? v[i] - m : 0.f;
+                        s2[i] = dlt * dlt;
+                    }
+                    const float c = colsum32(s2, lane);
+                    if (c0 + lane < np) wstat[q * np + c0 + lane] = make_float2(mean_l, c);
+                }
+            }
+            // the accumulator tile has been read: hand it back to the issuer, then finish the per-tile reductions
+            tc_fence_before();
+            asm volatile("bar.sync 1, 128;" ::: "memory");             // the four epilogue warps (also orders wstat)
+            if (threadIdx.x == 64) mbar_arrive(&acc_empty[ab]);
+            if (do_aff && p.aff_kind == TSC_OUT_POOLED) {
+                const float inv_l = 1.f / (float)p.L;
+                for (int c = threadIdx.x - 64; c < p.nbias; c += 128) {
+                    float a = 0.f;
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) a += wstat[w * np + c].x;
+                    reinterpret_cast<float*>(p.aff_out)[(size_t)b * p.nbias + c] = a * inv_l;      // AdaptiveAvgPool1d(1)
+                }
+            } else if (do_stat || do_red) {
+                const int rows_cta = min(128, p.L - l0);
+                for (int c = threadIdx.x - 64; c < np; c += 128) {
+                    if (do_red) {
+                        float a = 0.f, d = 0.f;
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) { const float2 t = wstat[w * np + c]; a += t.x; d += t.y; }
+                        reinterpret_cast<float2*>(p.red_partial)[(size_t)tile * np + c] = make_float2(a, d);
+                    } else {
+                        // Chan merges of the four warps' (n, mean, M2)
+                        float n = 0.f, mean = 0.f, m2 = 0.f;
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) {
+                            const int nw = max(0, min(32, rows_cta - w * 32));
+                            if (nw > 0) {
+                                const float2 t = wstat[w * np + c];
+                                welford_merge(n, mean, m2, (float)nw, t.x, t.y);
+                            }
+                        }
+                        reinterpret_cast<float2*>(p.stat_partial)[(size_t)tile * np + c] = make_float2(mean, m2);
+                    }
+                }
+            }
+            if (j + 1 < n_my) asm volatile("bar.sync 1, 128;" ::: "memory");     // wstat is rewritten by the next tile
+            if (j == 0 && warp == 2 && lane == 0) TL2(6);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (warp == 1 && lane == 0) TL2(7);
+}
+
+int make_c8_map(CUtensorMap* map, const void* base, int B, int kc, int L, int box_rows, int box_chunks);   // conv_tc.cu
+
+static inline int conv2_rp(int Kmax) { return (128 + Kmax - 1 + 7) & ~7; }
+static int knob2_stage_bytes();
+
+// ---- the schedule: runs + stages, built once per bank geometry and direction, cached ----------------------------------------
+static int build_sched(int direction, int Cin, int Cout, int Kmax, const int* s_of_tap, ConvSched* sc) {
+    TapTable tt;
+    if (build_tap_table(direction, Cin, Cout, Kmax, s_of_tap, &tt) != 0) return -1;
+    const int Rp = conv2_rp(Kmax);
+    memset(sc, 0, sizeof(*sc));
+    // a large activation tile leaves less room for the weight ring: halve the stage so that two stages still fit the
+    // half-SM shared-memory budget (two CTAs of different launches can then share an SM)
+    sc->stage_bytes = tt.kc * Rp * 16 > 48 * 1024 ? knob2_stage_bytes() / 2 : knob2_stage_bytes();
+    int n_runs = 0, n_stages = 0;
+    uint32_t used = 0;            // bytes of the open stage
+    uint32_t stage_src = 0;       // its source offset (16 B units)
+    bool init_done = false;
+    auto close_stage = [&]() -> int {
+        TSC_REQUIRE(n_stages < C2_MAX_STAGES, "kernel bank needs more than %d weight stages of %d B: unsupported", C2_MAX_STAGES,
+                    sc->stage_bytes);
+        sc->stages[n_stages++] = make_uint2(stage_src, used);
+        sc->runs[n_runs - 1].w |= RF_LAST;
+        used = 0;
+        return 0;
+    };
+    for (int oi = 0; oi < tt.n_order; ++oi) {
+        const int t = tt.order[oi];
+        const uint32_t n_lo = (uint32_t)tt.n_lo[t], kc_lo = (uint32_t)tt.kc_lo[t];
+        const uint32_t nt = (uint32_t)tt.np - n_lo, ksteps = ((uint32_t)tt.kc - kc_lo) / 2;
+        const uint32_t step_bytes = 2 * nt * 16;
+        TSC_REQUIRE(step_bytes <= (uint32_t)sc->stage_bytes, "one MMA's weights (%u B) exceed the %d B stage", step_bytes, sc->stage_bytes);
+        uint32_t kp = 0;
+        while (kp < ksteps) {
+            if (used + step_bytes > (uint32_t)sc->stage_bytes) { if (close_stage() != 0) return -1; }
+            uint32_t fit = ((uint32_t)sc->stage_bytes - used) / step_bytes;
+            uint32_t n = ksteps - kp < fit ? ksteps - kp : fit;
+            if (!init_done) n = 1;                           // the first MMA of a tile overwrites the accumulator: a run of its own
+            if (n > 127) n = 127;
+            TSC_REQUIRE(n_runs < C2_MAX_RUNS, "kernel bank needs more than %d issue runs: unsupported", C2_MAX_RUNS);
+            if (used == 0) stage_src = (uint32_t)tt.w_off[t] + 2 * kp * nt;
+            uint4 e;
+            e.x = (kc_lo + 2 * kp) * (uint32_t)Rp + (uint32_t)t;
+            e.y = (used >> 4) | (nt << 16);
+            e.z = (1u << 4) | (1u << 7) | (1u << 10) | ((nt >> 3) << 17) | ((128u >> 4) << 24);
+            e.w = n_lo | (n << 9) | (used == 0 ? RF_FIRST : 0u) | (!init_done ? RF_INIT : 0u);
+            sc->runs[n_runs++] = e;
+            init_done = true;
+            used += n * step_bytes;
+            kp += n;
+        }
+    }
+    TSC_REQUIRE(n_runs > 0, "kernel bank has no live tap");
+    if (close_stage() != 0) return -1;
+    sc->n_runs = n_runs;
+    sc->n_stages = n_stages;
+    return 0;
+}
+
+struct SchedKey {
+    int direction, Cin, Cout, Kmax;
+    std::vector<int> s;
+    bool operator<(const SchedKey& o) const {
+        if (direction != o.direction) return direction < o.direction;
+        if (Cin != o.Cin) return Cin < o.Cin;
+        if (Cout != o.Cout) return Cout < o.Cout;
+        if (Kmax != o.Kmax) return Kmax < o.Kmax;
+        return s < o.s;
+    }
+};
+
+// Host-side cache of the schedules (the only state of this file besides the attribute opt-in; behind a mutex).
+static const ConvSched* get_sched(int direction, int Cin, int Cout, int Kmax, const int* s_of_tap) {
+    static std::mutex mu;
+    static std::map<SchedKey, std::unique_ptr<ConvSched>> cache;
+    SchedKey key{direction, Cin, Cout, Kmax, std::vector<int>(s_of_tap, s_of_tap + (Kmax > 0 && Kmax <= TSC_MAX_TAPS ? Kmax : 0))};
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second.get();
+    std::unique_ptr<ConvSched> sc(new ConvSched);
+    if (build_sched(direction, Cin, Cout, Kmax, s_of_tap, sc.get()) != 0) return nullptr;
+    const ConvSched* out = sc.get();
+    cache.emplace(std::move(key), std::move(sc));
+    return out;
+}
+
+static long long* g_timeline2 = nullptr;     // debug only: device buffer of >= 8 clock64 samples
+
+// experiment knobs (environment, read once): TSC_C2_STAGE_KB, TSC_C2_SMEM_FULL, TSC_C2_GRID, TSC_C2_DEBUG
+static int env_int2(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e && e[0] ? atoi(e) : dflt;
+}
+static int knob2_stage_bytes() { static const int v = env_int2("TSC_C2_STAGE_KB", C2_STAGE_BYTES / 1024) * 1024; return v; }
+static int knob2_smem_full() { static const int v = env_int2("TSC_C2_SMEM_FULL", 0); return v; }
+static int knob2_grid() { static const int v = env_int2("TSC_C2_GRID", 0); return v; }
+static int knob2_debug() { static const int v = env_int2("TSC_C2_DEBUG", 0); return v; }
+
+}  // namespace tc
+
+void set_conv2_timeline(long long* dev) { tc::g_timeline2 = dev; }
+
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+            n = v;
+        else
+            n = 148;
+    }
+    return n;
+}
+
+int osconv2_tc(int direction, const void* x, int dtype, const void* w, const float* bias, float* y,
+               const tsc_conv_epilogue* epi, int B, int L, int Cin, int Cout, int Kmax, const int* s_of_tap, cudaStream_t cs) {
+    using namespace tc;
+    TSC_REQUIRE(dtype == TSC_BF16, "the tcgen05 engine takes bf16 operands");
+    const ConvSched* sc = get_sched(direction, Cin, Cout, Kmax, s_of_tap);
+    if (!sc) return -1;
+    const bool fwd = direction == TSC_DIR_FWD;
+    Conv2Params p;
+    memset(&p, 0, sizeof(p));
+    p.w = (const __nv_bfloat16*)w;
+    p.bias = fwd ? bias : nullptr;
+    p.nbias = fwd ? Cout : 0;
+    p.y = y;
+    if (epi) {
+        if (fwd) {
+            p.stat_partial = epi->stat_partial;
+            if (epi->affine_out) {
+                TSC_REQUIRE((epi->affine_scale && epi->affine_shift) || (epi->bn_gamma && epi->bn_beta && epi->bn_mean && epi->bn_var),
+                            "affine epilogue needs (scale, shift) or (gamma, beta, running mean, running var)");
+                TSC_REQUIRE(!epi->stat_partial, "affine epilogue (inference) and BatchNorm statistics (training) exclude each other");
+                TSC_REQUIRE(epi->affine_out_kind == TSC_OUT_C8_BF16 || epi->affine_out_kind == TSC_OUT_C8_F32 ||
+                            epi->affine_out_kind == TSC_OUT_NCL_F32 || epi->affine_out_kind == TSC_OUT_POOLED,
+                            "bad affine_out_kind %d", epi->affine_out_kind);
+                TSC_REQUIRE(epi->affine_out_kind != TSC_OUT_POOLED || L <= 128,
+                            "the pooled inference epilogue needs L <= 128 (one tile per sample), got %d", L);
+                p.aff_scale = epi->affine_scale; p.aff_shift = epi->affine_scale ? epi->affine_shift : nullptr;
+                p.bn_gamma = epi->bn_gamma; p.bn_beta = epi->bn_beta; p.bn_mean = epi->bn_mean; p.bn_var = epi->bn_var;
+                p.bn_eps = epi->bn_eps;
+                p.aff_res = epi->residual;
+                p.aff_out = epi->affine_out; p.aff_kind = epi->affine_out_kind; p.aff_relu = epi->affine_relu ? 1 : 0;
+            }
+        } else if (epi->red_partial) {
+            TSC_REQUIRE(epi->mask_y && epi->mask_mean && epi->mask_invstd, "dgrad reduction needs mask_y, mask_mean, mask_invstd");
+            TSC_REQUIRE(!epi->mask_scale || epi->mask_shift, "mask_scale needs mask_shift");
+            p.mask_y = epi->mask_y; p.mask_scale = epi->mask_scale; p.mask_shift = epi->mask_shift;
+            p.mask_mean = epi->mask_mean; p.mask_invstd = epi->mask_invstd; p.red_partial = epi->red_partial;
+        }
+    }
+    p.B = B; p.L = L; p.ltiles = cdiv(L, 128);
+    p.n_tiles = B * p.ltiles;
+    p.np = fwd ? pad16(Cout) : pad16(Cin);
+    p.kc = fwd ? pad16(Cin) / 8 : pad16(Cout) / 8;
+    p.pad_left = fwd ? (Kmax - 1) / 2 : Kmax / 2;
+    p.Rp = conv2_rp(Kmax);
+    p.x_bytes = p.kc * p.Rp * 16;
+    p.acc_stride = p.np <= 32 ? 32 : p.np <= 64 ? 64 : p.np <= 128 ? 128 : 256;
+    const int nsm = sm_count();
+    // one tile per CTA while the tiles fit one wave (single-buffered, half-SM budgets: CTAs of two streams share an SM);
+    // otherwise one persistent CTA per SM with double-buffered accumulator (and, if it fits, activation) tiles
+    const bool persistent = p.n_tiles > nsm;
+    int grid = persistent ? nsm : p.n_tiles;
+    if (persistent && knob2_grid() > 0 && knob2_grid() < grid) grid = knob2_grid();
+    p.na = persistent ? 2 : 1;
+    p.tiles_base = p.n_tiles / grid;
+    p.tiles_rem = p.n_tiles % grid;
+    p.tmem_cols = p.acc_stride * p.na;
+    p.off_bias = C2_HDR;
+    p.off_wstat = p.off_bias + 4 * p.np * 4;
+    p.off_xs = (p.off_wstat + 4 * p.np * 8 + 127) & ~127;
+    const int slot = sc->stage_bytes;
+    const int cap_full = 227 * 1024, cap_half = 113 * 1024;
+    auto layout = [&](int nx, int cap, int* ns_out) {
+        p.off_stages = (p.off_xs + nx * p.x_bytes + 127) & ~127;
+        int ns = (cap - p.off_stages) / slot;
+        if (ns > 8) ns = 8;
+        if (ns > sc->n_stages) ns = sc->n_stages;
+        *ns_out = ns;
+        return ns >= 2 || (ns == 1 && sc->n_stages == 1);
+    };
+    int ns = 0;
+    if (persistent) {
+        p.nx = 2;
+        if (!layout(2, cap_full, &ns)) { p.nx = 1; TSC_REQUIRE(layout(1, cap_full, &ns), "shape needs %d B of shared memory before the weight stages: unsupported", p.off_stages); }
+    } else {
+        p.nx = 1;
+        if (knob2_smem_full() || !layout(1, cap_half, &ns)) TSC_REQUIRE(layout(1, cap_full, &ns), "shape needs %d B of shared memory before the weight stages: unsupported", p.off_stages);
+    }
+    p.NS = ns;
+    p.tl = g_timeline2;
+    p.debug = knob2_debug();
+    CUtensorMap xmap;
+    if (make_c8_map(&xmap, x, B, p.kc, L, p.Rp, p.kc) != 0) return -1;
+    const int smem = p.off_stages + ns * slot;
+    static OnceAttr attr_once;             // once per process: opt in to the full 227 KB of dynamic shared memory
+    {
+        const cudaError_t e = run_once(attr_once, [] {
+            cudaError_t r = cudaFuncSetAttribute(osconv2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(osconv2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            return r;
+        });
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    const cudaError_t le = p.aff_out ? launch_pdl(osconv2_kernel<true>, dim3(grid), dim3(C2_THREADS), (size_t)smem, cs, xmap, *sc, p)
+                                     : launch_pdl(osconv2_kernel<false>, dim3(grid), dim3(C2_THREADS), (size_t)smem, cs, xmap, *sc, p);
+    if (le != cudaSuccess) { set_error("osconv2 launch: %s", cudaGetErrorString(le)); return (int)le; }
+    TSC_LAUNCH_CHECK();
+    return 0;
+}
+
+int read_clear_watchdog_conv2(int* code) {
+    int zero = 0;
+    cudaError_t e = cudaMemcpyFromSymbol(code, tc::g_watchdog, sizeof(int));
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaMemcpyToSymbol(tc::g_watchdog, &zero, sizeof(int));
+}
+
+}  // namespace tsc

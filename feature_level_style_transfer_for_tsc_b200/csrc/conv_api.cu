@@ -1,11 +1,16 @@
 // C-ABI entry points of the convolution family: engine dispatch (SIMT fp32 / tcgen05 bf16).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace tsc {
 int osconv_simt(int direction, const void* x, int dtype, const void* w, const float* bias, float* y, int B, int L, int Cin,
                 int Cout, int Kmax, const int* s_of_tap, cudaStream_t cs);
 int osconv_tc(int direction, const void* x, int dtype, const void* w, const void* plan, const float* bias, float* y,
               const tsc_conv_epilogue* epi, int B, int L, int Cin, int Cout, int Kmax, const int* s_of_tap, cudaStream_t cs);
+int osconv2_tc(int direction, const void* x, int dtype, const void* w, const float* bias, float* y,
+               const tsc_conv_epilogue* epi, int B, int L, int Cin, int Cout, int Kmax, const int* s_of_tap, cudaStream_t cs);
+int read_clear_watchdog_conv2(int* code);
+void set_conv2_timeline(long long* dev);
 size_t osconv_plan_bytes(int direction, int Cin, int Cout, int Kmax, const int* s_of_tap);
 int osconv_plan_build(int direction, int Cin, int Cout, int Kmax, const int* s_of_tap, void* host_plan);
 int oswgrad_simt(const void* dy, const void* x, int dtype, float* dW, void* workspace, int accumulate, int B, int L, int Cin,
@@ -47,9 +52,13 @@ int tsc_osconv(int engine, int direction, const void* x, int dtype, const void* 
                     "fused epilogues exist on the tcgen05 engine only");
         return osconv_simt(direction, x, dtype, w, bias, y, B, L, Cin, Cout, Kmax, s_of_tap, (cudaStream_t)stream);
     }
-    if (engine == TSC_ENGINE_TCGEN05)
-        return osconv_tc(direction, x, dtype, w, plan, bias, y, epilogue, B, L, Cin, Cout, Kmax, s_of_tap,
-                         (cudaStream_t)stream);
+    if (engine == TSC_ENGINE_TCGEN05) {
+        // the round-1 kernel (plan in shared memory, one tile per CTA) stays selectable for A/B measurements: TSC_CONV_V1=1
+        static const bool v1 = [] { const char* e = getenv("TSC_CONV_V1"); return e && e[0] == '1'; }();
+        if (v1 && plan)
+            return osconv_tc(direction, x, dtype, w, plan, bias, y, epilogue, B, L, Cin, Cout, Kmax, s_of_tap, (cudaStream_t)stream);
+        return osconv2_tc(direction, x, dtype, w, bias, y, epilogue, B, L, Cin, Cout, Kmax, s_of_tap, (cudaStream_t)stream);
+    }
     TSC_REQUIRE(false, "bad engine %d", engine);
 }
 
@@ -76,6 +85,7 @@ int tsc_oswgrad(int engine, const void* dy, const void* x, int dtype, float* dW,
 
 int tsc_debug_set_timeline(void* dev_buf) {
     tsc::set_conv_timeline((long long*)dev_buf);
+    tsc::set_conv2_timeline((long long*)dev_buf);
     tsc::set_wgrad_timeline((long long*)dev_buf);
     tsc::set_gram_timeline((long long*)dev_buf);
     return 0;
@@ -83,8 +93,10 @@ int tsc_debug_set_timeline(void* dev_buf) {
 
 int tsc_debug_read_and_clear_watchdog(int* host_code) {
     using namespace tsc;
-    int a = 0, b = 0, c = 0, r;
+    int a = 0, b = 0, c = 0, a2 = 0, r;
     if ((r = read_clear_watchdog_conv(&a)) != 0) return r;
+    if ((r = read_clear_watchdog_conv2(&a2)) != 0) return r;
+    if (!a) a = a2;
     if ((r = read_clear_watchdog_wgrad(&b)) != 0) return r;
     if ((r = read_clear_watchdog_gram(&c)) != 0) return r;
     *host_code = a ? a : (b ? b : c);
