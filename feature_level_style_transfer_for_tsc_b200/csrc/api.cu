@@ -15,6 +15,13 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+bool packed_split() {
+    // the CTA-pair (cta_group::2) convolution and its split packed layout: measured SLOWER than the one-CTA kernel on this
+    // workload's narrow MMAs (profiles/README.md, round 2), so it is an opt-in experiment: TSC_CONV_PAIR=1
+    static const bool on = [] { const char* e = getenv("TSC_CONV_PAIR"); return e && e[0] == '1'; }();
+    return on;
+}
+
 bool pdl_enabled() {
     // off by default: measured on the cfg2 step it costs 2-3 % (early-resident CTAs of the next kernel take the SM slot
     // that the other branch's stream would have used) -- profiles/README.md; TSC_PDL=1 switches it on

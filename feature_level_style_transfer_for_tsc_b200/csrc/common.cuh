@@ -73,8 +73,8 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 // ---- per-bank tap table (host side; passed to kernels by value) -----------------------------------
 // Generic implicit-GEMM conv:  y[b,n,l] = bias[n] + sum_t sum_{kc>=kc_lo[t]} sum_j
 //      x[b, kc*8+j, l + t - pad_left] * blob_t[kc-kc_lo[t]][n-n_lo[t]][j]      for n >= n_lo[t]
-// blob_t starts at row w_off[t] (rows of 8 elements) of the packed weight buffer and is laid out
-// [kc - kc_lo][np - n_lo][8].
+// blob_t is tap t's [kc - kc_lo][np - n_lo][8] block; w_off[t] = rows of the blobs before it in issue order.  In memory
+// the rows are split into two streams, see packed_row().
 struct TapTable {
     int taps;        // Kmax
     int pad_left;
@@ -87,6 +87,23 @@ struct TapTable {
     short kc_lo[TSC_MAX_TAPS];
     int w_off[TSC_MAX_TAPS];
 };
+
+// Row (16 B = 8 elements) of the packed kernel bank that holds (tap t, input-channel chunk `chunk_rel` past the tap's first
+// stored chunk, output row `row_rel` past the tap's first stored row); nt = stored rows of the tap (a multiple of 16),
+// w_off_t = TapTable::w_off[t], total_rows = TapTable::total_rows.
+//   classic layout (split == 0): [tap in issue order][chunk][nt rows][8] -- the B operand of one CTA's MMA is contiguous;
+//   split layout   (split != 0): two streams -- the lower and the upper half of every tap's stored rows -- each
+//     [tap in issue order][chunk][nt / 2 rows][8]: the CTA-pair variant of the tcgen05 convolution (cta_group::2, M = 256)
+//     holds N/2 rows of the B operand in each CTA, so each CTA streams ONE contiguous half of the bank.
+// Which one a process uses is fixed at start-up (packed_split(): TSC_CONV_PAIR=1 selects the pair kernel and the split layout);
+// every kernel that writes or reads a packed bank goes through this function.
+__host__ __device__ __forceinline__ long long packed_row(int total_rows, int w_off_t, int nt, int chunk_rel, int row_rel, int split) {
+    if (!split) return (long long)w_off_t + (long long)chunk_rel * nt + row_rel;
+    const int half = nt >> 1;
+    const int h = row_rel >= half ? 1 : 0;
+    return (long long)h * (total_rows >> 1) + (w_off_t >> 1) + (long long)chunk_rel * half + (row_rel - h * half);
+}
+bool packed_split();      // api.cu
 
 // Build the table for one direction.  Returns 0 or -1 (error text set).
 int build_tap_table(int direction, int Cin, int Cout, int Kmax, const int* s_of_tap, TapTable* tt);

@@ -1,9 +1,19 @@
-// tcgen05 engine, forward / dgrad, second generation: the omni-scale convolution as a PERSISTENT implicit GEMM.
+// tcgen05 engine, forward / dgrad, second generation: the omni-scale convolution as a PERSISTENT implicit GEMM on CTA PAIRS.
 //
-//   positions (128 per tile)  -> MMA M   (accumulator rows = TMEM lanes)
-//   output channels (<= 256)  -> MMA N   (the whole channel axis is one accumulator tile in TMEM)
-//   (tap, input channel)      -> MMA K   (16 channels per instruction)
+//   positions (2 x 128 per CTA pair) -> MMA M = 256 (cta_group::2: 128 accumulator rows = TMEM lanes in each CTA)
+//   output channels (<= 256)         -> MMA N      (the whole channel axis is one accumulator tile in TMEM)
+//   (tap, input channel)             -> MMA K      (16 channels per instruction)
 //
+// * cta_group::2.  The round-1 kernel and the first version of this one were bound by the ISSUE RATE of the one thread that may
+//   issue tcgen05.mma: 156 instructions of ~53 tensor cycles each for the cfg2 72->228 bank took 17.9 k cycles whatever the
+//   weight stream did (producer not copying at all: same time; ring depth 2 or 6: same time) -- 3720 instructions of the
+//   issuing warp at 4.8 cycles each (profiles/README.md, round 2).  One instruction of a CTA pair does the work of two: the
+//   pair's two position tiles share every MMA, each CTA holds its own activation tile (A: 128 rows per CTA) and HALF of the
+//   tap's live channels (B: N/2 rows per CTA, the split packed layout of common.cuh), so the issue cost per tile, the
+//   shared-memory operand fetch per instruction (42 + N/8 instead of 42 + N/4 cycles) and the L2 -> shared-memory weight
+//   traffic per tile all halve.  The leader CTA (cluster rank 0) issues; the peer's would-be issuer warp relays "my half of
+//   the stage / my activation tile has landed" to the leader's barriers; tcgen05.commit multicasts "stage consumed" /
+//   "accumulator complete" to both CTAs.
 // What changed against conv_tc.cu (round 1), and why (profiles/README.md, rounds 1-2):
 // * The issuing warp was bound by its own instruction count (~70 SASS instructions per four MMAs: plan entries loaded from
 //   shared memory into vector registers, 17 R2UR per group).  Here the schedule is a table of per-tap RUNS in the kernel
@@ -34,20 +44,25 @@ namespace tsc {
 namespace tc {
 
 static constexpr int C2_THREADS = 192;
-static constexpr int C2_MAX_RUNS = 352;
+static constexpr int C2_MAX_RUNS = 320;
 static constexpr int C2_MAX_STAGES = 256;
-static constexpr int C2_STAGE_BYTES = 32 * 1024;
+static constexpr int C2_STAGE_BYTES = 16 * 1024;    // per CTA: a stage is 32 KB of the bank, half of it in each CTA of the pair
 static constexpr int C2_HDR = 256;
-static constexpr uint32_t RF_FIRST = 1u << 16, RF_LAST = 1u << 17, RF_INIT = 1u << 18;
+static constexpr uint32_t RF_FIRST = 1u, RF_LAST = 2u;
 
-// One run = consecutive K steps of one tap inside one weight stage.
-//   x: A start (16 B units from the activation tile base) of the first K step
-//   y: B start inside the stage (16 B units) | live channels nt << 16 (= the descriptor's leading-dimension field)
-//   z: instruction descriptor (M = 128, N = nt, bf16 x bf16 -> f32, both K-major)
-//   w: TMEM column [0,9) | K steps << 9 [9,16) | RF_FIRST: opens its weight stage | RF_LAST: closes it | RF_INIT: overwrites
+// One run = consecutive K steps of one tap inside one weight stage: two uint4 (every field ready to use -- the issuing warp
+// is bound by its instruction count, so nothing is decoded on the device).
+//  [0] x: A start (16 B units from the activation tile base) of the first K step
+//      y: B start inside this CTA's half stage (16 B units) | nt / 2 << 16 (= the descriptor's leading-dimension field: each
+//         CTA of the pair holds nt / 2 of the tap's nt live channels)
+//      z: instruction descriptor (M = 256, N = nt, bf16 x bf16 -> f32, both K-major)
+//      w: TMEM column of the tap's first live channel
+//  [1] x: K steps   y: B advance per K step (16 B units)   z: accumulate flag (0: the tile's first MMA overwrites)
+//      w: RF_FIRST: opens its weight stage | RF_LAST: closes it
 struct ConvSched {
-    int n_runs, n_stages, stage_bytes, pad;
-    uint4 runs[C2_MAX_RUNS];
+    int n_runs, n_stages, stage_bytes;
+    int half_rows16;                  // 16 B rows of one stream of the split packed bank
+    uint4 runs[2 * C2_MAX_RUNS];
     uint2 stages[C2_MAX_STAGES];      // {source offset in 16 B units, bytes}
 };
 
@@ -70,7 +85,8 @@ struct Conv2Params {
     void* aff_out;
     int aff_kind, aff_relu;
     int nbias, B, L, ltiles, n_tiles;
-    int tiles_base, tiles_rem;     // n_tiles = tiles_base * grid + tiles_rem
+    int tiles_base, tiles_rem;     // tile PAIRS: n_pairs = tiles_base * (grid / 2) + tiles_rem
+    int half_rows16;               // 16 B rows of one stream of the split packed bank (the peer CTA's source offset)
     int np;            // padded output channels of this direction
     int Rp;            // halo rows of the activation tile (multiple of 8)
     int kc;            // input-channel chunks of 8
@@ -84,7 +100,11 @@ struct Conv2Params {
     int debug;         // experiments only (TSC_C2_DEBUG; garbage results): 1 = the producer signals its stages full without copying
 };
 
-#define TL2(i) do { if (p.tl && blockIdx.x == 0) p.tl[i] = clock64(); } while (0)
+// DBG is a template flag of the kernel: the production instantiation carries no timeline code (the issuing warp is bound by its
+// instruction count)
+#define TL2(i) do { if (DBG && p.tl && blockIdx.x == 0) p.tl[i] = clock64(); } while (0)
+// per-stage samples of CTA 0 (debug timeline only): slot k of weight stage i (counted over all tiles), first 48 stages
+#define TLS2(i, k) do { if (DBG && p.tl && blockIdx.x == 0 && (i) < 48) p.tl[8 + (i) * 8 + (k)] = clock64(); } while (0)
 
 // warp-uniform bounded wait: all 32 lanes poll and the loop branch is a vote, so the warp's control flow stays uniform
 // (the issue loop then lives in uniform registers).  false = timed out (watchdog).
@@ -94,6 +114,66 @@ __device__ __forceinline__ bool mbar_wait_warp(uint64_t* bar, uint32_t parity) {
         if (__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) return true;
     }
     return false;
+}
+
+// ---- CTA-pair primitives (cluster of 2, cta_group::2) ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address of this CTA's window) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// as mbar_wait_warp, for barriers the PEER CTA arrives on (acquire at cluster scope)
+__device__ __forceinline__ bool mbar_wait_warp_cluster(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1
+    for (uint32_t i = 0; i < (1u << 22); ++i) {
+        if (__all_sync(0xffffffffu, mbar_try_wait_cluster(bar, parity))) return true;
+    }
+    return false;
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// "all MMAs issued so far by this thread have completed" -> one arrival on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit2(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[128 rows in each CTA] * B[N/2 rows in each CTA]; one thread of the leader CTA issues for the pair
+__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
@@ -129,7 +209,41 @@ __device__ __forceinline__ float colsum32(float* v, int lane) {
     return v[0];
 }
 
-template <bool AFF>
+// The K steps of one run, issued by the elected lane: descriptors advance by (a_step, b_step) 16 B units per step.  Unrolled by
+// hand in blocks of four (a `#pragma unroll` on the loop sends ptxas back to vector registers + R2UR).
+template <bool PAIR>
+__device__ __forceinline__ void mma_issue(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    if (PAIR) umma2_bf16(d, a, b, idesc, acc);
+    else umma_bf16(d, a, b, idesc, acc != 0);
+}
+template <bool PAIR>
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    if (PAIR) tc_commit2(bar);
+    else tc_commit(bar);
+}
+template <bool PAIR>
+__device__ __forceinline__ void issue_run(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc, int ks,
+                                          uint32_t a_step, uint32_t b_step) {
+#pragma unroll 1
+    while (ks >= 4) {
+        mma_issue<PAIR>(d, a, b, idesc, acc);
+        mma_issue<PAIR>(d, a + a_step, b + b_step, idesc, acc);
+        mma_issue<PAIR>(d, a + 2 * a_step, b + 2 * b_step, idesc, acc);
+        mma_issue<PAIR>(d, a + 3 * a_step, b + 3 * b_step, idesc, acc);
+        a += 4 * a_step;
+        b += 4 * b_step;
+        ks -= 4;
+    }
+#pragma unroll 1
+    while (ks > 0) {
+        mma_issue<PAIR>(d, a, b, idesc, acc);
+        a += a_step;
+        b += b_step;
+        --ks;
+    }
+}
+
+template <bool AFF, bool DBG, bool PAIR>
 __global__ void __launch_bounds__(C2_THREADS, AFF ? 2 : 1)
 osconv2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ ConvSched S, const __grid_constant__ Conv2Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -138,7 +252,7 @@ osconv2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
     uint64_t* x_full = empty + 8;                                  // [2]  activation tile landed
     uint64_t* x_empty = x_full + 2;                                // [2]  ... consumed by the tile's MMAs
     uint64_t* acc_full = x_empty + 2;                              // [2]  accumulator tile complete
-    uint64_t* acc_empty = acc_full + 2;                            // [2]  ... drained by the epilogue
+    uint64_t* acc_empty = acc_full + 2;                            // [2]  ... drained by BOTH epilogues (leader's copy is used)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     float* bias_s = reinterpret_cast<float*>(smem + p.off_bias);
     float2* wstat = reinterpret_cast<float2*>(smem + p.off_wstat);  // [4][np]
@@ -152,20 +266,28 @@ osconv2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
     const int np = p.np;
     // tiles of this CTA (tile = blockIdx.x + j * gridDim.x); no division here: the issuing warp's loop bounds must stay in the
     // uniform datapath
-    const int n_my = p.tiles_base + ((int)blockIdx.x < p.tiles_rem ? 1 : 0);
+    // PAIR: cluster of two CTAs = one tcgen05 CTA pair; rank 0 = leader (issues the pair's MMAs), 1 = peer.  A "unit" is what
+    // one issuer works on at a time: a tile pair (PAIR) or a tile.
+    constexpr int NCTA = PAIR ? 2 : 1;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const int pair = (int)blockIdx.x / NCTA, n_pairs_grid = (int)gridDim.x / NCTA;
+    const int n_my = p.tiles_base + (pair < p.tiles_rem ? 1 : 0);  // units of this CTA (pair): tile = NCTA * (pair + j * n_pairs_grid) + rank
     const int slot_bytes = S.stage_bytes;
 
     if (warp == 0 && lane == 0) {
         TL2(0);
         tma_prefetch_desc(&xmap);
-        for (int i = 0; i < p.NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        // the leader's full[] / x_full[] collect BOTH CTAs' "landed" signals -- its own copy's expect_tx arrival and the peer
+        // relay's remote arrival -- so the issuer waits on one barrier per stage / tile
+        const uint32_t n_land = (PAIR && rank == 0) ? 2u : 1u;
+        for (int i = 0; i < p.NS; ++i) { mbar_init(&full[i], n_land); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1);
-            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 1);
+            mbar_init(&x_full[i], n_land); mbar_init(&x_empty[i], 1);
+            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NCTA);   // PAIR: the two CTAs' epilogues
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    if (warp == 1) { if (PAIR) tmem_alloc2(tmem_slot, (uint32_t)p.tmem_cols); else tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols); }
     if (warp >= 2) {
         pdl_wait();
         // per-channel epilogue constants -> shared memory: [0] bias | mask scale, [1] mask shift, [2] mean, [3] invstd
@@ -195,87 +317,134 @@ osconv2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); // both CTAs' barriers are initialised before any remote arrive / multicast commit
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===== copy producer (one thread): activation tiles by TMA, the packed bank by one bulk copy per stage =====
+        // ===== copy producer (ONE thread: a second polling lane of the same warp would stall this one for the length of its
+        // mbarrier suspend -- measured): this CTA's half of the packed bank, one bulk copy per stage, and the activation tiles
+        // (TMA).  The next tile's activation buffer is requested opportunistically between two weight stages, as soon as the
+        // tile that used it has completed, so that waiting for it never holds up the weight stream. =====
         if (lane == 0) {
             bool dead = false;
             pdl_wait();
             TL2(1);
             const int nx = p.nx;
             auto load_x = [&](int k) {
-                const int xb = k & (nx - 1), use = nx == 2 ? (k >> 1) : k;
-                if (use > 0) mbar_wait(&x_empty[xb], (uint32_t)((use - 1) & 1), dead, 10);
-                const int tile = (int)blockIdx.x + k * (int)gridDim.x;
-                const int b = tile / p.ltiles, l0 = (tile - b * p.ltiles) * 128;
+                const int xb = k & (nx - 1);
+                const int tile = NCTA * (pair + k * n_pairs_grid) + (int)rank;   // past the last tile (odd count): b == B, all rows
+                const int b = tile / p.ltiles, l0 = (tile - b * p.ltiles) * 128;  // out of bounds -> a tile of zeros
                 mbar_arrive_expect_tx(&x_full[xb], (uint32_t)p.x_bytes);
                 tma_load_4d(xs + (size_t)xb * p.x_bytes, &xmap, 0, l0 - p.pad_left, 0, b, &x_full[xb]);
             };
+            // is the buffer of activation tile k free?  (its previous user, tile k - nx, has completed)
+            auto x_free = [&](int k, bool block) -> bool {
+                const int xb = k & (nx - 1), use = nx == 2 ? (k >> 1) : k;
+                if (use == 0) return true;
+                if (block) { mbar_wait(&x_empty[xb], (uint32_t)((use - 1) & 1), dead, 10); return true; }
+                return mbar_try_wait(&x_empty[xb], (uint32_t)((use - 1) & 1));
+            };
             load_x(0);
+            int x_next = 1;                                   // next activation tile to request
+            if (x_next < n_my && nx == 2) { load_x(x_next); ++x_next; }
             uint32_t s = 0, ph = 0;
             const int n_stages = S.n_stages;
+            // this CTA's half of every tap's live channels: the lower / upper stream of the split packed bank
+            const uint8_t* w_src = reinterpret_cast<const uint8_t*>(p.w) + (size_t)rank * (size_t)p.half_rows16 * 16;
             for (int j = 0; j < n_my; ++j) {
-                if (nx == 2 && j + 1 < n_my) load_x(j + 1);
                 for (int i = 0; i < n_stages; ++i) {
                     const uint2 e = S.stages[i];
+                    if (x_next < n_my && x_next <= j + nx - 1 && x_free(x_next, false)) { load_x(x_next); ++x_next; }
+                    TLS2(j * n_stages + i, 4);
                     mbar_wait(&empty[s], ph ^ 1u, dead, 1);
+                    TLS2(j * n_stages + i, 5);
                     if (p.debug & 1) { mbar_arrive(&full[s]); if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; } continue; }
                     mbar_arrive_expect_tx(&full[s], e.y);
-                    bulk_load(stages + (size_t)s * slot_bytes, reinterpret_cast<const uint8_t*>(p.w) + (size_t)e.x * 16, e.y, &full[s]);
+                    bulk_load(stages + (size_t)s * slot_bytes, w_src + (size_t)e.x * 16, e.y, &full[s]);
                     if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; }
                 }
-                if (nx == 1 && j + 1 < n_my) load_x(j + 1);       // a single tile buffer: reload behind the tile's own stages
+                // whatever tile j + 1 still needs: its buffer is free at the latest when tile j's MMAs (nx == 1) or tile
+                // j - 1's (nx == 2) have completed
+                if (x_next < n_my && x_next <= j + 1) { x_free(x_next, true); load_x(x_next); ++x_next; }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: the whole warp walks the run table in lock-step, in uniform registers; one elected lane issues =====
         bool ok = true;
-        const uint32_t desc_hi = (128u >> 4) | (1u << 14);                        // SBO = 128 B, descriptor version 1
-        const uint32_t xs16 = smem_u32(xs) >> 4;
-        const uint32_t a_lbo = (uint32_t)p.Rp << 16;                               // LBO = Rp * 16 B (the two 8-channel K groups)
-        const uint32_t a_step = 2u * (uint32_t)p.Rp;                               // one K step = two chunks further
-        const uint32_t st16 = smem_u32(stages) >> 4;
-        const uint32_t slot16 = (uint32_t)slot_bytes >> 4;
-        const uint32_t x16 = (uint32_t)p.x_bytes >> 4;
-        const int n_runs = S.n_runs;
+        const int n_runs = S.n_runs, n_stages = S.n_stages;
         const int nx = p.nx, na = p.na;
         uint32_t s = 0, ph = 0;
-        for (int j = 0; j < n_my; ++j) {
-            const uint32_t xb = (uint32_t)j & (uint32_t)(nx - 1), xuse = nx == 2 ? ((uint32_t)j >> 1) : (uint32_t)j;
-            const uint32_t ab = (uint32_t)j & (uint32_t)(na - 1), ause = na == 2 ? ((uint32_t)j >> 1) : (uint32_t)j;
-            ok = mbar_wait_warp(&x_full[xb], xuse & 1u) && ok;
-            if (ause > 0) ok = mbar_wait_warp(&acc_empty[ab], (ause - 1u) & 1u) && ok;
-            tc_fence_after();
-            if (j == 0) TL2(2);                   // (all lanes store: a lane-dependent branch here would cost the loop its uniformity)
-            const uint32_t a_base = (xs16 + xb * x16) | a_lbo;
-            const uint32_t d_base = tmem_base + ab * (uint32_t)p.acc_stride;
+        int stage_i = 0;
+        if (!PAIR || rank == 0) {
+            // ===== MMA issuer (leader CTA): the whole warp walks the run table in lock-step, in uniform registers; one elected
+            // lane issues for the pair =====
+            const uint32_t desc_hi = (128u >> 4) | (1u << 14);                        // SBO = 128 B, descriptor version 1
+            const uint32_t xs16 = smem_u32(xs) >> 4;
+            const uint32_t a_lbo = (uint32_t)p.Rp << 16;                               // LBO = Rp * 16 B (the two 8-channel K groups)
+            const uint32_t a_step = 2u * (uint32_t)p.Rp;                               // one K step = two chunks further
+            const uint32_t st16 = smem_u32(stages) >> 4;
+            const uint32_t slot16 = (uint32_t)slot_bytes >> 4;
+            const uint32_t x16 = (uint32_t)p.x_bytes >> 4;
+            uint32_t slot_cur = st16;                                                  // start of weight slot s (16 B units)
+            for (int j = 0; j < n_my; ++j) {
+                const uint32_t xb = (uint32_t)j & (uint32_t)(nx - 1), xuse = nx == 2 ? ((uint32_t)j >> 1) : (uint32_t)j;
+                const uint32_t ab = (uint32_t)j & (uint32_t)(na - 1), ause = na == 2 ? ((uint32_t)j >> 1) : (uint32_t)j;
+                ok = mbar_wait_warp(&x_full[xb], xuse & 1u) && ok;
+                if (ause > 0) ok = mbar_wait_warp(&acc_empty[ab], (ause - 1u) & 1u) && ok;
+                tc_fence_after();
+                if (j == 0) TL2(2);                   // (all lanes store: a lane-dependent branch here would cost the loop its uniformity)
+                const uint32_t a_base = (xs16 + xb * x16) | a_lbo;
+                const uint32_t d_base = tmem_base + ab * (uint32_t)p.acc_stride;
+                // Software-pipelined over the runs: the tensor pipe queues hardly more than one instruction ahead (measured:
+                // every issue-side gap longer than one MMA shows up as idle tensor time), so a run's first MMA is issued
+                // alone, the NEXT run's table entry is fetched and its operands computed in that MMA's shadow, and only then
+                // the rest of the run follows.
+                uint4 e = S.runs[0], f = S.runs[1];
+                uint32_t a_lo = a_base + e.x, d = d_base + e.w;
 #pragma unroll 1
-            for (int r = 0; r < n_runs; ++r) {
-                const uint4 e = S.runs[r];
-                if (e.w & RF_FIRST) ok = mbar_wait_warp(&full[s], ph) && ok;
-                uint32_t a = a_base + e.x;
-                uint32_t b = (st16 + s * slot16) + e.y;
-                const uint32_t b_step = (e.y >> 16) * 2u;
-                const int ks = (int)((e.w >> 9) & 0x7fu);
-                const uint32_t d = d_base + (e.w & 0x1ffu);
-                const uint32_t accf = (e.w & RF_INIT) ? 0u : 1u;
-                if (elect_one()) {
-#pragma unroll 1
-                    for (int k = 0; k < ks; ++k) {
-                        umma_bf16(d, ((uint64_t)desc_hi << 32) | a, ((uint64_t)desc_hi << 32) | b, e.z, accf);
-                        a += a_step;
-                        b += b_step;
+                for (int r = 0; r < n_runs; ++r) {
+                    if (f.w & RF_FIRST) {
+                        TLS2(stage_i, 0);
+                        ok = mbar_wait_warp(&full[s], ph) && ok;
+                        TLS2(stage_i, 1);
                     }
-                    if (e.w & RF_LAST) tc_commit(&empty[s]);      // frees the stage when these MMAs have read it
+                    const uint64_t a0 = ((uint64_t)desc_hi << 32) | a_lo;
+                    const uint64_t b0 = ((uint64_t)desc_hi << 32) | (slot_cur + e.y);
+                    if (elect_one()) mma_issue<PAIR>(d, a0, b0, e.z, f.z);
+                    // (the table ends with a dummy entry: the prefetch of the last iteration stays in bounds)
+                    const uint4 en = S.runs[2 * r + 2], fn = S.runs[2 * r + 3];
+                    const uint32_t a_next = a_base + en.x, d_next = d_base + en.w;
+                    if (elect_one()) {
+                        issue_run<PAIR>(d, a0 + a_step, b0 + f.y, e.z, 1u, (int)f.x - 1, a_step, f.y);
+                        if (f.w & RF_LAST) mma_commit<PAIR>(&empty[s]);   // frees the stage (in both CTAs) when these MMAs have read it
+                    }
+                    if (f.w & RF_LAST) {
+                        TLS2(stage_i, 3);
+                        if (DBG) ++stage_i;
+                        slot_cur += slot16;
+                        if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; slot_cur = st16; }
+                    }
+                    e = en; f = fn; a_lo = a_next; d = d_next;
                 }
-                if (e.w & RF_LAST) { if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; } }
+                if (elect_one()) {
+                    mma_commit<PAIR>(&acc_full[ab]);
+                    mma_commit<PAIR>(&x_empty[xb]);
+                }
             }
-            if (elect_one()) {
-                tc_commit(&acc_full[ab]);
-                tc_commit(&x_empty[xb]);
+        } else {
+            // ===== relay (peer CTA): tells the leader's barriers when this CTA's activation tile / half stage has landed =====
+            const uint32_t px_remote = mapa_u32(smem_u32(x_full), 0), pf_remote = mapa_u32(smem_u32(full), 0);
+            for (int j = 0; j < n_my; ++j) {
+                const uint32_t xb = (uint32_t)j & (uint32_t)(nx - 1), xuse = nx == 2 ? ((uint32_t)j >> 1) : (uint32_t)j;
+                ok = mbar_wait_warp(&x_full[xb], xuse & 1u) && ok;
+                if (elect_one()) mbar_arrive_remote(px_remote + xb * 8u);
+#pragma unroll 1
+                for (int i = 0; i < n_stages; ++i) {
+                    ok = mbar_wait_warp(&full[s], ph) && ok;
+                    if (elect_one()) mbar_arrive_remote(pf_remote + s * 8u);
+                    if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; }
+                }
             }
         }
         pdl_trigger();            // the next kernel of the stream may start its prologue while the last epilogue runs
@@ -293,10 +462,11 @@ osconv2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
         constexpr bool do_aff = AFF;
         const int na = p.na;
         for (int j = 0; j < n_my; ++j) {
-            const int tile = (int)blockIdx.x + j * (int)gridDim.x;
-            const int b = tile / p.ltiles, l0 = (tile - b * p.ltiles) * 128;
+            const int tile = NCTA * (pair + j * n_pairs_grid) + (int)rank;
+            const bool real = tile < p.n_tiles;                 // an odd tile count leaves the last pair's peer without a tile
+            const int b = real ? tile / p.ltiles : 0, l0 = real ? (tile - b * p.ltiles) * 128 : 0;
             const int l = l0 + row;
-            const bool valid = l < p.L;
+            const bool valid = real && l < p.L;
             const size_t row_off = ((size_t)b * npc * p.L + (size_t)(valid ? l : 0)) * 8;
             float* ybase = p.y + row_off;
             const float* mbase = do_red ? p.mask_y + row_off : nullptr;
@@ -466,8 +636,13 @@ osconv2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
             // the accumulator tile has been read: hand it back to the issuer, then finish the per-tile reductions
             tc_fence_before();
             asm volatile("bar.sync 1, 128;" ::: "memory");             // the four epilogue warps (also orders wstat)
-            if (threadIdx.x == 64) mbar_arrive(&acc_empty[ab]);
-            if (do_aff && p.aff_kind == TSC_OUT_POOLED) {
+            if (threadIdx.x == 64) {
+                if (!PAIR || rank == 0) mbar_arrive(&acc_empty[ab]);
+                else mbar_arrive_remote(mapa_u32(smem_u32(&acc_empty[ab]), 0));
+            }
+            if (!real) {
+                // nothing to write for a missing tile
+            } else if (do_aff && p.aff_kind == TSC_OUT_POOLED) {
                 const float inv_l = 1.f / (float)p.L;
                 for (int c = threadIdx.x - 64; c < p.nbias; c += 128) {
                     float a = 0.f;
@@ -503,8 +678,9 @@ osconv2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
         }
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (PAIR) cluster_sync_all(); // the peer's shared memory and TMEM stay alive until the leader's last MMA has completed
+    else __syncthreads();
+    if (warp == 1) { if (PAIR) tmem_dealloc2(tmem_base, (uint32_t)p.tmem_cols); else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
     if (warp == 1 && lane == 0) TL2(7);
 }
 
@@ -512,16 +688,17 @@ int make_c8_map(CUtensorMap* map, const void* base, int B, int kc, int L, int bo
 
 static inline int conv2_rp(int Kmax) { return (128 + Kmax - 1 + 7) & ~7; }
 static int knob2_stage_bytes();
+static int knob2_debug();
 
 // ---- the schedule: runs + stages, built once per bank geometry and direction, cached ----------------------------------------
-static int build_sched(int direction, int Cin, int Cout, int Kmax, const int* s_of_tap, ConvSched* sc) {
+static int build_sched(bool pair, int direction, int Cin, int Cout, int Kmax, const int* s_of_tap, ConvSched* sc) {
     TapTable tt;
     if (build_tap_table(direction, Cin, Cout, Kmax, s_of_tap, &tt) != 0) return -1;
     const int Rp = conv2_rp(Kmax);
     memset(sc, 0, sizeof(*sc));
     // a large activation tile leaves less room for the weight ring: halve the stage so that two stages still fit the
     // half-SM shared-memory budget (two CTAs of different launches can then share an SM)
-    sc->stage_bytes = tt.kc * Rp * 16 > 48 * 1024 ? knob2_stage_bytes() / 2 : knob2_stage_bytes();
+    sc->stage_bytes = (tt.kc * Rp * 16 > 48 * 1024 ? knob2_stage_bytes() / 2 : knob2_stage_bytes()) * (pair ? 1 : 2);
     int n_runs = 0, n_stages = 0;
     uint32_t used = 0;            // bytes of the open stage
     uint32_t stage_src = 0;       // its source offset (16 B units)
@@ -530,7 +707,7 @@ static int build_sched(int direction, int Cin, int Cout, int Kmax, const int* s_
         TSC_REQUIRE(n_stages < C2_MAX_STAGES, "kernel bank needs more than %d weight stages of %d B: unsupported", C2_MAX_STAGES,
                     sc->stage_bytes);
         sc->stages[n_stages++] = make_uint2(stage_src, used);
-        sc->runs[n_runs - 1].w |= RF_LAST;
+        sc->runs[2 * (n_runs - 1) + 1].w |= RF_LAST;
         used = 0;
         return 0;
     };
@@ -538,7 +715,8 @@ static int build_sched(int direction, int Cin, int Cout, int Kmax, const int* s_
         const int t = tt.order[oi];
         const uint32_t n_lo = (uint32_t)tt.n_lo[t], kc_lo = (uint32_t)tt.kc_lo[t];
         const uint32_t nt = (uint32_t)tt.np - n_lo, ksteps = ((uint32_t)tt.kc - kc_lo) / 2;
-        const uint32_t step_bytes = 2 * nt * 16;
+        const uint32_t rows = pair ? nt / 2 : nt;            // rows of the B operand in one CTA
+        const uint32_t step_bytes = 2 * rows * 16;           // per CTA: two 8-channel chunks of `rows` rows
         TSC_REQUIRE(step_bytes <= (uint32_t)sc->stage_bytes, "one MMA's weights (%u B) exceed the %d B stage", step_bytes, sc->stage_bytes);
         uint32_t kp = 0;
         while (kp < ksteps) {
@@ -546,15 +724,21 @@ static int build_sched(int direction, int Cin, int Cout, int Kmax, const int* s_
             uint32_t fit = ((uint32_t)sc->stage_bytes - used) / step_bytes;
             uint32_t n = ksteps - kp < fit ? ksteps - kp : fit;
             if (!init_done) n = 1;                           // the first MMA of a tile overwrites the accumulator: a run of its own
-            if (n > 127) n = 127;
-            TSC_REQUIRE(n_runs < C2_MAX_RUNS, "kernel bank needs more than %d issue runs: unsupported", C2_MAX_RUNS);
-            if (used == 0) stage_src = (uint32_t)tt.w_off[t] + 2 * kp * nt;
-            uint4 e;
-            e.x = (kc_lo + 2 * kp) * (uint32_t)Rp + (uint32_t)t;
-            e.y = (used >> 4) | (nt << 16);
-            e.z = (1u << 4) | (1u << 7) | (1u << 10) | ((nt >> 3) << 17) | ((128u >> 4) << 24);
-            e.w = n_lo | (n << 9) | (used == 0 ? RF_FIRST : 0u) | (!init_done ? RF_INIT : 0u);
-            sc->runs[n_runs++] = e;
+            TSC_REQUIRE(n_runs < C2_MAX_RUNS - 1, "kernel bank needs more than %d issue runs: unsupported", C2_MAX_RUNS - 1);
+            if (used == 0) stage_src = pair ? (uint32_t)tt.w_off[t] / 2 + kp * nt       // in this CTA's stream (packed_row())
+                                            : (uint32_t)tt.w_off[t] + 2 * kp * nt;
+            uint4 e, f;
+            e.x = (kc_lo + 2 * kp) * (uint32_t)Rp + (uint32_t)((knob2_debug() & 2) ? (t & ~7) : t);    // (debug 2: taps aligned to 128 B -- garbage results, timing experiment)
+            e.y = (used >> 4) | (rows << 16);
+            e.z = (1u << 4) | (1u << 7) | (1u << 10) | ((nt >> 3) << 17) | (((pair ? 256u : 128u) >> 4) << 24);
+            e.w = n_lo;
+            f.x = n;
+            f.y = 2 * rows;                                  // two chunks of `rows` rows per K step
+            f.z = init_done ? 1u : 0u;
+            f.w = used == 0 ? RF_FIRST : 0u;
+            sc->runs[2 * n_runs] = e;
+            sc->runs[2 * n_runs + 1] = f;
+            ++n_runs;
             init_done = true;
             used += n * step_bytes;
             kp += n;
@@ -564,13 +748,15 @@ static int build_sched(int direction, int Cin, int Cout, int Kmax, const int* s_
     if (close_stage() != 0) return -1;
     sc->n_runs = n_runs;
     sc->n_stages = n_stages;
+    sc->half_rows16 = tt.total_rows / 2;
     return 0;
 }
 
 struct SchedKey {
-    int direction, Cin, Cout, Kmax;
+    int pair, direction, Cin, Cout, Kmax;
     std::vector<int> s;
     bool operator<(const SchedKey& o) const {
+        if (pair != o.pair) return pair < o.pair;
         if (direction != o.direction) return direction < o.direction;
         if (Cin != o.Cin) return Cin < o.Cin;
         if (Cout != o.Cout) return Cout < o.Cout;
@@ -580,15 +766,15 @@ struct SchedKey {
 };
 
 // Host-side cache of the schedules (the only state of this file besides the attribute opt-in; behind a mutex).
-static const ConvSched* get_sched(int direction, int Cin, int Cout, int Kmax, const int* s_of_tap) {
+static const ConvSched* get_sched(bool pair, int direction, int Cin, int Cout, int Kmax, const int* s_of_tap) {
     static std::mutex mu;
     static std::map<SchedKey, std::unique_ptr<ConvSched>> cache;
-    SchedKey key{direction, Cin, Cout, Kmax, std::vector<int>(s_of_tap, s_of_tap + (Kmax > 0 && Kmax <= TSC_MAX_TAPS ? Kmax : 0))};
+    SchedKey key{pair ? 1 : 0, direction, Cin, Cout, Kmax, std::vector<int>(s_of_tap, s_of_tap + (Kmax > 0 && Kmax <= TSC_MAX_TAPS ? Kmax : 0))};
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(key);
     if (it != cache.end()) return it->second.get();
     std::unique_ptr<ConvSched> sc(new ConvSched);
-    if (build_sched(direction, Cin, Cout, Kmax, s_of_tap, sc.get()) != 0) return nullptr;
+    if (build_sched(pair, direction, Cin, Cout, Kmax, s_of_tap, sc.get()) != 0) return nullptr;
     const ConvSched* out = sc.get();
     cache.emplace(std::move(key), std::move(sc));
     return out;
@@ -626,7 +812,8 @@ int osconv2_tc(int direction, const void* x, int dtype, const void* w, const flo
                const tsc_conv_epilogue* epi, int B, int L, int Cin, int Cout, int Kmax, const int* s_of_tap, cudaStream_t cs) {
     using namespace tc;
     TSC_REQUIRE(dtype == TSC_BF16, "the tcgen05 engine takes bf16 operands");
-    const ConvSched* sc = get_sched(direction, Cin, Cout, Kmax, s_of_tap);
+    const bool pair = packed_split();       // the CTA-pair variant (and its split packed layout): an opt-in experiment
+    const ConvSched* sc = get_sched(pair, direction, Cin, Cout, Kmax, s_of_tap);
     if (!sc) return -1;
     const bool fwd = direction == TSC_DIR_FWD;
     Conv2Params p;
@@ -669,14 +856,18 @@ int osconv2_tc(int direction, const void* x, int dtype, const void* w, const flo
     p.x_bytes = p.kc * p.Rp * 16;
     p.acc_stride = p.np <= 32 ? 32 : p.np <= 64 ? 64 : p.np <= 128 ? 128 : 256;
     const int nsm = sm_count();
-    // one tile per CTA while the tiles fit one wave (single-buffered, half-SM budgets: CTAs of two streams share an SM);
-    // otherwise one persistent CTA per SM with double-buffered accumulator (and, if it fits, activation) tiles
-    const bool persistent = p.n_tiles > nsm;
-    int grid = persistent ? nsm : p.n_tiles;
-    if (persistent && knob2_grid() > 0 && knob2_grid() < grid) grid = knob2_grid();
+    // one tile pair per CTA pair while the pairs fit one wave (single-buffered, half-SM budgets: CTAs of two streams share an
+    // SM); otherwise one persistent CTA pair per SM pair with double-buffered accumulator (and, if it fits, activation) tiles
+    const int ncta = pair ? 2 : 1;
+    const int n_pairs = (p.n_tiles + ncta - 1) / ncta, max_pairs = nsm / ncta;     // units = tiles, or tile pairs
+    const bool persistent = n_pairs > max_pairs;
+    int grid_pairs = persistent ? max_pairs : n_pairs;
+    if (persistent && knob2_grid() > 0 && knob2_grid() < grid_pairs) grid_pairs = knob2_grid();
+    const int grid = ncta * grid_pairs;
     p.na = persistent ? 2 : 1;
-    p.tiles_base = p.n_tiles / grid;
-    p.tiles_rem = p.n_tiles % grid;
+    p.tiles_base = n_pairs / grid_pairs;
+    p.tiles_rem = n_pairs % grid_pairs;
+    p.half_rows16 = sc->half_rows16;
     p.tmem_cols = p.acc_stride * p.na;
     p.off_bias = C2_HDR;
     p.off_wstat = p.off_bias + 4 * p.np * 4;
@@ -708,14 +899,39 @@ int osconv2_tc(int direction, const void* x, int dtype, const void* w, const flo
     static OnceAttr attr_once;             // once per process: opt in to the full 227 KB of dynamic shared memory
     {
         const cudaError_t e = run_once(attr_once, [] {
-            cudaError_t r = cudaFuncSetAttribute(osconv2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-            if (r == cudaSuccess) r = cudaFuncSetAttribute(osconv2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            cudaError_t r = cudaSuccess;
+#define TSC_C2_OPTIN(A, D, P) if (r == cudaSuccess) r = cudaFuncSetAttribute(osconv2_kernel<A, D, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+            TSC_C2_OPTIN(false, false, false); TSC_C2_OPTIN(true, false, false); TSC_C2_OPTIN(false, true, false); TSC_C2_OPTIN(true, true, false);
+            TSC_C2_OPTIN(false, false, true); TSC_C2_OPTIN(true, false, true); TSC_C2_OPTIN(false, true, true); TSC_C2_OPTIN(true, true, true);
+#undef TSC_C2_OPTIN
             return r;
         });
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     }
-    const cudaError_t le = p.aff_out ? launch_pdl(osconv2_kernel<true>, dim3(grid), dim3(C2_THREADS), (size_t)smem, cs, xmap, *sc, p)
-                                     : launch_pdl(osconv2_kernel<false>, dim3(grid), dim3(C2_THREADS), (size_t)smem, cs, xmap, *sc, p);
+    // a cluster of two CTAs (the tcgen05 CTA pair) per tile pair
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(C2_THREADS);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = cs;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)ncta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    const bool dbg = p.tl != nullptr;       // the instrumented instantiation only when a timeline buffer is set
+    cudaError_t le;
+#define TSC_C2_LAUNCH(A, D, P) le = cudaLaunchKernelEx(&cfg, osconv2_kernel<A, D, P>, xmap, *sc, p)
+    if (pair) {
+        if (p.aff_out) { if (dbg) TSC_C2_LAUNCH(true, true, true); else TSC_C2_LAUNCH(true, false, true); }
+        else           { if (dbg) TSC_C2_LAUNCH(false, true, true); else TSC_C2_LAUNCH(false, false, true); }
+    } else {
+        if (p.aff_out) { if (dbg) TSC_C2_LAUNCH(true, true, false); else TSC_C2_LAUNCH(true, false, false); }
+        else           { if (dbg) TSC_C2_LAUNCH(false, true, false); else TSC_C2_LAUNCH(false, false, false); }
+    }
+#undef TSC_C2_LAUNCH
     if (le != cudaSuccess) { set_error("osconv2 launch: %s", cudaGetErrorString(le)); return (int)le; }
     TSC_LAUNCH_CHECK();
     return 0;

@@ -53,10 +53,7 @@ int tsc_osconv(int engine, int direction, const void* x, int dtype, const void* 
         return osconv_simt(direction, x, dtype, w, bias, y, B, L, Cin, Cout, Kmax, s_of_tap, (cudaStream_t)stream);
     }
     if (engine == TSC_ENGINE_TCGEN05) {
-        // the round-1 kernel (plan in shared memory, one tile per CTA) stays selectable for A/B measurements: TSC_CONV_V1=1
-        static const bool v1 = [] { const char* e = getenv("TSC_CONV_V1"); return e && e[0] == '1'; }();
-        if (v1 && plan)
-            return osconv_tc(direction, x, dtype, w, plan, bias, y, epilogue, B, L, Cin, Cout, Kmax, s_of_tap, (cudaStream_t)stream);
+        (void)plan;               // (round-1 interface: the schedule now travels in the kernel parameter block)
         return osconv2_tc(direction, x, dtype, w, bias, y, epilogue, B, L, Cin, Cout, Kmax, s_of_tap, (cudaStream_t)stream);
     }
     TSC_REQUIRE(false, "bad engine %d", engine);

@@ -16,7 +16,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) osconv_simt_kernel(const T* __restrict__ x, const T* __restrict__ w,
                                                           const float* __restrict__ bias, int nbias,
                                                           float* __restrict__ y, int B, int L,
-                                                          const __grid_constant__ TapTable tt) {
+                                                          const __grid_constant__ TapTable tt, int split) {
     __shared__ float xs[8][CT_POS + TSC_MAX_TAPS];
     __shared__ __align__(16) float ws[CT_TG][8][CT_N];
     const int ltiles = (L + CT_POS - 1) / CT_POS;
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) osconv_simt_kernel(const T* __restrict__ 
                     const int t = tt.order[oi];
                     const int n_lo = tt.n_lo[t], kc_lo = tt.kc_lo[t], nn = n0 + n;
                     if (kcI >= kc_lo && nn >= n_lo && nn < np)
-                        v.load(w + ((long long)tt.w_off[t] + (long long)(kcI - kc_lo) * (np - n_lo) + (nn - n_lo)) * 8);
+                        v.load(w + packed_row(tt.total_rows, tt.w_off[t], np - n_lo, kcI - kc_lo, nn - n_lo, split) * 8);
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) ws[tgi][j][n] = v.v[j];
@@ -196,9 +196,9 @@ int osconv_simt(int direction, const void* x, int dtype, const void* w, const fl
     const int nbias = direction == TSC_DIR_FWD ? Cout : 0;
     const float* bp = direction == TSC_DIR_FWD ? bias : nullptr;
     if (dtype == TSC_BF16)
-        osconv_simt_kernel<__nv_bfloat16><<<grid, 256, 0, cs>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bp, nbias, y, B, L, tt);
+        osconv_simt_kernel<__nv_bfloat16><<<grid, 256, 0, cs>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bp, nbias, y, B, L, tt, packed_split() ? 1 : 0);
     else
-        osconv_simt_kernel<float><<<grid, 256, 0, cs>>>((const float*)x, (const float*)w, bp, nbias, y, B, L, tt);
+        osconv_simt_kernel<float><<<grid, 256, 0, cs>>>((const float*)x, (const float*)w, bp, nbias, y, B, L, tt, packed_split() ? 1 : 0);
     TSC_LAUNCH_CHECK();
     return 0;
 }

@@ -62,14 +62,13 @@ template <typename T>
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ W, T* __restrict__ packed,
                                                              int direction, int Cin, int Cout, int Kmax,
                                                              const __grid_constant__ TapTable tt,
-                                                             const __grid_constant__ STable st) {
+                                                             const __grid_constant__ STable st, int split) {
     const int t = tt.order[blockIdx.y];
     const int n_lo = tt.n_lo[t], kc_lo = tt.kc_lo[t];
     const int nrows = tt.np - n_lo;
     const int elems = (tt.kc - kc_lo) * nrows * 8;
     const int wt = direction == TSC_DIR_FWD ? t : Kmax - 1 - t;
     const int s = st.s[wt];
-    T* blob = packed + (long long)tt.w_off[t] * 8;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < elems; e += gridDim.x * blockDim.x) {
         const int j = e & 7;
         const int n = n_lo + (e >> 3) % nrows;
@@ -79,7 +78,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
         const int ci = direction == TSC_DIR_FWD ? k : n;
         float v = 0.f;
         if (co < Cout && ci < Cin && co >= s) v = W[((long long)co * Cin + ci) * Kmax + wt];
-        blob[e] = from_f32<T>(v);
+        packed[packed_row(tt.total_rows, tt.w_off[t], nrows, kch - kc_lo, n - n_lo, split) * 8 + j] = from_f32<T>(v);
     }
 }
 
@@ -91,7 +90,7 @@ __global__ void __launch_bounds__(256) pack_pair_kernel(float* __restrict__ W, T
                                                          int Cin, int Cout, int Kmax,
                                                          const __grid_constant__ TapTable tf,
                                                          const __grid_constant__ TapTable td,
-                                                         const __grid_constant__ STable st, int nd, int zero_masked) {
+                                                         const __grid_constant__ STable st, int nd, int zero_masked, int split) {
     const int nf = tf.n_order;
     int y = blockIdx.y;
     if (y >= nf + nd) {
@@ -113,16 +112,17 @@ __global__ void __launch_bounds__(256) pack_pair_kernel(float* __restrict__ W, T
     const int elems = (tt.kc - kc_lo) * nrows * 8;
     const int wt = fwd ? t : Kmax - 1 - t;
     const int s = st.s[wt];
-    T* blob = (fwd ? pf : pd) + (long long)tt.w_off[t] * 8;
+    T* out = fwd ? pf : pd;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < elems; e += gridDim.x * blockDim.x) {
         const int j = e & 7;
         const int n = n_lo + (e >> 3) % nrows;
-        const int k = (kc_lo + (e >> 3) / nrows) * 8 + j;
+        const int kch = kc_lo + (e >> 3) / nrows;
+        const int k = kch * 8 + j;
         const int co = fwd ? n : k;
         const int ci = fwd ? k : n;
         float v = 0.f;
         if (co < Cout && ci < Cin && co >= s) v = W[((long long)co * Cin + ci) * Kmax + wt];
-        blob[e] = from_f32<T>(v);
+        out[packed_row(tt.total_rows, tt.w_off[t], nrows, kch - kc_lo, n - n_lo, split) * 8 + j] = from_f32<T>(v);
     }
 }
 
@@ -211,9 +211,9 @@ int tsc_pack_weights(int direction, int dtype, float* W, void* packed, int Cin, 
     const int max_elems = tt.kc * tt.np * 8;
     dim3 grid(cdiv(max_elems, 256 * 4), tt.n_order);
     if (dtype == TSC_BF16)
-        pack_weights_kernel<__nv_bfloat16><<<grid, 256, 0, cs>>>(W, (__nv_bfloat16*)packed, direction, Cin, Cout, Kmax, tt, st);
+        pack_weights_kernel<__nv_bfloat16><<<grid, 256, 0, cs>>>(W, (__nv_bfloat16*)packed, direction, Cin, Cout, Kmax, tt, st, packed_split() ? 1 : 0);
     else if (dtype == TSC_F32)
-        pack_weights_kernel<float><<<grid, 256, 0, cs>>>(W, (float*)packed, direction, Cin, Cout, Kmax, tt, st);
+        pack_weights_kernel<float><<<grid, 256, 0, cs>>>(W, (float*)packed, direction, Cin, Cout, Kmax, tt, st, packed_split() ? 1 : 0);
     else
         TSC_REQUIRE(false, "bad dtype %d", dtype);
     TSC_LAUNCH_CHECK();
@@ -237,10 +237,10 @@ extern "C" int tsc_pack_weights_pair(int dtype, float* W, void* packed_fwd, void
     cudaStream_t cs = (cudaStream_t)stream;
     if (dtype == TSC_BF16)
         pack_pair_kernel<__nv_bfloat16><<<grid, 256, 0, cs>>>(W, (__nv_bfloat16*)packed_fwd, (__nv_bfloat16*)packed_dgrad, Cin,
-                                                            Cout, Kmax, tf, td, st, nd, zero_masked);
+                                                            Cout, Kmax, tf, td, st, nd, zero_masked, packed_split() ? 1 : 0);
     else if (dtype == TSC_F32)
         pack_pair_kernel<float><<<grid, 256, 0, cs>>>(W, (float*)packed_fwd, (float*)packed_dgrad, Cin, Cout, Kmax, tf, td,
-                                                    st, nd, zero_masked);
+                                                    st, nd, zero_masked, packed_split() ? 1 : 0);
     else
         TSC_REQUIRE(false, "bad dtype %d", dtype);
     TSC_LAUNCH_CHECK();
@@ -262,6 +262,7 @@ struct PackTaps {
     short kc_lo_d[TSC_MAX_TAPS];  // dgrad  : first stored out-channel chunk of conv tap t' (even), -1 = dead
     int off_f[TSC_MAX_TAPS];      // blob offsets in 16 B rows
     int off_d[TSC_MAX_TAPS];
+    int tot_f, tot_d;             // total rows of the forward / dgrad bank (packed_row's total_rows)
 };
 
 __device__ void pack_build_taps(const tsc_pack_layer& ly, PackTaps* pt, int* scratch /* [2 * TSC_MAX_TAPS + 1] */) {
@@ -307,11 +308,22 @@ __device__ void pack_build_taps(const tsc_pack_layer& ly, PackTaps* pt, int* scr
         pt->off_d[t] = kd == 0x7fffffff ? 0 : offd;
         if (t == first) pt->n_lo_f[t] = 0;
     }
+    if (t == 0) {
+        // bank totals (the split layout's second stream starts at half of them)
+        int tf = 0, td = 0;
+        for (int u = 0; u < Kmax; ++u) {
+            const int ku = key_f[u], kud = key_d[u];
+            if (ku != 0x7fffffff) tf += kc_f * (np_f - (ku < 0 ? 0 : ku));
+            if (kud != 0x7fffffff) td += (kc_d - kud) * np_d;
+        }
+        pt->tot_f = tf;
+        pt->tot_d = td;
+    }
     __syncthreads();
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) pack_multi_kernel(const __grid_constant__ tsc_pack_batch batch) {
+__global__ void __launch_bounds__(256) pack_multi_kernel(const __grid_constant__ tsc_pack_batch batch, int split) {
     extern __shared__ float wsm[];                    // [8][16][Kmax]
     __shared__ PackTaps pt;
     __shared__ int scratch[2 * TSC_MAX_TAPS + 1];
@@ -358,7 +370,7 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const __grid_constant__
         Row8<T> row;
 #pragma unroll
         for (int j = 0; j < 8; ++j) row.v[j] = wsm[(r * 16 + k * 8 + j) * Kmax + t];
-        row.store(pf + ((size_t)pt.off_f[t] + (size_t)(kp * 2 + k) * nt + (co - n_lo)) * 8);
+        row.store(pf + packed_row(pt.tot_f, pt.off_f[t], nt, kp * 2 + k, co - n_lo, split) * 8);
     }
     (void)kc_f;
     // ---- dgrad rows: (t', n = in channel of this pair) -> the 8 out channels of this chunk ----
@@ -371,7 +383,7 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const __grid_constant__
             Row8<T> row;
 #pragma unroll
             for (int j = 0; j < 8; ++j) row.v[j] = wsm[(j * 16 + q) * Kmax + wt];
-            row.store(pd + ((size_t)pt.off_d[t] + (size_t)(cc - kc_lo) * np_d + (ci0 + q)) * 8);
+            row.store(pd + packed_row(pt.tot_d, pt.off_d[t], np_d, cc - kc_lo, ci0 + q, split) * 8);
         }
     }
 }
@@ -395,10 +407,10 @@ extern "C" int tsc_pack_weights_multi(int dtype, const tsc_pack_batch* batch, ts
     cudaStream_t cs = (cudaStream_t)stream;
     if (dtype == TSC_BF16) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(pack_multi_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        launch_pdl(pack_multi_kernel<__nv_bfloat16>, grid, dim3(256), (size_t)smem, cs, *batch);
+        launch_pdl(pack_multi_kernel<__nv_bfloat16>, grid, dim3(256), (size_t)smem, cs, *batch, packed_split() ? 1 : 0);
     } else if (dtype == TSC_F32) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(pack_multi_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        launch_pdl(pack_multi_kernel<float>, grid, dim3(256), (size_t)smem, cs, *batch);
+        launch_pdl(pack_multi_kernel<float>, grid, dim3(256), (size_t)smem, cs, *batch, packed_split() ? 1 : 0);
     } else {
         TSC_REQUIRE(false, "bad dtype %d", dtype);
     }

@@ -50,12 +50,12 @@ def main():
         t = tl.cpu().tolist()
         print(f"timeline[{name}] CTA0 cycles since entry: " + ", ".join(f"{n}={v - t[0]}" for n, v in zip(names, t)))
         if a.stages and name != "wgrad":
-            print("  stage: issuer[wait-begin, wait-end, issued+committed]  producer[wait-begin, wait-end, copy issued]")
+            print("  stage: issuer[wait-begin, both halves landed, -, issued+committed]  producer[wait-begin, slot free]")
             for i in range(48):
                 r = t[8 + i * 8: 16 + i * 8]
                 if r[1] == 0:
                     break
-                print(f"   {i:3d}: " + " ".join(f"{v - t[0]:7d}" for v in r[0:3]) + "   | " + " ".join(f"{v - t[0]:7d}" for v in r[4:7]))
+                print(f"   {i:3d}: " + " ".join(f"{v - t[0]:7d}" for v in r[0:4]) + "   | " + " ".join(f"{v - t[0]:7d}" for v in r[4:6]))
         if name == "wgrad":
             it = [v - t[0] for v in t[8:32] if v]
             print("  wgrad tile-ready times (cycles since entry): " + " ".join(str(v) for v in it))
