@@ -246,7 +246,7 @@ class KernelProfile:
     """Times every C-ABI call family with CUDA events on the launching stream (instrumented pass, run after
     the timed region; never part of a reported step time)."""
     LAUNCHES = dict(ncl_to_c8=1, c8_to_ncl=1, pack_weights=1, pack_weights_pair=1, pack_weights_multi=1, rmsprop_step=1,
-                    osconv=1, oswgrad=2, bn_stats=2, bn_eval_coeffs=1, bn_apply=1, bn_bwd_reduce=2, bn_bwd_apply=1,
+                    osconv=1, oswgrad=2, head_ce_fwd=1, head_ce_bwd=1, weighted_scalar_sum=1, bn_stats=2, bn_eval_coeffs=1, bn_apply=1, bn_bwd_reduce=2, bn_bwd_apply=1,
                     bn_apply_fused=1, bn_bwd_top=1, bn_bwd_top_pooled=1, bn_bwd_apply_fused=1, adain_fwd=1, adain_bwd=1, gram_loss_fwd=2,
                     gram_loss_bwd=1, rowstats=1, multi_l2norm=2, class_precision=1, entropy_vote=1, cdan_fuse_fwd=1, cdan_fuse_bwd=1, cdan_distance_fwd=1, cdan_distance_bwd=1)
 

@@ -111,6 +111,12 @@ def _run_stack(layers, x, shortcut=None, final_relu=False, pooled=False):
     return out
 
 
+def _own_head(hidden: nn.Linear, pooled: torch.Tensor) -> bool:
+    """The fused head kernel covers the classifier shapes of the reference (<= 64 classes, <= 256 pooled channels, fp32)."""
+    return (pooled.is_cuda and hidden.bias is not None and hidden.out_features <= 64 and hidden.in_features <= 1024
+            and os.environ.get("TSC_TORCH_HEAD") != "1")
+
+
 class build_layer_with_layer_parameter(nn.Module):
     """One OS layer: mask*W -> zero pad -> Conv1d(Cin, sum Cout, Kmax) -> BatchNorm1d -> optional ReLU
     (reference lines 46-77).
@@ -158,8 +164,23 @@ class OS_CNN(nn.Module):
     def forward(self, X):
         X_f = _run_stack(list(self.net), X, pooled=True)        # AdaptiveAvgPool1d(1) + squeeze(-1), fused into the stack
         if not self.few_shot:
+            if _own_head(self.hidden, X_f):
+                return _F.head_cross_entropy(X_f, self.hidden.weight, self.hidden.bias, None)[0], X_f
             return self.hidden(X_f), X_f
         return X_f.unsqueeze(-1), X_f
+
+    def forward_loss(self, X, labels):
+        """(logits, pooled, mean cross-entropy against ``labels``): ``forward`` followed by ``nn.CrossEntropyLoss()`` as the
+        trainer applies it (train_and_test.py:593-603), with the Linear head and the loss in ONE kernel each way.  Beyond
+        the reference surface; used by train_step."""
+        if self.few_shot:
+            raise RuntimeError("few_shot classifiers have no Linear head to train with a cross-entropy loss")
+        X_f = _run_stack(list(self.net), X, pooled=True)
+        if _own_head(self.hidden, X_f):
+            logits, ce = _F.head_cross_entropy(X_f, self.hidden.weight, self.hidden.bias, labels.contiguous())
+            return logits, X_f, ce
+        logits = self.hidden(X_f)
+        return logits, X_f, torch.nn.functional.cross_entropy(logits, labels)
 
 
 class OS_block(nn.Module):

@@ -131,6 +131,10 @@ SIGNATURES = {
     "tsc_multi_l2norm": (_i, [ctypes.POINTER(TensorList), _p, _p, _p]),
     "tsc_class_precision": (_i, [_p, _p, _p, _p, _p, _i, _i, _p]),
     "tsc_entropy_vote": (_i, [_p, _p, _p, _p, _i, _i, _i, _f, _f, _p]),
+    "tsc_head_ce_workspace_bytes": (_sz, [_i]),
+    "tsc_head_ce_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "tsc_head_ce_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "tsc_weighted_scalar_sum": (_i, [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_float), _i, _p, _p]),
     "tsc_debug_read_and_clear_watchdog": (_i, [_ip]),
     "tsc_debug_set_timeline": (_i, [_p]),
 }

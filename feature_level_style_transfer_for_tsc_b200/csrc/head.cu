@@ -8,6 +8,7 @@
 //   g[b,k]      = dlogits[b,k] + dloss * (p[b,k] - [k == y_b]) / B                  (dlogits: gradient arriving at the logits
 //   dpooled = g W;   dW = g^T pooled;   dbias = sum_b g                              from other consumers, e.g. C-DAN; nullable)
 #include "common.cuh"
+#include <algorithm>
 
 namespace tsc {
 

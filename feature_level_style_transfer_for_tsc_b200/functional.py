@@ -489,3 +489,57 @@ def gram_style_loss(a: torch.Tensor, b: torch.Tensor, engine: Optional[int] = No
     if a.shape != b.shape:
         raise RuntimeError(f"gram_style_loss needs equal shapes, got {tuple(a.shape)} and {tuple(b.shape)}")
     return GramStyleLossFunction.apply(a, b, ops.get_engine("gram") if engine is None else engine)
+
+
+class HeadCEFunction(torch.autograd.Function):
+    """Linear head + softmax cross-entropy (ops.head_ce_fwd / head_ce_bwd).  Returns (logits, loss); ``labels`` None gives
+    logits only (loss is a zero scalar that must not be used).  With ``direct`` the parameter gradients are added into the
+    existing ``.grad`` buffers inside the kernel (flat data-parallel bucket) and reported as None."""
+
+    @staticmethod
+    def forward(ctx, pooled, W, bias, labels, direct):
+        pooled = pooled.contiguous()
+        logits, prob, loss = ops.head_ce_fwd(pooled, W, bias, labels)
+        ctx.save_for_backward(pooled, W, bias, prob, labels if labels is not None else torch.empty(0, device=pooled.device))
+        ctx.has_labels = labels is not None
+        ctx.direct = bool(direct)
+        ctx.need_dpooled = pooled.requires_grad
+        ctx.set_materialize_grads(False)          # an unused output arrives as None, not as a zero-filled tensor
+        return logits, loss
+
+    @staticmethod
+    def backward(ctx, dlogits, dloss):
+        pooled, W, bias, prob, labels = ctx.saved_tensors
+        use_loss = ctx.has_labels and dloss is not None
+        dl = dlogits.contiguous().float() if dlogits is not None else None
+        if dl is None and not use_loss:
+            return None, None, None, None, None
+        direct = ctx.direct and W.grad is not None and bias.grad is not None and W.grad.is_contiguous()
+        dpooled, dW, db = ops.head_ce_bwd(dloss.contiguous().float() if use_loss else None, dl, prob,
+                                          labels if use_loss else None, pooled, W, ctx.need_dpooled,
+                                          W.grad if direct else None, bias.grad if direct else None)
+        if direct:
+            return dpooled, None, None, None, None
+        return dpooled, dW, db, None, None
+
+
+def head_cross_entropy(pooled: torch.Tensor, W: torch.Tensor, bias: torch.Tensor, labels: Optional[torch.Tensor]):
+    """(logits, mean cross-entropy) of ``Linear(W, bias)`` over pooled features [B, C]; one kernel forward, one backward."""
+    return HeadCEFunction.apply(pooled, W, bias, labels, _DIRECT_GRADS)
+
+
+class _WeightedSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, weights, *terms):
+        ctx.weights = [float(w) for w in weights]
+        return ops.weighted_scalar_sum([t.contiguous().float() for t in terms], ctx.weights)
+
+    @staticmethod
+    def backward(ctx, dout):
+        # terms with weight 1 share the incoming gradient tensor (no launch)
+        return (None, *[dout if w == 1.0 else dout * w for w in ctx.weights])
+
+
+def weighted_loss_sum(terms, weights) -> torch.Tensor:
+    """sum_i weights[i] * terms[i] of scalar losses (the total loss of a step) in one launch."""
+    return _WeightedSum.apply(list(weights), *terms)

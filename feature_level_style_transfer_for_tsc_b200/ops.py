@@ -626,6 +626,67 @@ def cdan_distance_bwd(dloss, saved, B: int):
     return du, dcritic
 
 
+_HEAD_WS = {}
+
+
+def _head_workspace(B: int, device, owner: int) -> torch.Tensor:
+    """Zero-initialised scratch of the head kernel, one per (head weight, batch): the kernel leaves it zeroed, so it is
+    allocated (and cleared) once -- no fill launch per step.  Keyed by the weight's address: the classifiers of a step run
+    on different streams, but one head never runs twice at the same time."""
+    key = (str(device), owner, B)
+    ws = _HEAD_WS.get(key)
+    if ws is None:
+        n = int(L.load().tsc_head_ce_workspace_bytes(B)) // 4 + 4
+        ws = _HEAD_WS[key] = torch.zeros(n, device=device, dtype=torch.float32)
+    return ws
+
+
+def head_ce_fwd(pooled: torch.Tensor, W: torch.Tensor, bias: torch.Tensor, labels: Optional[torch.Tensor]):
+    """(logits [B,K], prob [B,K], loss () | None) of Linear + softmax cross-entropy (mean over the batch), one launch."""
+    _req(pooled, name="pooled"); _req(W, name="head weight"); _req(bias, name="head bias")
+    B, C = pooled.shape
+    K = W.shape[0]
+    if tuple(W.shape) != (K, C) or bias.numel() != K:
+        raise RuntimeError(f"head shapes do not agree: pooled {tuple(pooled.shape)}, W {tuple(W.shape)}, bias {tuple(bias.shape)}")
+    logits = torch.empty((B, K), device=pooled.device, dtype=torch.float32)
+    prob = torch.empty((B, K), device=pooled.device, dtype=torch.float32)
+    loss = ws = None
+    if labels is not None:
+        _req(labels, torch.int64, "labels")
+        if labels.numel() != B:
+            raise RuntimeError(f"{labels.numel()} labels for {B} rows")
+        loss = torch.empty((), device=pooled.device, dtype=torch.float32)
+        ws = _head_workspace(B, pooled.device, W.data_ptr())
+    L.check(L.load().tsc_head_ce_fwd(_ptr(pooled), _ptr(W), _ptr(bias), _ptr(labels), _ptr(logits), _ptr(prob), _ptr(loss),
+                                     _ptr(ws), B, C, K, _stream()), "tsc_head_ce_fwd")
+    return logits, prob, loss
+
+
+def head_ce_bwd(dloss, dlogits, prob, labels, pooled, W, need_dpooled: bool, dW_out=None, dbias_out=None):
+    """(dpooled | None, dW, dbias); with dW_out / dbias_out the parameter gradients are ADDED in place."""
+    B, C = pooled.shape
+    K = W.shape[0]
+    dpooled = torch.empty_like(pooled) if need_dpooled else None
+    acc = dW_out is not None
+    dW = dW_out if acc else torch.empty_like(W)
+    db = dbias_out if acc else torch.empty(K, device=W.device, dtype=torch.float32)
+    L.check(L.load().tsc_head_ce_bwd(_ptr(dloss), _ptr(dlogits), _ptr(prob), _ptr(labels), _ptr(pooled), _ptr(W), _ptr(dpooled),
+                                     _ptr(dW), _ptr(db), 1 if acc else 0, B, C, K, _stream()), "tsc_head_ce_bwd")
+    return dpooled, dW, db
+
+
+def weighted_scalar_sum(terms: Sequence[torch.Tensor], weights: Sequence[float]) -> torch.Tensor:
+    """sum_i weights[i] * terms[i] for up to 8 fp32 CUDA scalars, one launch."""
+    n = len(terms)
+    if not 1 <= n <= 8 or len(weights) != n:
+        raise RuntimeError("weighted_scalar_sum takes 1..8 scalars and as many weights")
+    ptrs = (ctypes.c_void_p * n)(*[_req(t, name=f"term {i}").data_ptr() for i, t in enumerate(terms)])
+    ws = (ctypes.c_float * n)(*[float(w) for w in weights])
+    out = torch.empty((), device=terms[0].device, dtype=torch.float32)
+    L.check(L.load().tsc_weighted_scalar_sum(ptrs, ws, n, _ptr(out), _stream()), "tsc_weighted_scalar_sum")
+    return out
+
+
 def multi_l2norm(tensors: Sequence[torch.Tensor]) -> torch.Tensor:
     """[||t_0||, ..., ||t_{n-1}||, sum of them] (fp32, device) for up to L.MAX_LIST fp32 CUDA tensors, two launches."""
     if not 1 <= len(tensors) <= L.MAX_LIST:

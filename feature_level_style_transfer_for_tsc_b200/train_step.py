@@ -67,10 +67,8 @@ class StyleTransferModelSet(nn.Module):
             ssf = self.du(sf)
             s2t = TF.adain(ssf, tf)
             l_style = TF.gram_style_loss(s2t, tf)
-            logits_t, _ = self.cl_t(tf)
-            logits_s, _ = self.cl_s(ssf)
-            ce_t = F.cross_entropy(logits_t, yt)
-            ce_s = F.cross_entropy(logits_s, ys)
+            logits_t, _, ce_t = self.cl_t.forward_loss(tf, yt)
+            logits_s, _, ce_s = self.cl_s.forward_loss(ssf, ys)
         else:
             # Every kernel of one branch is a single wave of <= 148 CTAs with long load / epilogue phases, and the conv,
             # wgrad and BatchNorm kernels keep to half of an SM's shared memory and TMEM: the two branches' launches are
@@ -84,19 +82,19 @@ class StyleTransferModelSet(nn.Module):
                 sf = self.fe_s(xs)
                 ssf = self.du(sf)
             tf = self.fe_t(xt)
-            logits_t, _ = self.cl_t(tf)               # needs tf only: runs while the source branch is still busy
-            ce_t = F.cross_entropy(logits_t, yt)
+            logits_t, _, ce_t = self.cl_t.forward_loss(tf, yt)      # needs tf only: runs while the source branch is still busy
             main.wait_stream(side)
             ssf.record_stream(main)
             s2t = TF.adain(ssf, tf)
             l_style = TF.gram_style_loss(s2t, tf)
             with torch.cuda.stream(side):
-                logits_s, _ = self.cl_s(ssf)
-                ce_s = F.cross_entropy(logits_s, ys)
+                logits_s, _, ce_s = self.cl_s.forward_loss(ssf, ys)
             main.wait_stream(side)
             logits_s.record_stream(main)
             ce_s.record_stream(main)
-        return dict(loss=ce_t + ce_s + style_weight * l_style, ce_t=ce_t, ce_s=ce_s, l_style=l_style,
+        loss = TF.weighted_loss_sum([ce_t, ce_s, l_style], [1.0, 1.0, float(style_weight)]) if xt.is_cuda \
+            else ce_t + ce_s + style_weight * l_style
+        return dict(loss=loss, ce_t=ce_t, ce_s=ce_s, l_style=l_style,
                     logits_t=logits_t, logits_s=logits_s, tf=tf, ssf=ssf, s2t=s2t)
 
 
@@ -212,8 +210,8 @@ class SingleDomainModelSet(nn.Module):
         self.feature_channels = cf
 
     def forward(self, x, y, style_weight: float = 1.0) -> Dict[str, torch.Tensor]:
-        logits, _ = self.cl(self.fe(x))
-        return dict(loss=F.cross_entropy(logits, y), logits=logits)
+        logits, _, ce = self.cl.forward_loss(self.fe(x), y)
+        return dict(loss=ce, logits=logits)
 
 
 class FlatParameters:

@@ -319,6 +319,24 @@ int tsc_class_precision(const float* logits, const long long* labels, int* pred,
 int tsc_entropy_vote(const float* logits, const double* precision, float* score, int* pred, int M, int N, int K,
                      float entropy_gain, float weight_base, tsc_stream_t stream);
 
+/* ---- classifier head fused with the training loss: replaces `self.hidden(X_f)` (OS_CNN/OS_CNN.py:108-109) followed by
+ * nn.CrossEntropyLoss (train_and_test.py:593-603) and their autograd -- one launch forward, one backward.
+ *   logits[b,k] = bias[k] + sum_c pooled[b,c] W[k,c];  prob = softmax(logits);  loss = -(1/B) sum_b log prob[b, labels[b]]
+ *   backward: g = dlogits (nullable: gradient from other consumers of the logits) + dloss * (prob - onehot) / B
+ *             (dloss: device scalar, NULL = 1; labels NULL = no loss term);  dpooled = g W (nullable);  dW = g^T pooled;
+ *             dbias = sum_b g;  accumulate != 0 adds into dW / dbias (slices of the flat gradient bucket).
+ * pooled [B,C], W [K,C], bias [K], logits / prob [B,K] fp32; labels int64 (NULL: logits only); K <= TSC_MAX_CLASSES.
+ * workspace: tsc_head_ce_workspace_bytes(B) bytes, ZERO before its first use (every launch leaves it zeroed). */
+size_t tsc_head_ce_workspace_bytes(int B);
+int tsc_head_ce_fwd(const float* pooled, const float* W, const float* bias, const long long* labels, float* logits,
+                    float* prob, float* loss, void* workspace, int B, int C, int K, tsc_stream_t stream);
+int tsc_head_ce_bwd(const float* dloss, const float* dlogits, const float* prob, const long long* labels,
+                    const float* pooled, const float* W, float* dpooled, float* dW, float* dbias, int accumulate,
+                    int B, int C, int K, tsc_stream_t stream);
+/* out = sum_i weights[i] * *terms[i] over n <= 8 device scalars (weights: HOST array): the step's total loss
+ * (train_and_test.py:660-672 style weighted sums) in one launch. */
+int tsc_weighted_scalar_sum(const float* const* terms, const float* weights, int n, float* out, tsc_stream_t stream);
+
 /* ---- debugging aid: the tcgen05 kernels bound every mbarrier wait; a timed-out wait stores a
  * non-zero code here (device word, read back by the caller when it wants to). */
 int tsc_debug_read_and_clear_watchdog(int* host_code);

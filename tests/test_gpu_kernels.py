@@ -421,3 +421,52 @@ def test_bad_arguments_raise(T):
     geom = ops.dense_geometry(3, 4, 1)
     with pytest.raises(RuntimeError):
         ops.pack_weights(geom, torch.zeros(4, 3, 2, device="cuda"), L.DIR_FWD, L.TSC_F32, False)
+
+
+@pytest.mark.parametrize("B,C,K", [(128, 144, 6), (37, 50, 4), (5, 225, 33)])
+def test_head_linear_cross_entropy_against_torch(T, B, C, K):
+    """Fused classifier head (OS_CNN.py:108-109 + nn.CrossEntropyLoss, train_and_test.py:593-603): logits, loss and every
+    gradient against torch autograd in float64, with and without an extra gradient arriving at the logits, and adding into
+    existing gradient buffers."""
+    from feature_level_style_transfer_for_tsc_b200 import functional as TF
+    g = torch.Generator().manual_seed(3)
+    pooled = torch.randn(B, C, generator=g)
+    W = torch.randn(K, C, generator=g) * 0.2
+    bias = torch.randn(K, generator=g)
+    y = torch.randint(0, K, (B,), generator=g)
+    extra = torch.randn(B, K, generator=g)
+    pd, Wd, bd = (t.double().requires_grad_(True) for t in (pooled, W, bias))
+    lg_ref = torch.nn.functional.linear(pd, Wd, bd)
+    loss_ref = torch.nn.functional.cross_entropy(lg_ref, y)
+    (2.5 * loss_ref + (lg_ref * extra.double()).sum()).backward()
+    pc, Wc, bc = (t.cuda().requires_grad_(True) for t in (pooled, W, bias))
+    lg, loss = TF.head_cross_entropy(pc, Wc, bc, y.cuda())
+    (2.5 * loss + (lg * extra.cuda()).sum()).backward()
+    torch.cuda.synchronize()
+    assert rel_err(lg.detach().cpu(), lg_ref.detach()) < 1e-5
+    assert abs(float(loss) - float(loss_ref)) < 1e-5 * abs(float(loss_ref))
+    for got, ref in ((pc.grad, pd.grad), (Wc.grad, Wd.grad), (bc.grad, bd.grad)):
+        assert rel_err(got.cpu(), ref) < 2e-5
+    # logits only (no labels): the eval-mode call of the trainer (train_and_test.py:584-586); gradient through the logits
+    pc2 = pooled.cuda().requires_grad_(True)
+    lg2, none = TF.head_cross_entropy(pc2, Wc.detach(), bc.detach(), None)
+    assert none is None and torch.equal(lg2.detach(), lg.detach())
+    (lg2 * extra.cuda()).sum().backward()
+    assert rel_err(pc2.grad.cpu(), (extra.double() @ W.double())) < 2e-5
+    # direct accumulation into existing .grad buffers (flat data-parallel bucket)
+    TF.set_direct_grads(True)
+    try:
+        W3, b3 = W.cuda().requires_grad_(True), bias.cuda().requires_grad_(True)
+        W3.grad, b3.grad = torch.ones_like(W3), torch.ones_like(b3)
+        _, loss3 = TF.head_cross_entropy(pooled.cuda(), W3, b3, y.cuda())
+        loss3.backward()
+    finally:
+        TF.set_direct_grads(False)
+    Wd.grad = None; bd.grad = None
+    torch.nn.functional.cross_entropy(torch.nn.functional.linear(pooled.double(), Wd, bd), y).backward()
+    assert rel_err((W3.grad - 1).cpu(), Wd.grad) < 2e-5 and rel_err((b3.grad - 1).cpu(), bd.grad) < 2e-5
+    # the total-loss kernel
+    a, b = torch.tensor(1.5, device="cuda", requires_grad=True), torch.tensor(-2.0, device="cuda", requires_grad=True)
+    tot = TF.weighted_loss_sum([a, b, loss.detach()], [1.0, 3.0, 0.5])
+    tot.backward()
+    assert abs(float(tot) - (1.5 - 6.0 + 0.5 * float(loss))) < 1e-5 and float(a.grad) == 1.0 and float(b.grad) == 3.0
