@@ -209,37 +209,49 @@ __device__ __forceinline__ float colsum32(float* v, int lane) {
     return v[0];
 }
 
-// The K steps of one run, issued by the elected lane: descriptors advance by (a_step, b_step) 16 B units per step.  Unrolled by
-// hand in blocks of four (a `#pragma unroll` on the loop sends ptxas back to vector registers + R2UR).
-template <bool PAIR>
-__device__ __forceinline__ void mma_issue(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-    if (PAIR) umma2_bf16(d, a, b, idesc, acc);
-    else umma_bf16(d, a, b, idesc, acc != 0);
-}
+// The K steps of one run, issued by the elected lane as ONE inline-PTX loop: per MMA two 32-bit adds on the low descriptor
+// words (the high words -- SBO, descriptor version -- never change), the loop counter and the branch.  Written in PTX because
+// the issuing warp is bound by its instruction count: from C++ ptxas built the 64-bit descriptors with carry chains and
+// register-pair moves (13 SASS instructions per MMA in the tail loop, 26 per MMA over the whole loop -- ncu source page,
+// profiles/r2_conv2_B1024.md); this form needs 6.
 template <bool PAIR>
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     if (PAIR) tc_commit2(bar);
     else tc_commit(bar);
 }
 template <bool PAIR>
-__device__ __forceinline__ void issue_run(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc, int ks,
-                                          uint32_t a_step, uint32_t b_step) {
-#pragma unroll 1
-    while (ks >= 4) {
-        mma_issue<PAIR>(d, a, b, idesc, acc);
-        mma_issue<PAIR>(d, a + a_step, b + b_step, idesc, acc);
-        mma_issue<PAIR>(d, a + 2 * a_step, b + 2 * b_step, idesc, acc);
-        mma_issue<PAIR>(d, a + 3 * a_step, b + 3 * b_step, idesc, acc);
-        a += 4 * a_step;
-        b += 4 * b_step;
-        ks -= 4;
-    }
-#pragma unroll 1
-    while (ks > 0) {
-        mma_issue<PAIR>(d, a, b, idesc, acc);
-        a += a_step;
-        b += b_step;
-        --ks;
+__device__ __forceinline__ void issue_run(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t acc,
+                                          uint32_t ks, uint32_t a_step, uint32_t b_step) {
+    if (PAIR) {
+        asm volatile(
+            "{\n\t.reg .pred pa, pk;\n\t.reg .b32 k;\n\t.reg .b64 da, db, a0, b0;\n\t"
+            "mov.b64 a0, {%1, %3};\n\tmov.b64 b0, {%2, %3};\n\t"
+            "mov.u32 k, 0;\n\t"
+            "setp.ne.b32 pa, %5, 0;\n"
+            "RUN_LOOP:\n\t"
+            "mad.wide.u32 da, k, %7, a0;\n\t"
+            "mad.wide.u32 db, k, %8, b0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, pa;\n\t"
+            "add.u32 k, k, 1;\n\t"
+            "setp.ne.u32 pk, k, %6;\n\t"
+            "@pk bra.uni RUN_LOOP;\n\t}"
+            ::"r"(d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(acc), "r"(ks), "r"(a_step), "r"(b_step)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred pa, pk;\n\t.reg .b32 k;\n\t.reg .b64 da, db, a0, b0;\n\t"
+            "mov.b64 a0, {%1, %3};\n\tmov.b64 b0, {%2, %3};\n\t"
+            "mov.u32 k, 0;\n\t"
+            "setp.ne.b32 pa, %5, 0;\n"
+            "RUN_LOOP:\n\t"
+            "mad.wide.u32 da, k, %7, a0;\n\t"
+            "mad.wide.u32 db, k, %8, b0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pa;\n\t"
+            "add.u32 k, k, 1;\n\t"
+            "setp.ne.u32 pk, k, %6;\n\t"
+            "@pk bra.uni RUN_LOOP;\n\t}"
+            ::"r"(d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(acc), "r"(ks), "r"(a_step), "r"(b_step)
+            : "memory");
     }
 }
 
@@ -358,8 +370,9 @@ osconv2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                     const uint2 e = S.stages[i];
                     if (x_next < n_my && x_next <= j + nx - 1 && x_free(x_next, false)) { load_x(x_next); ++x_next; }
                     TLS2(j * n_stages + i, 4);
-                    mbar_wait(&empty[s], ph ^ 1u, dead, 1);
+                    if (p.debug & 512) mbar_wait_sleep(&empty[s], ph ^ 1u, dead, 1, 200); else mbar_wait(&empty[s], ph ^ 1u, dead, 1);
                     TLS2(j * n_stages + i, 5);
+                    if (p.debug & 1024) continue;          // experiment: no weight pipeline at all (the issuer neither waits nor commits)
                     if (p.debug & 1) { mbar_arrive(&full[s]); if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; } continue; }
                     mbar_arrive_expect_tx(&full[s], e.y);
                     bulk_load(stages + (size_t)s * slot_bytes, w_src + (size_t)e.x * 16, e.y, &full[s]);
@@ -396,28 +409,19 @@ osconv2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                 if (j == 0) TL2(2);                   // (all lanes store: a lane-dependent branch here would cost the loop its uniformity)
                 const uint32_t a_base = (xs16 + xb * x16) | a_lbo;
                 const uint32_t d_base = tmem_base + ab * (uint32_t)p.acc_stride;
-                // Software-pipelined over the runs: the tensor pipe queues hardly more than one instruction ahead (measured:
-                // every issue-side gap longer than one MMA shows up as idle tensor time), so a run's first MMA is issued
-                // alone, the NEXT run's table entry is fetched and its operands computed in that MMA's shadow, and only then
-                // the rest of the run follows.
-                uint4 e = S.runs[0], f = S.runs[1];
-                uint32_t a_lo = a_base + e.x, d = d_base + e.w;
+                // One table entry per run, no software pipelining: the loop is ~25 uniform instructions per run plus 6 per MMA
 #pragma unroll 1
                 for (int r = 0; r < n_runs; ++r) {
-                    if (f.w & RF_FIRST) {
+                    const uint4 e = S.runs[2 * r], f = S.runs[2 * r + 1];
+                    if ((f.w & RF_FIRST) && !(p.debug & 1024)) {
                         TLS2(stage_i, 0);
                         ok = mbar_wait_warp(&full[s], ph) && ok;
                         TLS2(stage_i, 1);
                     }
-                    const uint64_t a0 = ((uint64_t)desc_hi << 32) | a_lo;
-                    const uint64_t b0 = ((uint64_t)desc_hi << 32) | (slot_cur + e.y);
-                    if (elect_one()) mma_issue<PAIR>(d, a0, b0, e.z, f.z);
-                    // (the table ends with a dummy entry: the prefetch of the last iteration stays in bounds)
-                    const uint4 en = S.runs[2 * r + 2], fn = S.runs[2 * r + 3];
-                    const uint32_t a_next = a_base + en.x, d_next = d_base + en.w;
+                    const uint32_t a_lo = a_base + e.x, b_lo = slot_cur + e.y, d = d_base + e.w;
                     if (elect_one()) {
-                        issue_run<PAIR>(d, a0 + a_step, b0 + f.y, e.z, 1u, (int)f.x - 1, a_step, f.y);
-                        if (f.w & RF_LAST) mma_commit<PAIR>(&empty[s]);   // frees the stage (in both CTAs) when these MMAs have read it
+                        issue_run<PAIR>(d, a_lo, b_lo, desc_hi, e.z, f.z, f.x, a_step, f.y);
+                        if ((f.w & RF_LAST) && !(p.debug & 1024)) mma_commit<PAIR>(&empty[s]);   // frees the stage (in both CTAs) when these MMAs have read it
                     }
                     if (f.w & RF_LAST) {
                         TLS2(stage_i, 3);
@@ -425,7 +429,6 @@ osconv2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                         slot_cur += slot16;
                         if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; slot_cur = st16; }
                     }
-                    e = en; f = fn; a_lo = a_next; d = d_next;
                 }
                 if (elect_one()) {
                     mma_commit<PAIR>(&acc_full[ab]);
@@ -474,7 +477,7 @@ osconv2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
             const uint32_t t_acc = tmem_base + (uint32_t)(ab * p.acc_stride) + ((uint32_t)(q * 32) << 16);
             // one thread polls the accumulator barrier; the other 127 sleep in a named barrier instead of spinning on
             // mbarrier.try_wait next to the MMA issuer
-            if (threadIdx.x == 64) mbar_wait(&acc_full[ab], (uint32_t)(ause & 1), dead, 4);
+            if (threadIdx.x == 64) { if (p.debug & 256) mbar_wait_sleep(&acc_full[ab], (uint32_t)(ause & 1), dead, 4, 500); else mbar_wait(&acc_full[ab], (uint32_t)(ause & 1), dead, 4); }
             asm volatile("bar.sync 2, 128;" ::: "memory");
             tc_fence_after();
             if (j == 0 && warp == 2 && lane == 0) TL2(5);
@@ -736,6 +739,22 @@ static int build_sched(bool pair, int direction, int Cin, int Cout, int Kmax, co
             f.y = 2 * rows;                                  // two chunks of `rows` rows per K step
             f.z = init_done ? 1u : 0u;
             f.w = used == 0 ? RF_FIRST : 0u;
+            // timing experiments only (TSC_C2_DEBUG bits, garbage results): which property of the MMA stream costs issue time?
+            //   16: every MMA reads the same A rows (no tap shift, no K walk over the tile's chunks beyond the kernel's own step)
+            //   32: every MMA reads the same B rows (start of the weight slot)      64: every MMA has N = np at column 0
+            //  128: every MMA has N = 112 at column 0
+            {
+                const int dbg = knob2_debug();
+                if (dbg & 16) e.x = 0;
+                if (dbg & (64 | 128)) {
+                    const uint32_t nn = (dbg & 64) ? (uint32_t)tt.np : 112u, rr = pair ? nn / 2 : nn;
+                    e.y = (e.y & 0xffffu) | (rr << 16);
+                    e.z = (1u << 4) | (1u << 7) | (1u << 10) | ((nn >> 3) << 17) | (((pair ? 256u : 128u) >> 4) << 24);
+                    e.w = 0;
+                    f.y = 2 * rr;
+                }
+                if (dbg & 32) { e.y &= 0xffff0000u; f.y = 0; }
+            }
             sc->runs[2 * n_runs] = e;
             sc->runs[2 * n_runs + 1] = f;
             ++n_runs;

@@ -48,6 +48,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, bool& 
     dead = true;
     atomicCAS(&g_watchdog, 0, (code << 16) | (int)(blockIdx.x & 0xffff));
 }
+// As mbar_wait, for a thread that waits LONG next to the MMA issuer (accumulator poller, weight producer): between two polls it
+// sleeps `ns` nanoseconds instead of re-issuing the try_wait at once.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, bool& dead, int code, uint32_t ns) {
+    if (dead) return;
+    for (uint32_t i = 0; i < (1u << 20); ++i) {
+        if (mbar_try_wait(bar, parity)) return;
+        __nanosleep(ns);
+    }
+    dead = true;
+    atomicCAS(&g_watchdog, 0, (code << 16) | (int)(blockIdx.x & 0xffff));
+}
 
 // ---- TMA ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
