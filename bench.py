@@ -335,18 +335,19 @@ class KernelProfile:
 
 
 def conv_traffic_from_profile(launches_per_step):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the step's osconv_tc_kernel launches from the committed ncu capture
-    (profiles/r1s4_step_dram_traffic.json, tools/ncu_traffic.py; cfg2 step only).  Bytes per step, like `achieved`."""
-    path = os.path.join(ROOT, "profiles", "r1s4_step_dram_traffic.json")
+    """dram__bytes_read.sum + dram__bytes_write.sum of the step's conv launches (osconv2_kernel) from the committed ncu capture of
+    the eager cfg2 step (profiles/r2_step_dram_traffic.json, made by tools/ncu_traffic.py from profiles/r2_traffic_step.csv).
+    Bytes per step, like `achieved`."""
+    path = os.path.join(ROOT, "profiles", "r2_step_dram_traffic.json")
     if not os.path.exists(path):
         return None, "no ncu capture committed"
     with open(path) as f:
         kernels = json.load(f)["kernels"]
     for name, d in kernels.items():
-        if "osconv_tc_kernel<0>" in name and abs(d["launches_per_step"] - launches_per_step) < 0.5:
+        if "osconv2_kernel<0, 0, 0>" in name and abs(d["launches_per_step"] - launches_per_step) < 0.5:
             return (d["dram_read_bytes_per_step"] + d["dram_write_bytes_per_step"],
                     "bytes per step over the %d conv launches, ncu cold-cache capture of the eager cfg2 step "
-                    "(profiles/r1s4_step_dram_traffic.json): reads only -- at this size every write stays in the 126 MB L2"
+                    "(profiles/r2_step_dram_traffic.json): reads only -- at this size every write stays in the 126 MB L2"
                     % launches_per_step)
     return None, "the committed ncu capture is of the cfg2 step (24 conv launches); this workload differs"
 
@@ -409,7 +410,7 @@ def conv_roofline(torch, ops, L, conv_calls, peaks, reps=20):
                            us=round(t * 1e6, 2), tflops=round(f / t / 1e12, 1)))
     achieved = tot_f / tot_t / 1e12 if tot_t else 0.0
     traffic, traffic_note = conv_traffic_from_profile(sum(c for _, c in groups.values()))
-    return dict(kernel="osconv_tc_kernel (forward + dgrad launches of one step)", bound="tensor", achieved=achieved,
+    return dict(kernel="osconv2_kernel (forward + dgrad launches of one step)", bound="tensor", achieved=achieved,
                 peak=peaks["bf16"], unit="TFLOP/s", frac=achieved / peaks["bf16"], traffic=traffic, traffic_note=traffic_note,
                 peak_source=peaks["source"] + " bf16 burst (kernel timed alone)",
                 algorithmic_flops_per_step=tot_f, device_ms_per_step=tot_t * 1e3, launches=detail)
