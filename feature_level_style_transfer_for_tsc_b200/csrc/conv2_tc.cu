@@ -63,7 +63,7 @@ struct ConvSched {
     int n_runs, n_stages, stage_bytes;
     int half_rows16;                  // 16 B rows of one stream of the split packed bank
     uint4 runs[2 * C2_MAX_RUNS];
-    uint2 stages[C2_MAX_STAGES];      // {source offset in 16 B units, bytes}
+    uint4 stages[C2_MAX_STAGES];      // {source offset in 16 B units, bytes, first run, runs} -- a stage holds whole runs
 };
 
 struct Conv2Params {
@@ -367,13 +367,13 @@ osconv2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
             const uint8_t* w_src = reinterpret_cast<const uint8_t*>(p.w) + (size_t)rank * (size_t)p.half_rows16 * 16;
             for (int j = 0; j < n_my; ++j) {
                 for (int i = 0; i < n_stages; ++i) {
-                    const uint2 e = S.stages[i];
+                    const uint4 e = S.stages[i];
                     if (x_next < n_my && x_next <= j + nx - 1 && x_free(x_next, false)) { load_x(x_next); ++x_next; }
                     TLS2(j * n_stages + i, 4);
-                    if (p.debug & 512) mbar_wait_sleep(&empty[s], ph ^ 1u, dead, 1, 200); else mbar_wait(&empty[s], ph ^ 1u, dead, 1);
+                    if (DBG && (p.debug & 512)) mbar_wait_sleep(&empty[s], ph ^ 1u, dead, 1, 200); else mbar_wait(&empty[s], ph ^ 1u, dead, 1);
                     TLS2(j * n_stages + i, 5);
-                    if (p.debug & 1024) continue;          // experiment: no weight pipeline at all (the issuer neither waits nor commits)
-                    if (p.debug & 1) { mbar_arrive(&full[s]); if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; } continue; }
+                    if (DBG && (p.debug & 1024)) continue;  // experiment: no weight pipeline at all (the issuer neither waits nor commits)
+                    if (DBG && (p.debug & 1)) { mbar_arrive(&full[s]); if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; } continue; }
                     mbar_arrive_expect_tx(&full[s], e.y);
                     bulk_load(stages + (size_t)s * slot_bytes, w_src + (size_t)e.x * 16, e.y, &full[s]);
                     if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; }
@@ -388,7 +388,6 @@ osconv2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
         const int n_runs = S.n_runs, n_stages = S.n_stages;
         const int nx = p.nx, na = p.na;
         uint32_t s = 0, ph = 0;
-        int stage_i = 0;
         if (!PAIR || rank == 0) {
             // ===== MMA issuer (leader CTA): the whole warp walks the run table in lock-step, in uniform registers; one elected
             // lane issues for the pair =====
@@ -409,23 +408,39 @@ osconv2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                 if (j == 0) TL2(2);                   // (all lanes store: a lane-dependent branch here would cost the loop its uniformity)
                 const uint32_t a_base = (xs16 + xb * x16) | a_lbo;
                 const uint32_t d_base = tmem_base + ab * (uint32_t)p.acc_stride;
-                // One table entry per run, no software pipelining: the loop is ~25 uniform instructions per run plus 6 per MMA
+                if (DBG && (p.debug & 2048)) {
+                    // experiment: the micro-benchmark's loop inside this kernel -- 3 * n_runs + 6 identical MMAs (N = 112), no
+                    // table, no barriers; what does the issue slot cost here?  (profiles/r2_conv2_issue_bisection.md)
+                    const uint32_t idesc_x = (1u << 4) | (1u << 7) | (1u << 10) | ((112u >> 3) << 17) | (((PAIR ? 256u : 128u) >> 4) << 24);
+                    const uint32_t b_x = st16 | ((PAIR ? 56u : 112u) << 16);
 #pragma unroll 1
-                for (int r = 0; r < n_runs; ++r) {
-                    const uint4 e = S.runs[2 * r], f = S.runs[2 * r + 1];
-                    if ((f.w & RF_FIRST) && !(p.debug & 1024)) {
-                        TLS2(stage_i, 0);
-                        ok = mbar_wait_warp(&full[s], ph) && ok;
-                        TLS2(stage_i, 1);
+                    for (int i = 0; i < 3 * n_runs + 6; i += 4) {
+                        if (elect_one()) issue_run<PAIR>(d_base, a_base, b_x, desc_hi, idesc_x, 1u, 4u, 0u, 0u);
                     }
-                    const uint32_t a_lo = a_base + e.x, b_lo = slot_cur + e.y, d = d_base + e.w;
-                    if (elect_one()) {
-                        issue_run<PAIR>(d, a_lo, b_lo, desc_hi, e.z, f.z, f.x, a_step, f.y);
-                        if ((f.w & RF_LAST) && !(p.debug & 1024)) mma_commit<PAIR>(&empty[s]);   // frees the stage (in both CTAs) when these MMAs have read it
-                    }
-                    if (f.w & RF_LAST) {
-                        TLS2(stage_i, 3);
-                        if (DBG) ++stage_i;
+                } else {
+                    // Stage by stage: one vote-wait, ONE elected region that walks the stage's runs (a run = the K steps of one
+                    // tap inside this stage: a table entry, three adds and the inline-PTX K loop), one commit.  The tensor pipe
+                    // accepts an MMA only when its predecessor has fetched its operands (~68 cycles at this bank's mean N): what
+                    // the issuer does between two MMAs is free up to that length and serial beyond it -- the per-run header
+                    // is what has to stay short (measured: profiles/r2_conv2_issue_bisection.md).
+                    const bool no_pipe = DBG && (p.debug & 1024);
+#pragma unroll 1
+                    for (int i = 0; i < n_stages; ++i) {
+                        if (!no_pipe) {
+                            TLS2(j * n_stages + i, 0);
+                            ok = mbar_wait_warp(&full[s], ph) && ok;
+                            TLS2(j * n_stages + i, 1);
+                        }
+                        if (elect_one()) {
+                            const uint32_t r0 = S.stages[i].z, r1 = r0 + S.stages[i].w;     // (read here: a value that lives across the
+#pragma unroll 1                                                                            //  vote loop above lands in a vector register)
+                            for (uint32_t r = r0; r < r1; ++r) {
+                                const uint4 e = S.runs[2 * r], f = S.runs[2 * r + 1];
+                                issue_run<PAIR>(d_base + e.w, a_base + e.x, slot_cur + e.y, desc_hi, e.z, f.z, f.x, a_step, f.y);
+                            }
+                            if (!no_pipe) mma_commit<PAIR>(&empty[s]);   // frees the stage (in both CTAs) when these MMAs have read it
+                        }
+                        TLS2(j * n_stages + i, 3);
                         slot_cur += slot16;
                         if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; slot_cur = st16; }
                     }
@@ -477,7 +492,7 @@ osconv2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
             const uint32_t t_acc = tmem_base + (uint32_t)(ab * p.acc_stride) + ((uint32_t)(q * 32) << 16);
             // one thread polls the accumulator barrier; the other 127 sleep in a named barrier instead of spinning on
             // mbarrier.try_wait next to the MMA issuer
-            if (threadIdx.x == 64) { if (p.debug & 256) mbar_wait_sleep(&acc_full[ab], (uint32_t)(ause & 1), dead, 4, 500); else mbar_wait(&acc_full[ab], (uint32_t)(ause & 1), dead, 4); }
+            if (threadIdx.x == 64) { if (DBG && (p.debug & 256)) mbar_wait_sleep(&acc_full[ab], (uint32_t)(ause & 1), dead, 4, 500); else mbar_wait(&acc_full[ab], (uint32_t)(ause & 1), dead, 4); }
             asm volatile("bar.sync 2, 128;" ::: "memory");
             tc_fence_after();
             if (j == 0 && warp == 2 && lane == 0) TL2(5);
@@ -706,11 +721,13 @@ static int build_sched(bool pair, int direction, int Cin, int Cout, int Kmax, co
     uint32_t used = 0;            // bytes of the open stage
     uint32_t stage_src = 0;       // its source offset (16 B units)
     bool init_done = false;
+    int stage_first_run = 0;
     auto close_stage = [&]() -> int {
         TSC_REQUIRE(n_stages < C2_MAX_STAGES, "kernel bank needs more than %d weight stages of %d B: unsupported", C2_MAX_STAGES,
                     sc->stage_bytes);
-        sc->stages[n_stages++] = make_uint2(stage_src, used);
+        sc->stages[n_stages++] = make_uint4(stage_src, used, (uint32_t)stage_first_run, (uint32_t)(n_runs - stage_first_run));
         sc->runs[2 * (n_runs - 1) + 1].w |= RF_LAST;
+        stage_first_run = n_runs;
         used = 0;
         return 0;
     };
@@ -940,7 +957,7 @@ int osconv2_tc(int direction, const void* x, int dtype, const void* w, const flo
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    const bool dbg = p.tl != nullptr;       // the instrumented instantiation only when a timeline buffer is set
+    const bool dbg = p.tl != nullptr || p.debug != 0;   // the instrumented instantiation only when a timeline buffer or an experiment knob is set
     cudaError_t le;
 #define TSC_C2_LAUNCH(A, D, P) le = cudaLaunchKernelEx(&cfg, osconv2_kernel<A, D, P>, xmap, *sc, p)
     if (pair) {
