@@ -555,9 +555,20 @@ def run_ours(args):
     table = prof.table(psteps)
     prof.uninstall()
 
-    if rank != 0:
+    def shutdown():
+        """Leave the process group without ever hanging the launcher: the step graph (NCCL inside) is released first, and a
+        watchdog ends the process if the teardown still blocks."""
         if world > 1:
+            sys.stdout.flush()
+            t = threading.Timer(30.0, lambda: os._exit(0))
+            t.daemon = True
+            t.start()
+            trainer.release_graph()
             dist.destroy_process_group()
+            t.cancel()
+
+    if rank != 0:
+        shutdown()
         return
     peaks = load_peaks()
     kern = {k: dict(ms_per_step=round(v["ms_per_step"], 4), launches=v["launches_per_step"],
@@ -608,8 +619,7 @@ def run_ours(args):
     if world == 1 and not args.no_extra and not cfg4 and not cfg3:
         line["gpu_eager_baseline"] = gpu_eager_baseline(torch)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown()
 
 
 def main():

@@ -17,6 +17,7 @@ linear in the gradient, so the scale is NOT folded into the learning rate).
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -59,6 +60,20 @@ class StyleTransferModelSet(nn.Module):
         self.feature_channels = cf_t
 
     two_streams = True      # run the target and the source branch on two CUDA streams (they are independent up to AdaIN)
+    grads_final_callback = None   # set by the data-parallel trainer: called with a module name ("cl_t", "cl_s") during backward
+                                  # as soon as that module's parameter gradients are complete (its slice of the flat
+                                  # bucket can be all-reduced while the extractors' backward is still running)
+
+    def _announce_final(self, feature: torch.Tensor, name: str) -> None:
+        """The gradient of an extractor output is complete only after every consumer has run its backward -- among them
+        the classifier `name` (and, in the C-DAN pair, its second call on the generated features, whose gradient reaches
+        the target feature through AdaIN's style input)."""
+        cb = self.grads_final_callback
+        if cb is not None and feature.requires_grad:
+            def hook(grad, _name=name, _cb=cb):
+                _cb(_name)
+                return None
+            feature.register_hook(hook)
 
     def forward(self, xt, yt, xs, ys, style_weight: float = 1.0) -> Dict[str, torch.Tensor]:
         if not (self.two_streams and xt.is_cuda):
@@ -92,6 +107,8 @@ class StyleTransferModelSet(nn.Module):
             main.wait_stream(side)
             logits_s.record_stream(main)
             ce_s.record_stream(main)
+        self._announce_final(tf, "cl_t")
+        self._announce_final(ssf, "cl_s")
         loss = TF.weighted_loss_sum([ce_t, ce_s, l_style], [1.0, 1.0, float(style_weight)]) if xt.is_cuda \
             else ce_t + ce_s + style_weight * l_style
         return dict(loss=loss, ce_t=ce_t, ce_s=ce_s, l_style=l_style,
@@ -283,6 +300,22 @@ class Trainer:
             clamps = getattr(model, "CLAMPS", {})
             groups = [(list(getattr(model, name).parameters()), lr, clamps.get(name, 0.0)) for name, lr in lrs.items()]
         self.flat = FlatParameters(groups)
+        # slice of the flat bucket of every named group (for the early, overlapped part of the gradient exchange)
+        self._group_range = {}
+        if not (lrs is None and hasattr(model, "parameter_groups")):
+            lo = 0
+            for name, hi in zip(lrs.keys(), self.flat.group_end):
+                self._group_range[name] = (lo, hi)
+                lo = hi
+        # TSC_DP_OVERLAP=1: all-reduce a classifier's slice as soon as its gradients are final, during backward.  Off by default:
+        # measured on 2 x B200 (profiles/r2_dp_exchange.md) the early all-reduces cost more than they hide -- the compute
+        # kernels are single waves sized to the SM count, and NCCL's resident CTAs turn them into two waves (1.256 ms per step
+        # against 1.223 with one all-reduce after backward; capping NCCL_MAX_CTAS makes both slower)
+        self.overlap_exchange = os.environ.get("TSC_DP_OVERLAP", "0") == "1"
+        self._comm_stream = None
+        self._early_works, self._early_done = [], []
+        if hasattr(model, "grads_final_callback"):
+            model.grads_final_callback = self._on_grads_final
         self.use_graph = use_graph
         self._graph = None
         self._static_in = None
@@ -301,7 +334,72 @@ class Trainer:
                     for t in m.random_matrix:
                         dist.broadcast(t, src=src, group=self.group)
 
+    def _world(self) -> int:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(self.group)
+        return 1
+
+    def _model_streams(self):
+        out = []
+        for m in self.model.modules():
+            st = getattr(m, "_side_stream", None)
+            if st is not None:
+                out.append(st)
+            out.extend(getattr(m, "_streams", None) or [])
+        return out
+
+    def _on_grads_final(self, name: str) -> None:
+        """Autograd hook (see StyleTransferModelSet._announce_final): the gradients of group `name` are complete -- start
+        the all-reduce of its slice on the communication stream while the rest of backward keeps the compute streams busy."""
+        if not self.overlap_exchange or name not in self._group_range or name in self._early_done or self._world() <= 1:
+            return
+        import torch.distributed as dist
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream()
+        comm = self._comm_stream
+        comm.wait_stream(torch.cuda.current_stream())
+        for st in self._model_streams():          # the group's wgrad / BatchNorm-backward kernels ran on its branch's stream
+            comm.wait_stream(st)
+        lo, hi = self._group_range[name]
+        with torch.cuda.stream(comm):
+            self._early_works.append(dist.all_reduce(self.flat.flat_g[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        self._early_done.append(name)
+
+    def _exchange(self) -> int:
+        """Sum the flat gradient bucket over the ranks: whatever the backward hooks have not already put on the wire, in as
+        few contiguous all-reduces as possible.  Returns the world size (the 1/N is applied inside the optimizer kernel)."""
+        world = self._world()
+        if world <= 1:
+            return 1
+        import torch.distributed as dist
+        if not self._early_done:
+            dist.all_reduce(self.flat.flat_g, op=dist.ReduceOp.SUM, group=self.group)
+            return world
+        done = sorted(self._group_range[n] for n in self._early_done)
+        pos, rest = 0, []
+        for lo, hi in done + [(self.flat.flat_g.numel(), self.flat.flat_g.numel())]:
+            if lo > pos:
+                rest.append((pos, lo))
+            pos = max(pos, hi)
+        for lo, hi in rest:
+            dist.all_reduce(self.flat.flat_g[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+        for w in self._early_works:
+            w.wait()                               # the current stream waits for the early slices
+        torch.cuda.current_stream().wait_stream(self._comm_stream)
+        self._early_works, self._early_done = [], []
+        return world
+
+    def _step_body(self, *inputs):
+        """forward + backward + gradient exchange + optimizer: what one CUDA graph replays (NCCL collectives are capturable,
+        so a data-parallel step is still ONE graph launch, and the exchange overlaps the tail of backward inside it)."""
+        loss = self._fwd_bwd(*inputs)
+        world = self._exchange()
+        self.flat.rmsprop(grad_scale=1.0 / world)
+        return loss
+
     def _fwd_bwd(self, *inputs):
+        self._early_works, self._early_done = [], []
         self.flat.zero_grad()
         # every parameter owns a slice of the flat gradient bucket: the wgrad / BatchNorm-backward kernels add into it
         # in place (no AccumulateGrad kernels), so the bucket is complete the moment backward returns
@@ -323,12 +421,8 @@ class Trainer:
             # own streams and reported None to autograd -- order the all-reduce / optimizer behind them explicitly instead
             # of relying on autograd's end-of-backward leaf-stream synchronisation
             cur = torch.cuda.current_stream()
-            for m in self.model.modules():
-                st = getattr(m, "_side_stream", None)
-                if st is not None:
-                    cur.wait_stream(st)
-                for st in (getattr(m, "_streams", None) or []):
-                    cur.wait_stream(st)
+            for st in self._model_streams():
+                cur.wait_stream(st)
         finally:
             OSM.defer_batch_counters(False)
             TF.set_direct_grads(prev)
@@ -339,21 +433,36 @@ class Trainer:
         self._static_in = [t.clone() for t in inputs]
         # the warm-up passes must leave no trace: BatchNorm running statistics are forward side effects
         saved = [b.detach().clone() for b in self.model.buffers()]
+        saved_p, saved_v = self.flat.flat_p.clone(), self.flat.flat_v.clone()      # the warm-up steps update the parameters
         sched = self.model.schedule_state() if hasattr(self.model, "schedule_state") else None
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(3):                          # warm-up on a side stream, as graph capture requires
-                self._fwd_bwd(*self._static_in)
+            for _ in range(3):                          # warm-up on a side stream, as graph capture requires (NCCL included)
+                self._step_body(*self._static_in)
         torch.cuda.current_stream().wait_stream(side)
+        with torch.no_grad():
+            self.flat.flat_p.copy_(saved_p)
+            self.flat.flat_v.copy_(saved_v)
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
-            self._static_loss = self._fwd_bwd(*self._static_in)
+            self._static_loss = self._step_body(*self._static_in)
+        # capturing does not execute: parameters and optimizer state are untouched; BatchNorm statistics were moved by the
+        # warm-up steps only
         with torch.no_grad():
             for b, v in zip(self.model.buffers(), saved):
                 b.copy_(v)
         if sched is not None:
             self.model.set_schedule_state(sched)
+
+    def release_graph(self) -> None:
+        """Drop the captured step.  A CUDA graph that holds NCCL collectives must be destroyed BEFORE the process group is:
+        ``destroy_process_group`` waits for the communicator's captured work to be released and hangs otherwise."""
+        if self._graph is not None:
+            torch.cuda.synchronize()
+            self._graph = None
+            self._static_loss = None
+            torch.cuda.synchronize()
 
     def step(self, *inputs) -> torch.Tensor:
         if self.use_graph:
@@ -364,9 +473,5 @@ class Trainer:
             if hasattr(self.model, "advance_schedules"):
                 self.model.advance_schedules()          # host-side schedules (C-DAN reversal strength) -> device scalars
             self._graph.replay()
-            loss = self._static_loss
-        else:
-            loss = self._fwd_bwd(*inputs)
-        world = self.flat.all_reduce_sum(self.group)
-        self.flat.rmsprop(grad_scale=1.0 / world)
-        return loss
+            return self._static_loss
+        return self._step_body(*inputs)

@@ -3,7 +3,7 @@
   * the all-reduced flat gradient bucket / N equals the mean of the oracle's per-shard gradients (every rank runs the
     oracle on every shard -- SURVEY section 4, last table row; per-rank BatchNorm statistics = DDP semantics),
   * the parameters after the fused RMSprop update are bit-identical on all ranks,
-  * and the same holds when the step is replayed from a CUDA graph.
+  * and the same holds when the whole step (exchange and optimizer included) is replayed from ONE CUDA graph.
 
 Prints one JSON line per rank-0 check; exits non-zero on failure."""
 import json
@@ -67,16 +67,13 @@ def main():
             tr = Trainer(model, style_weight=style_w, use_graph=use_graph)
             tr.broadcast_parameters(0)
             ins = [shard(xt, rank).to(dev), shard(yt, rank).to(dev), shard(xs, rank).to(dev), shard(ys, rank).to(dev)]
-            if use_graph:
-                tr._capture(*ins)
-                for dst, src in zip(tr._static_in, ins):
-                    dst.copy_(src)
-                tr._graph.replay()
-            else:
-                tr._fwd_bwd(*ins)
-            n = tr.flat.all_reduce_sum(tr.group)
-            assert n == world
+            # one whole step -- forward, backward, the gradient exchange (classifier slices all-reduced during backward, the
+            # rest after it) and the fused RMSprop -- eagerly or as ONE replayed CUDA graph with the NCCL collectives inside;
+            # the bucket still holds the summed gradients afterwards (the optimizer only reads it)
+            print(f"[rank {rank}] {engine} graph={use_graph}: step", file=sys.stderr, flush=True)
+            tr.step(*ins)
             torch.cuda.synchronize()
+            print(f"[rank {rank}] {engine} graph={use_graph}: step done", file=sys.stderr, flush=True)
             worst = 0.0
             worst_key = None
             for gname in ("fe_t", "cl_t", "fe_s", "du", "cl_s"):
@@ -86,8 +83,7 @@ def main():
                     e = l2_rel((p.grad / world).detach().cpu(), ref[(gname, k)])
                     if e > worst:
                         worst, worst_key = e, f"{gname}.{k}"
-            tr.flat.rmsprop(grad_scale=1.0 / world)
-            torch.cuda.synchronize()
+            tr.release_graph()            # a graph with NCCL inside must not outlive its use (and never the process group)
             gathered = [torch.empty_like(tr.flat.flat_p) for _ in range(world)]
             dist.all_gather(gathered, tr.flat.flat_p)
             identical = all(torch.equal(gathered[0], g) for g in gathered[1:])
@@ -101,8 +97,15 @@ def main():
                                       params_bit_identical_across_ranks=identical, ok=good)), flush=True)
     flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)
+    code = 1 if int(flag) else 0
+    sys.stdout.flush()
+    import threading
+    t = threading.Timer(30.0, lambda: os._exit(code))      # never hang the launcher in the teardown
+    t.daemon = True
+    t.start()
     dist.destroy_process_group()
-    sys.exit(1 if int(flag) else 0)
+    t.cancel()
+    sys.exit(code)
 
 
 if __name__ == "__main__":

@@ -20,7 +20,7 @@ def test_two_rank_step_equals_the_mean_of_the_oracle_shards():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29517", os.path.join(ROOT, "tests", "dp_worker.py")]
     env = dict(os.environ, NCCL_DEBUG="WARN")
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
     lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
     out = os.path.join(ROOT, "gpurun_out", "r2_dp_equality.jsonl")
     os.makedirs(os.path.dirname(out), exist_ok=True)
