@@ -15,6 +15,7 @@ import os
 import torch
 import torch.nn as nn
 
+from .. import _lib
 from .. import ops
 from .. import functional as _F
 from ..functional import LayerSpec, StackSpec, direct_grads, os_stack
@@ -99,9 +100,14 @@ def _run_stack(layers, x, shortcut=None, final_relu=False, pooled=False):
     if shortcut is not None:
         sc_spec = _bn_layer_spec(shortcut.geometry, shortcut.bn, False, zero_masked=False)
         params += _bn_params(shortcut.conv1d, shortcut.bn)
-    spec = StackSpec(layers=specs, shortcut=sc_spec, final_relu=final_relu, engine=ops.get_engine("conv"),
-                     wgrad_engine=ops.get_engine("wgrad"), op_dtype=ops.op_dtype(), direct_grads=direct_grads(),
-                     pooled=(pooled and shortcut is None and ops.engine_name() == "tcgen05" and _F.FUSED_PATH
+    # a layer wider than one TMEM accumulator tile (> 256 padded channels: the reference's layer recipe gives 336 at L = 64,
+    # 560 at L = 32, train_and_test.py:38-53) takes its whole stack to the fp32 CUDA-core engine -- same C-ABI, same layouts
+    wide = any(sp.geom.wide for sp in specs) or (sc_spec is not None and sc_spec.geom.wide)
+    conv_eng = _lib.ENGINE_SIMT if wide else ops.get_engine("conv")
+    wgrad_eng = _lib.ENGINE_SIMT if wide else ops.get_engine("wgrad")
+    spec = StackSpec(layers=specs, shortcut=sc_spec, final_relu=final_relu, engine=conv_eng,
+                     wgrad_engine=wgrad_eng, op_dtype=(_lib.TSC_F32 if wide else ops.op_dtype()), direct_grads=direct_grads(),
+                     pooled=(pooled and shortcut is None and not wide and ops.engine_name() == "tcgen05" and _F.FUSED_PATH
                              and os.environ.get("TSC_NO_POOLED") != "1"))
     if x.dtype != torch.float32:
         raise RuntimeError(f"OS-CNN input must be float32 (the reference casts with .float()), got {x.dtype}")

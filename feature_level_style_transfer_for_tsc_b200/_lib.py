@@ -23,7 +23,7 @@ TSC_F32, TSC_BF16 = 0, 1
 ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1
 DIR_FWD, DIR_DGRAD = 0, 1
 OUT_C8_F32, OUT_C8_BF16, OUT_NCL_F32, OUT_POOLED = 0, 1, 2, 3
-MAX_TAPS, MAX_CHANNELS = 96, 256
+MAX_TAPS, MAX_CHANNELS, MAX_CHANNELS_WIDE = 96, 256, 2048
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]

@@ -37,8 +37,8 @@ bool pdl_enabled() {
 int build_tap_table(int direction, int Cin, int Cout, int Kmax, const int* s_of_tap, TapTable* tt) {
     TSC_REQUIRE(direction == TSC_DIR_FWD || direction == TSC_DIR_DGRAD, "bad direction %d", direction);
     TSC_REQUIRE(Kmax >= 1 && Kmax <= TSC_MAX_TAPS, "Kmax=%d outside [1,%d]", Kmax, TSC_MAX_TAPS);
-    TSC_REQUIRE(Cin >= 1 && Cin <= TSC_MAX_CHANNELS && Cout >= 1 && Cout <= TSC_MAX_CHANNELS,
-                "channel counts (%d,%d) outside [1,%d]", Cin, Cout, TSC_MAX_CHANNELS);
+    TSC_REQUIRE(Cin >= 1 && Cin <= TSC_MAX_CHANNELS_WIDE && Cout >= 1 && Cout <= TSC_MAX_CHANNELS_WIDE,
+                "channel counts (%d,%d) outside [1,%d]", Cin, Cout, TSC_MAX_CHANNELS_WIDE);
     TSC_REQUIRE(s_of_tap != nullptr, "s_of_tap is NULL");
     memset(tt, 0, sizeof(*tt));
     tt->taps = Kmax;

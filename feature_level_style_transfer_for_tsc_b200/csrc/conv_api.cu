@@ -54,6 +54,9 @@ int tsc_osconv(int engine, int direction, const void* x, int dtype, const void* 
     }
     if (engine == TSC_ENGINE_TCGEN05) {
         (void)plan;               // (round-1 interface: the schedule now travels in the kernel parameter block)
+        TSC_REQUIRE(Cin <= TSC_MAX_CHANNELS && Cout <= TSC_MAX_CHANNELS,
+                    "tcgen05 engine: channel counts (%d,%d) exceed one TMEM accumulator tile (%d); use TSC_ENGINE_SIMT", Cin, Cout,
+                    TSC_MAX_CHANNELS);
         return osconv2_tc(direction, x, dtype, w, bias, y, epilogue, B, L, Cin, Cout, Kmax, s_of_tap, (cudaStream_t)stream);
     }
     TSC_REQUIRE(false, "bad engine %d", engine);
@@ -72,7 +75,8 @@ int tsc_oswgrad(int engine, const void* dy, const void* x, int dtype, float* dW,
     TSC_REQUIRE(B > 0 && L > 0, "bad shape B=%d L=%d", B, L);
     TSC_REQUIRE(dtype == TSC_F32 || dtype == TSC_BF16, "bad dtype %d", dtype);
     TSC_REQUIRE(Kmax >= 1 && Kmax <= TSC_MAX_TAPS && s_of_tap, "bad kernel bank");
-    TSC_REQUIRE(Cin >= 1 && Cin <= TSC_MAX_CHANNELS && Cout >= 1 && Cout <= TSC_MAX_CHANNELS, "bad channel counts");
+    const int cmax = engine == TSC_ENGINE_SIMT ? TSC_MAX_CHANNELS_WIDE : TSC_MAX_CHANNELS;
+    TSC_REQUIRE(Cin >= 1 && Cin <= cmax && Cout >= 1 && Cout <= cmax, "channel counts (%d,%d) outside [1,%d] of this engine", Cin, Cout, cmax);
     if (engine == TSC_ENGINE_SIMT)
         return oswgrad_simt(dy, x, dtype, dW, workspace, accumulate, B, L, Cin, Cout, Kmax, s_of_tap, (cudaStream_t)stream);
     if (engine == TSC_ENGINE_TCGEN05)

@@ -397,8 +397,8 @@ extern "C" int tsc_pack_weights_multi(int dtype, const tsc_pack_batch* batch, ts
     for (int i = 0; i < batch->n; ++i) {
         const tsc_pack_layer& ly = batch->layer[i];
         TSC_REQUIRE(ly.W && ly.packed_fwd, "layer %d: NULL tensor", i);
-        TSC_REQUIRE(ly.Kmax >= 1 && ly.Kmax <= TSC_MAX_TAPS && ly.Cin >= 1 && ly.Cin <= TSC_MAX_CHANNELS && ly.Cout >= 1 &&
-                        ly.Cout <= TSC_MAX_CHANNELS, "layer %d: bad geometry", i);
+        TSC_REQUIRE(ly.Kmax >= 1 && ly.Kmax <= TSC_MAX_TAPS && ly.Cin >= 1 && ly.Cin <= TSC_MAX_CHANNELS_WIDE && ly.Cout >= 1 &&
+                        ly.Cout <= TSC_MAX_CHANNELS_WIDE, "layer %d: bad geometry", i);
         max_blocks = max(max_blocks, (pad16(ly.Cout) / 8) * (pad16(ly.Cin) / 16));
         max_k = max(max_k, ly.Kmax);
     }

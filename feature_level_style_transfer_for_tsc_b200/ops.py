@@ -94,9 +94,12 @@ class BankGeometry:
     def __post_init__(self):
         if not (1 <= self.kmax <= L.MAX_TAPS):
             raise ValueError(f"kernel size {self.kmax} outside [1, {L.MAX_TAPS}]")
-        if not (1 <= self.cin <= L.MAX_CHANNELS and 1 <= self.cout <= L.MAX_CHANNELS):
-            raise ValueError(f"channel counts ({self.cin}, {self.cout}) outside [1, {L.MAX_CHANNELS}]")
+        if not (1 <= self.cin <= L.MAX_CHANNELS_WIDE and 1 <= self.cout <= L.MAX_CHANNELS_WIDE):
+            raise ValueError(f"channel counts ({self.cin}, {self.cout}) outside [1, {L.MAX_CHANNELS_WIDE}]")
         self.cin_p, self.cout_p = pad16(self.cin), pad16(self.cout)
+        # wider than one TMEM accumulator tile (the reference's recipe for series shorter than ~80 samples): such a layer --
+        # and with it its whole stack -- runs on the fp32 CUDA-core engine
+        self.wide = self.cin_p > L.MAX_CHANNELS or self.cout_p > L.MAX_CHANNELS
         self.s_arr = L.int_array(self.s_of_tap)
         self.pad_l, self.pad_r = (self.kmax - 1) // 2, self.kmax // 2
         self._packed_bytes = {}

@@ -41,8 +41,12 @@ extern "C" {
 #define TSC_MAX_TAPS 96          /* largest supported Kmax (reference caps it at 89, train_and_test.py:40) */
 #define TSC_MAX_CHANNELS 256     /* largest padded channel count of one OS layer = one TMEM accumulator tile.  The reference's
                                   * layer recipe (train_and_test.py:38-53) gives 228 at L >= 124 but MORE for short series
-                                  * (336 at L = 64, 560 at L = 32): such layers are rejected with an error (documented limit,
-                                  * DESIGN.md section 6) */
+                                  * (336 at L = 64, 560 at L = 32): the tcgen05 entry points reject such layers; they are
+                                  * served by the fp32 CUDA-core engine up to TSC_MAX_CHANNELS_WIDE */
+#define TSC_MAX_CHANNELS_WIDE 2048 /* channel limit of the fp32 CUDA-core engine (TSC_ENGINE_SIMT), of the packing / layout / BatchNorm
+                                  * kernels and of tsc_oswgrad on that engine: layers wider than one TMEM tile -- the reference's
+                                  * recipe for series shorter than ~80 samples -- run there (the Python modules switch such a
+                                  * stack to it) */
 #define TSC_MAX_OPT_GROUPS 32    /* parameter groups of one tsc_rmsprop_step call */
 #define TSC_MAX_LIST 32          /* tensors of one tsc_multi_l2norm call */
 #define TSC_MAX_CLASSES 64       /* classes of the voting kernels */

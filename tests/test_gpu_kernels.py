@@ -415,7 +415,13 @@ def test_bad_arguments_raise(T):
     with pytest.raises(RuntimeError):
         ops.ncl_to_c8(torch.randn(2, 3, 4), L.TSC_F32)            # CPU tensor
     with pytest.raises(ValueError):
-        ops.dense_geometry(3, 300, 1)                              # too many channels
+        ops.dense_geometry(3, 3000, 1)                             # beyond TSC_MAX_CHANNELS_WIDE
+    wide = ops.dense_geometry(3, 300, 1)                           # wider than one TMEM tile: accepted, CUDA-core engine only
+    assert wide.wide
+    with pytest.raises(RuntimeError):
+        x8 = ops.ncl_to_c8(torch.randn(2, 3, 16, device="cuda"), L.TSC_BF16)
+        wf = ops.pack_weights(wide, torch.zeros(300, 3, 1, device="cuda"), L.DIR_FWD, L.TSC_BF16, False)
+        ops.osconv(L.ENGINE_TCGEN05, L.DIR_FWD, wide, x8, wf, torch.zeros(300, device="cuda"))
     with pytest.raises(ValueError):
         ops.bank_geometry([(1, 2, 3), (1, 2, 1), (1, 2, 3)])       # not nested
     geom = ops.dense_geometry(3, 4, 1)

@@ -229,6 +229,49 @@ def test_cfg4_long_series_against_the_oracle(T, engine, tol):
     T.set_engine("tcgen05")
 
 
+def test_short_series_wide_layers_run_on_the_cuda_core_engine(T):
+    """Series shorter than ~80 samples: the reference's layer recipe (train_and_test.py:38-53) gives layers wider than one
+    TMEM accumulator tile (L = 64, C = 3: 72 / 336 / 144 channels).  Those stacks run on the fp32 CUDA-core engine whatever
+    engine is selected -- the modules construct and train instead of raising -- and match the oracle at fp32 tolerance:
+    features, logits, loss, the head gradient and the live-tap gradient of the 336-channel bank."""
+    T.set_engine("tcgen05")
+    C, Ln, K, B = 3, 64, 4, 6
+    lpl_e, lpl_c = O.trainer_layer_lists(C, Ln)
+    widths = [sum(p[1] for p in layer) for layer in lpl_e]
+    assert max(widths) > 256, widths
+    fe, cl = build_modules(T, lpl_e, lpl_c, K, 11)
+    assert any(layer.geometry.wide for layer in fe.net_1.net.net)
+    torch.manual_seed(11)
+    ofe, ocl = O.init_extractor(lpl_e), O.init_classifier(lpl_c, K)
+    ofe, ocl = O.clone_state(ofe, requires_grad=True), O.clone_state(ocl, requires_grad=True)
+    x, y = O.synthetic_batch(B, C, Ln, K, 7)
+    feat = fe(x.cuda())
+    logits, pooled = cl(feat)
+    loss = torch.nn.functional.cross_entropy(logits, y.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    assert T.ops.read_watchdog() == 0
+    ofeat = O.extractor_forward(ofe, lpl_e, x, True)
+    ologits, opooled = O.classifier_forward(ocl, lpl_c, ofeat, True)
+    oloss = torch.nn.functional.cross_entropy(ologits, y)
+    oloss.backward()
+    wide_cls = any(layer.geometry.wide for layer in cl.net)
+    tol = 2e-4 if wide_cls else 1.5e-2           # a classifier without a wide layer stays on the selected (bf16) engine
+    assert rel_err(feat.detach().cpu(), ofeat.detach()) < 2e-4
+    assert rel_err(logits.detach().cpu(), ologits.detach()) < 4 * tol
+    assert abs(float(loss) - float(oloss)) < 10 * tol
+    wide_i = max(range(len(widths)), key=lambda i: widths[i])
+    gw = fe.net_1.net.net[wide_i].conv1d.weight.grad.cpu().numpy()
+    gref = ofe[f"net_1.net.net.{wide_i}.conv1d.weight"].grad.numpy() * O.build_mask(lpl_e[wide_i])
+    assert l2_rel(gw, gref) < (5e-3 if wide_cls else 0.3)
+    assert np.abs(gw * (1 - O.build_mask(lpl_e[wide_i]))).max() == 0.0
+    # the forward-only evaluation path of the same modules
+    fe.eval(); cl.eval()
+    with torch.no_grad():
+        lg, _ = cl(fe(x.cuda()))
+    assert lg.shape == (B, K) and bool(torch.isfinite(lg).all())
+
+
 def test_eval_mode_batchnorm_with_grad_on_the_fused_path(T):
     """train_and_test.py:583-586: the classifier is flipped to .eval() for one forward WITH autograd.  The fused path
     then takes its BatchNorm coefficients from the running statistics, leaves them untouched, and its backward is a

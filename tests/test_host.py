@@ -156,3 +156,18 @@ def test_default_engine_is_the_tensor_core_path_for_every_family():
         assert fresh.engine_name() == "tcgen05" and fresh.op_dtype() == L.TSC_BF16
     finally:
         importlib.reload(ops)
+
+
+def test_short_series_layers_are_marked_wide_instead_of_rejected():
+    """train_and_test.py:38-53 gives > 256-channel layers for series shorter than ~80 samples; the geometry accepts them (up to
+    TSC_MAX_CHANNELS_WIDE) and marks them for the fp32 CUDA-core engine."""
+    from feature_level_style_transfer_for_tsc_b200 import _lib as L
+    from feature_level_style_transfer_for_tsc_b200.OS_CNN.OS_CNN import OS_CNN, OS_CNN_res
+    from feature_level_style_transfer_for_tsc_b200.train_step import trainer_layer_lists
+    for Ln, widest in ((64, 336), (32, 560), (16, 1020)):
+        ext, cls, cf = trainer_layer_lists(3, Ln)
+        fe, cl = OS_CNN_res(ext), OS_CNN(cls, 4)
+        flags = [layer.geometry.wide for layer in fe.net_1.net.net]
+        assert max(sum(p[1] for p in layer) for layer in ext) == widest and any(flags)
+        assert cl.net[0].geometry.wide          # the classifier's first bank reads the widest feature map
+    assert L.MAX_CHANNELS == 256 and L.MAX_CHANNELS_WIDE == 2048
