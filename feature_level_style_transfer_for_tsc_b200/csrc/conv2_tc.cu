@@ -47,7 +47,7 @@ static constexpr int C2_THREADS = 192;
 static constexpr int C2_MAX_RUNS = 320;
 static constexpr int C2_MAX_STAGES = 256;
 static constexpr int C2_STAGE_BYTES = 16 * 1024;    // per CTA: a stage is 32 KB of the bank, half of it in each CTA of the pair
-static constexpr int C2_HDR = 256;
+static constexpr int C2_HDR = 384;
 static constexpr uint32_t RF_FIRST = 1u, RF_LAST = 2u;
 
 // One run = consecutive K steps of one tap inside one weight stage: two uint4 (every field ready to use -- the issuing warp
@@ -92,7 +92,9 @@ struct Conv2Params {
     int kc;            // input-channel chunks of 8
     int pad_left;
     int NS;            // weight stages in the ring
-    int nx, na;        // activation tiles / accumulator tiles (1 or 2)
+    int nx, na;        // activation tiles / accumulator tiles (1, 2 or 4)
+    int lg_nx, lg_na;  // their base-2 logarithms
+    int dual;          // persistent CTAs: two position tiles share every weight stage (one pass over the bank per tile pair)
     int acc_stride;    // TMEM columns per accumulator tile
     int tmem_cols;
     int off_bias, off_wstat, off_xs, off_stages, x_bytes;
@@ -261,11 +263,11 @@ osconv2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);            // [8]  weight stage filled
     uint64_t* empty = full + 8;                                    // [8]  weight stage consumed
-    uint64_t* x_full = empty + 8;                                  // [2]  activation tile landed
-    uint64_t* x_empty = x_full + 2;                                // [2]  ... consumed by the tile's MMAs
-    uint64_t* acc_full = x_empty + 2;                              // [2]  accumulator tile complete
-    uint64_t* acc_empty = acc_full + 2;                            // [2]  ... drained by BOTH epilogues (leader's copy is used)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* x_full = empty + 8;                                  // [4]  activation tile landed
+    uint64_t* x_empty = x_full + 4;                                // [4]  ... consumed by the tile's MMAs
+    uint64_t* acc_full = x_empty + 4;                              // [4]  accumulator tile complete
+    uint64_t* acc_empty = acc_full + 4;                            // [4]  ... drained by BOTH epilogues (leader's copy is used)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 4);
     float* bias_s = reinterpret_cast<float*>(smem + p.off_bias);
     float2* wstat = reinterpret_cast<float2*>(smem + p.off_wstat);  // [4][np]
     uint8_t* xs = smem + p.off_xs;
@@ -293,7 +295,7 @@ osconv2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
         // relay's remote arrival -- so the issuer waits on one barrier per stage / tile
         const uint32_t n_land = (PAIR && rank == 0) ? 2u : 1u;
         for (int i = 0; i < p.NS; ++i) { mbar_init(&full[i], n_land); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 4; ++i) {
             mbar_init(&x_full[i], n_land); mbar_init(&x_empty[i], 1);
             mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NCTA);   // PAIR: the two CTAs' epilogues
         }
@@ -353,34 +355,37 @@ osconv2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
             };
             // is the buffer of activation tile k free?  (its previous user, tile k - nx, has completed)
             auto x_free = [&](int k, bool block) -> bool {
-                const int xb = k & (nx - 1), use = nx == 2 ? (k >> 1) : k;
+                const int xb = k & (nx - 1), use = k >> p.lg_nx;
                 if (use == 0) return true;
                 if (block) { mbar_wait(&x_empty[xb], (uint32_t)((use - 1) & 1), dead, 10); return true; }
                 return mbar_try_wait(&x_empty[xb], (uint32_t)((use - 1) & 1));
             };
             load_x(0);
             int x_next = 1;                                   // next activation tile to request
-            if (x_next < n_my && nx == 2) { load_x(x_next); ++x_next; }
+            while (x_next < n_my && x_next < nx) { load_x(x_next); ++x_next; }
+            // dual: one pass over the bank serves the tile pair (2u, 2u + 1)
+            const int tpp = p.dual ? 2 : 1;                   // tiles per pass
+            const int n_pass = (n_my + tpp - 1) / tpp;
             uint32_t s = 0, ph = 0;
             const int n_stages = S.n_stages;
             // this CTA's half of every tap's live channels: the lower / upper stream of the split packed bank
             const uint8_t* w_src = reinterpret_cast<const uint8_t*>(p.w) + (size_t)rank * (size_t)p.half_rows16 * 16;
-            for (int j = 0; j < n_my; ++j) {
+            for (int u = 0; u < n_pass; ++u) {
+                const int j = u * tpp;                        // first tile of this pass
                 for (int i = 0; i < n_stages; ++i) {
                     const uint4 e = S.stages[i];
                     if (x_next < n_my && x_next <= j + nx - 1 && x_free(x_next, false)) { load_x(x_next); ++x_next; }
-                    TLS2(j * n_stages + i, 4);
+                    TLS2(u * n_stages + i, 4);
                     if (DBG && (p.debug & 512)) mbar_wait_sleep(&empty[s], ph ^ 1u, dead, 1, 200); else mbar_wait(&empty[s], ph ^ 1u, dead, 1);
-                    TLS2(j * n_stages + i, 5);
+                    TLS2(u * n_stages + i, 5);
                     if (DBG && (p.debug & 1024)) continue;  // experiment: no weight pipeline at all (the issuer neither waits nor commits)
                     if (DBG && (p.debug & 1)) { mbar_arrive(&full[s]); if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; } continue; }
                     mbar_arrive_expect_tx(&full[s], e.y);
                     bulk_load(stages + (size_t)s * slot_bytes, w_src + (size_t)e.x * 16, e.y, &full[s]);
                     if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; }
                 }
-                // whatever tile j + 1 still needs: its buffer is free at the latest when tile j's MMAs (nx == 1) or tile
-                // j - 1's (nx == 2) have completed
-                if (x_next < n_my && x_next <= j + 1) { x_free(x_next, true); load_x(x_next); ++x_next; }
+                // whatever the next pass still needs: its buffers are free at the latest when this pass's MMAs have completed
+                while (x_next < n_my && x_next < j + 2 * tpp) { x_free(x_next, true); load_x(x_next); ++x_next; }
             }
         }
     } else if (warp == 1) {
@@ -399,15 +404,26 @@ osconv2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
             const uint32_t slot16 = (uint32_t)slot_bytes >> 4;
             const uint32_t x16 = (uint32_t)p.x_bytes >> 4;
             uint32_t slot_cur = st16;                                                  // start of weight slot s (16 B units)
-            for (int j = 0; j < n_my; ++j) {
-                const uint32_t xb = (uint32_t)j & (uint32_t)(nx - 1), xuse = nx == 2 ? ((uint32_t)j >> 1) : (uint32_t)j;
-                const uint32_t ab = (uint32_t)j & (uint32_t)(na - 1), ause = na == 2 ? ((uint32_t)j >> 1) : (uint32_t)j;
-                ok = mbar_wait_warp(&x_full[xb], xuse & 1u) && ok;
-                if (ause > 0) ok = mbar_wait_warp(&acc_empty[ab], (ause - 1u) & 1u) && ok;
+            // One pass over the bank serves one tile, or -- persistent CTAs with several tiles (dual) -- the tile pair
+            // (2u, 2u + 1): every run is issued for both tiles back to back, so the L2 -> shared-memory weight traffic and the
+            // barrier round trips of the weight pipeline are paid once per pair (at B = 1024 they were 31 % of the kernel:
+            // profiles/r2_conv2_issue_bisection.md).  The pair's accumulators are two of the `na` TMEM tiles.
+            const int tpp = p.dual ? 2 : 1;
+            const int n_pass = (n_my + tpp - 1) / tpp;
+            for (int u = 0; u < n_pass; ++u) {
+                const uint32_t j0 = (uint32_t)(u * tpp);
+                const bool has_b = tpp == 2 && (int)j0 + 1 < n_my;
+                const uint32_t j1 = has_b ? j0 + 1u : j0;
+                const uint32_t xb0 = j0 & (uint32_t)(nx - 1), xuse0 = j0 >> p.lg_nx, xb1 = j1 & (uint32_t)(nx - 1), xuse1 = j1 >> p.lg_nx;
+                const uint32_t ab0 = j0 & (uint32_t)(na - 1), ause0 = j0 >> p.lg_na, ab1 = j1 & (uint32_t)(na - 1), ause1 = j1 >> p.lg_na;
+                ok = mbar_wait_warp(&x_full[xb0], xuse0 & 1u) && ok;
+                if (has_b) ok = mbar_wait_warp(&x_full[xb1], xuse1 & 1u) && ok;
+                if (ause0 > 0) ok = mbar_wait_warp(&acc_empty[ab0], (ause0 - 1u) & 1u) && ok;
+                if (has_b && ause1 > 0) ok = mbar_wait_warp(&acc_empty[ab1], (ause1 - 1u) & 1u) && ok;
                 tc_fence_after();
-                if (j == 0) TL2(2);                   // (all lanes store: a lane-dependent branch here would cost the loop its uniformity)
-                const uint32_t a_base = (xs16 + xb * x16) | a_lbo;
-                const uint32_t d_base = tmem_base + ab * (uint32_t)p.acc_stride;
+                if (u == 0) TL2(2);                   // (all lanes store: a lane-dependent branch here would cost the loop its uniformity)
+                const uint32_t a_base = (xs16 + xb0 * x16) | a_lbo, a_base1 = (xs16 + xb1 * x16) | a_lbo;
+                const uint32_t d_base = tmem_base + ab0 * (uint32_t)p.acc_stride, d_base1 = tmem_base + ab1 * (uint32_t)p.acc_stride;
                 if (DBG && (p.debug & 2048)) {
                     // experiment: the micro-benchmark's loop inside this kernel -- 3 * n_runs + 6 identical MMAs (N = 112), no
                     // table, no barriers; what does the issue slot cost here?  (profiles/r2_conv2_issue_bisection.md)
@@ -427,9 +443,9 @@ osconv2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
 #pragma unroll 1
                     for (int i = 0; i < n_stages; ++i) {
                         if (!no_pipe) {
-                            TLS2(j * n_stages + i, 0);
+                            TLS2(u * n_stages + i, 0);
                             ok = mbar_wait_warp(&full[s], ph) && ok;
-                            TLS2(j * n_stages + i, 1);
+                            TLS2(u * n_stages + i, 1);
                         }
                         if (elect_one()) {
                             const uint32_t r0 = S.stages[i].z, r1 = r0 + S.stages[i].w;     // (read here: a value that lives across the
@@ -437,24 +453,29 @@ osconv2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                             for (uint32_t r = r0; r < r1; ++r) {
                                 const uint4 e = S.runs[2 * r], f = S.runs[2 * r + 1];
                                 issue_run<PAIR>(d_base + e.w, a_base + e.x, slot_cur + e.y, desc_hi, e.z, f.z, f.x, a_step, f.y);
+                                if (has_b) issue_run<PAIR>(d_base1 + e.w, a_base1 + e.x, slot_cur + e.y, desc_hi, e.z, f.z, f.x, a_step, f.y);
                             }
                             if (!no_pipe) mma_commit<PAIR>(&empty[s]);   // frees the stage (in both CTAs) when these MMAs have read it
                         }
-                        TLS2(j * n_stages + i, 3);
+                        TLS2(u * n_stages + i, 3);
                         slot_cur += slot16;
                         if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1u; slot_cur = st16; }
                     }
                 }
                 if (elect_one()) {
-                    mma_commit<PAIR>(&acc_full[ab]);
-                    mma_commit<PAIR>(&x_empty[xb]);
+                    mma_commit<PAIR>(&acc_full[ab0]);
+                    mma_commit<PAIR>(&x_empty[xb0]);
+                    if (has_b) {
+                        mma_commit<PAIR>(&acc_full[ab1]);
+                        mma_commit<PAIR>(&x_empty[xb1]);
+                    }
                 }
             }
         } else {
             // ===== relay (peer CTA): tells the leader's barriers when this CTA's activation tile / half stage has landed =====
             const uint32_t px_remote = mapa_u32(smem_u32(x_full), 0), pf_remote = mapa_u32(smem_u32(full), 0);
             for (int j = 0; j < n_my; ++j) {
-                const uint32_t xb = (uint32_t)j & (uint32_t)(nx - 1), xuse = nx == 2 ? ((uint32_t)j >> 1) : (uint32_t)j;
+                const uint32_t xb = (uint32_t)j & (uint32_t)(nx - 1), xuse = (uint32_t)j >> p.lg_nx;
                 ok = mbar_wait_warp(&x_full[xb], xuse & 1u) && ok;
                 if (elect_one()) mbar_arrive_remote(px_remote + xb * 8u);
 #pragma unroll 1
@@ -488,7 +509,7 @@ osconv2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
             const size_t row_off = ((size_t)b * npc * p.L + (size_t)(valid ? l : 0)) * 8;
             float* ybase = p.y + row_off;
             const float* mbase = do_red ? p.mask_y + row_off : nullptr;
-            const int ab = j & (na - 1), ause = na == 2 ? (j >> 1) : j;
+            const int ab = j & (na - 1), ause = j >> p.lg_na;
             const uint32_t t_acc = tmem_base + (uint32_t)(ab * p.acc_stride) + ((uint32_t)(q * 32) << 16);
             // one thread polls the accumulator barrier; the other 127 sleep in a named barrier instead of spinning on
             // mbarrier.try_wait next to the MMA issuer
@@ -707,6 +728,7 @@ int make_c8_map(CUtensorMap* map, const void* base, int B, int kc, int L, int bo
 static inline int conv2_rp(int Kmax) { return (128 + Kmax - 1 + 7) & ~7; }
 static int knob2_stage_bytes();
 static int knob2_debug();
+static int knob2_dual();
 
 // ---- the schedule: runs + stages, built once per bank geometry and direction, cached ----------------------------------------
 static int build_sched(bool pair, int direction, int Cin, int Cout, int Kmax, const int* s_of_tap, ConvSched* sc) {
@@ -827,6 +849,7 @@ static int knob2_stage_bytes() { static const int v = env_int2("TSC_C2_STAGE_KB"
 static int knob2_smem_full() { static const int v = env_int2("TSC_C2_SMEM_FULL", 0); return v; }
 static int knob2_grid() { static const int v = env_int2("TSC_C2_GRID", 0); return v; }
 static int knob2_debug() { static const int v = env_int2("TSC_C2_DEBUG", 0); return v; }
+static int knob2_dual() { static const int v = env_int2("TSC_C2_DUAL", 1); return v; }
 
 }  // namespace tc
 
@@ -900,11 +923,16 @@ int osconv2_tc(int direction, const void* x, int dtype, const void* w, const flo
     int grid_pairs = persistent ? max_pairs : n_pairs;
     if (persistent && knob2_grid() > 0 && knob2_grid() < grid_pairs) grid_pairs = knob2_grid();
     const int grid = ncta * grid_pairs;
-    p.na = persistent ? 2 : 1;
+    // persistent CTAs: two tiles per pass over the bank (not for CTA pairs); four accumulator tiles when they fit TMEM, so
+    // that the epilogues of one tile pair overlap the MMAs of the next
+    // (measured, profiles/r2_conv2_dual.md: pays when the epilogues still overlap -- four accumulator tiles, np <= 128 -- or
+    // when the bank is large, >= 256 KB per pass; a small bank behind a wide accumulator loses the overlap for nothing)
+    const size_t bank_bytes = (size_t)sc->half_rows16 * 32;
+    p.dual = (persistent && !pair && knob2_dual() && (p.acc_stride <= 128 || bank_bytes >= 256 * 1024)) ? 1 : 0;
+    p.na = persistent ? ((p.dual && p.acc_stride <= 128) ? 4 : 2) : 1;
     p.tiles_base = n_pairs / grid_pairs;
     p.tiles_rem = n_pairs % grid_pairs;
     p.half_rows16 = sc->half_rows16;
-    p.tmem_cols = p.acc_stride * p.na;
     p.off_bias = C2_HDR;
     p.off_wstat = p.off_bias + 4 * p.np * 4;
     p.off_xs = (p.off_wstat + 4 * p.np * 8 + 127) & ~127;
@@ -921,12 +949,22 @@ int osconv2_tc(int direction, const void* x, int dtype, const void* w, const flo
     int ns = 0;
     if (persistent) {
         p.nx = 2;
-        if (!layout(2, cap_full, &ns)) { p.nx = 1; TSC_REQUIRE(layout(1, cap_full, &ns), "shape needs %d B of shared memory before the weight stages: unsupported", p.off_stages); }
+        if (p.dual && layout(4, cap_full, &ns) && ns >= 3) {
+            p.nx = 4;                            // the next pair's activation tiles land while this pair is being multiplied
+        } else if (!layout(2, cap_full, &ns)) {
+            p.nx = 1;
+            p.dual = 0;                          // (a tile pair needs two activation buffers)
+            if (p.na == 4) p.na = 2;
+            TSC_REQUIRE(layout(1, cap_full, &ns), "shape needs %d B of shared memory before the weight stages: unsupported", p.off_stages);
+        }
     } else {
         p.nx = 1;
         if (knob2_smem_full() || !layout(1, cap_half, &ns)) TSC_REQUIRE(layout(1, cap_full, &ns), "shape needs %d B of shared memory before the weight stages: unsupported", p.off_stages);
     }
     p.NS = ns;
+    p.tmem_cols = p.acc_stride * p.na;
+    p.lg_nx = p.nx == 4 ? 2 : p.nx == 2 ? 1 : 0;
+    p.lg_na = p.na == 4 ? 2 : p.na == 2 ? 1 : 0;
     p.tl = g_timeline2;
     p.debug = knob2_debug();
     CUtensorMap xmap;
