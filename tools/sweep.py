@@ -61,7 +61,7 @@ def main():
 
     # ---- conv family on the widest bank of each configuration ----
     conv_shapes = [(9, 128, 128), (9, 128, 1024), (9, 128, 4096)] if a.quick else \
-        [(9, 128, 128), (9, 128, 1024), (9, 128, 4096), (3, 1024, 256), (3, 1024, 1024), (9, 512, 1024)]
+        [(9, 128, 128), (9, 128, 1024), (9, 128, 4096), (3, 1024, 256), (3, 1024, 1024), (9, 512, 1024), (3, 4096, 64)]
     for (C, Ln, B) in conv_shapes:
         ext, cls, cf = trainer_layer_lists(C, Ln)
         g = ops.bank_geometry(ext[1])
