@@ -54,23 +54,51 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled during the timed region -- in process through NVML (`nvidia_ml_py`).  Round 1
+    spawned `nvidia-smi` every 50 ms; with eight ranks doing that concurrently single steps of the timed region took 26 ms
+    instead of 1.3 (`profiles/r2_dp_exchange.md`): a subprocess per sample is itself a disturbance.  `nvidia-smi` remains the
+    fallback when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
         self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        self.nvml, self.handle, self.source = None, None, "nvidia-smi"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it lists plain indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [int(v) for v in vis.split(",")] if vis and all(v.strip().isdigit() for v in vis.split(",")) else None
+            phys = ids[index] if ids and index < len(ids) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = int(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml, self.source = pynvml, "nvml"
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = int(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        bits = [n.nvmlClocksEventReasonHwSlowdown, n.nvmlClocksEventReasonHwThermalSlowdown,
+                n.nvmlClocksEventReasonSwThermalSlowdown, n.nvmlClocksEventReasonSwPowerCap]
+        return [str(sm), str(self.max_sm)] + ["Active" if mask & b else "Not Active" for b in bits]
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self.nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                          str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.02 if self.nvml is not None else 0.05)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -84,10 +112,9 @@ class ClockSampler:
     def summary(self):
         sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
         mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in self.rows for n, v in zip(self.NAMES, r[2:6]) if v.lower().startswith("active")})
         return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=(max(mx) if mx else None), reasons=reasons,
-                    samples=len(self.rows))
+                    samples=len(self.rows), source=self.source)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -503,10 +530,19 @@ def run_ours(args):
             e1.record()
             evs.append((e0, e1))
         torch.cuda.synchronize()
-        return sum(a.elapsed_time(b) for a, b in evs) * 1e-3
+        ts = sorted(a.elapsed_time(b) for a, b in evs)
+        spread.append((ts[0], ts[len(ts) // 2], ts[-1]))
+        return sum(ts) * 1e-3
 
+    spread = []                                  # (min, median, max) step ms of every timed region of this rank
     for _ in range(max(args.warmup, 3)):
         trainer.step(*dev_in)
+    if world > 1:
+        # a captured NCCL collective keeps setting itself up over its first replays (measured on 8 GPUs: the first ~100
+        # replays of the step graph averaged 2.1 ms against 1.3 ms afterwards): these extra untimed replays come on top of
+        # the --warmup steps, the K timed steps are unchanged
+        for _ in range(30):
+            trainer.step(*dev_in)
     barrier()
     with ClockSampler(local_rank) as clocks:
         t_dev = timed(args.steps, False)
@@ -612,7 +648,10 @@ def run_ours(args):
                 run=dict(engine=args.engine, parallelism=f"dp{world}", cuda_graph=not args.no_graph),
                 e2e=dict(value=series / t_e2e, unit=UNIT, h2d_bytes_per_step=h2d_bytes * world, d2h_bytes_per_step=4 * world,
                          ms_per_step=t_e2e / args.steps * 1e3),
-                gpu_launches=int(launches), clocks=clocks.summary(), roofline=roof, kernels=kern)
+                gpu_launches=int(launches), clocks=clocks.summary(), roofline=roof, kernels=kern,
+                step_ms_spread=dict(device=dict(zip(("min", "median", "max"), [round(v, 4) for v in spread[0]])),
+                                    e2e=dict(zip(("min", "median", "max"), [round(v, 4) for v in spread[1]])),
+                                    note="rank 0, per-step CUDA-event times of the two timed regions"))
     if cpu:
         line["cpu_baseline"] = cpu
     line.update(extra)
