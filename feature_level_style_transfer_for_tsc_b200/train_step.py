@@ -283,6 +283,17 @@ class FlatParameters:
                          self.group_clamp)
 
 
+def remaining_ranges(done, n: int):
+    """The parts of [0, n) that the half-open ranges in `done` do not cover, as few contiguous ranges as possible and in
+    ascending order (what is left of the flat gradient bucket after the early all-reduces of a step)."""
+    pos, rest = 0, []
+    for lo, hi in sorted(done) + [(n, n)]:
+        if lo > pos:
+            rest.append((pos, lo))
+        pos = max(pos, hi)
+    return rest
+
+
 class Trainer:
     """forward + backward + (all-reduce) + fused RMSprop of the cfg2 step.
 
@@ -376,13 +387,7 @@ class Trainer:
         if not self._early_done:
             dist.all_reduce(self.flat.flat_g, op=dist.ReduceOp.SUM, group=self.group)
             return world
-        done = sorted(self._group_range[n] for n in self._early_done)
-        pos, rest = 0, []
-        for lo, hi in done + [(self.flat.flat_g.numel(), self.flat.flat_g.numel())]:
-            if lo > pos:
-                rest.append((pos, lo))
-            pos = max(pos, hi)
-        for lo, hi in rest:
+        for lo, hi in remaining_ranges([self._group_range[n] for n in self._early_done], self.flat.flat_g.numel()):
             dist.all_reduce(self.flat.flat_g[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
         for w in self._early_works:
             w.wait()                               # the current stream waits for the early slices

@@ -171,3 +171,21 @@ def test_short_series_layers_are_marked_wide_instead_of_rejected():
         assert max(sum(p[1] for p in layer) for layer in ext) == widest and any(flags)
         assert cl.net[0].geometry.wide          # the classifier's first bank reads the widest feature map
     assert L.MAX_CHANNELS == 256 and L.MAX_CHANNELS_WIDE == 2048
+
+
+def test_remaining_ranges_of_the_gradient_bucket():
+    """What the data-parallel trainer still has to all-reduce after the early (overlapped) slices: every element of the
+    bucket exactly once, in as few contiguous ranges as possible."""
+    from feature_level_style_transfer_for_tsc_b200.train_step import remaining_ranges
+    assert remaining_ranges([], 10) == [(0, 10)]
+    assert remaining_ranges([(0, 10)], 10) == []
+    assert remaining_ranges([(2, 4), (7, 10)], 10) == [(0, 2), (4, 7)]
+    assert remaining_ranges([(7, 9), (2, 4)], 10) == [(0, 2), (4, 7), (9, 10)]          # any order
+    assert remaining_ranges([(2, 5), (4, 6)], 8) == [(0, 2), (6, 8)]                     # overlapping slices
+    # the cfg2 groups (fe_t, cl_t, fe_s, du, cl_s): the classifiers went early
+    ends = [100, 160, 260, 300, 372]
+    rng = dict(zip(("fe_t", "cl_t", "fe_s", "du", "cl_s"), zip([0] + ends[:-1], ends)))
+    rest = remaining_ranges([rng["cl_t"], rng["cl_s"]], ends[-1])
+    assert rest == [(0, 100), (160, 300)]
+    covered = sorted(rest + [rng["cl_t"], rng["cl_s"]])
+    assert covered[0][0] == 0 and covered[-1][1] == ends[-1] and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
