@@ -48,12 +48,14 @@ class GradNormSide:
     """The balanced weights of one side, their Adam optimizer and the first-batch reference losses
     (train_and_test.py:501-510)."""
 
-    def __init__(self, names: Sequence[str], init: Sequence[float], total: float, lr: float, device):
+    def __init__(self, names: Sequence[str], init: Sequence[float], total: float, lr: float, device, capturable: bool = False):
         self.names = tuple(names)
         self.total = float(total)
         self.weights = nn.Parameter(torch.tensor(list(init), dtype=torch.float32, device=device))
-        self.optimizer = torch.optim.Adam([self.weights], lr=lr)
+        # capturable: Adam keeps its step count on the device, so that its update can be part of a CUDA graph (same formulas)
+        self.optimizer = torch.optim.Adam([self.weights], lr=lr, capturable=bool(capturable))
         self.initial: Optional[np.ndarray] = None     # sigmoid of the first batch's losses (:663-666)
+        self.initial_dev: Optional[torch.Tensor] = None   # the same on the device (step_device)
 
     def renormalize_(self) -> None:
         """train_and_test.py:752-757"""
@@ -62,12 +64,13 @@ class GradNormSide:
             self.weights.mul_(self.total / torch.sum(self.weights))
 
 
-def target_side(device) -> GradNormSide:
-    return GradNormSide(("target_nf_loss", "target_classification_loss"), (2, 5), 7, 0.0002, device)
+def target_side(device, capturable: bool = False) -> GradNormSide:
+    return GradNormSide(("target_nf_loss", "target_classification_loss"), (2, 5), 7, 0.0002, device, capturable)
 
 
-def source_side(device) -> GradNormSide:
-    return GradNormSide(("source_nf_loss", "source_classification_loss", "s2t2s_classification_loss"), (2, 2, 4), 8, 0.001, device)
+def source_side(device, capturable: bool = False) -> GradNormSide:
+    return GradNormSide(("source_nf_loss", "source_classification_loss", "s2t2s_classification_loss"), (2, 2, 4), 8, 0.001, device,
+                        capturable)
 
 
 def shared_grad_norm_sums(losses: Sequence[torch.Tensor], shared_params: List[torch.Tensor]) -> torch.Tensor:
@@ -92,6 +95,16 @@ def _weight_gradient(w: np.ndarray, sums: np.ndarray, loss_values: np.ndarray, i
     return norms, target, grad
 
 
+def _weight_gradient_device(w: torch.Tensor, sums: torch.Tensor, loss_values: torch.Tensor, initial: torch.Tensor, alpha: float):
+    """``_weight_gradient`` on the device (fp32 tensors of 2-3 elements): no host round trip, capturable in a CUDA graph."""
+    norms = w.abs() * sums
+    ratio = torch.sigmoid(loss_values) / initial
+    inv_rate = ratio / ratio.mean()
+    target = norms.mean() * inv_rate.pow(alpha)
+    grad = torch.sign(norms - target) * torch.sign(w) * sums
+    return norms, target, grad
+
+
 class JointStageDriver:
     """One call of ``step`` = train_and_test.py:646-766 for one batch.
 
@@ -103,13 +116,54 @@ class JointStageDriver:
     """
 
     def __init__(self, shared_t: nn.Module, shared_s: nn.Module, optimizers: Sequence, clamps: Iterable = (),
-                 alpha: float = ALPHA, device="cuda"):
+                 alpha: float = ALPHA, device="cuda", capturable: bool = False):
         self.shared_t, self.shared_s = shared_t, shared_s
         self.optimizers = list(optimizers)
         self.clamps = list(clamps)
         self.alpha = alpha
-        self.t = target_side(device)
-        self.s = source_side(device)
+        self.t = target_side(device, capturable)
+        self.s = source_side(device, capturable)
+
+    def step_device(self, losses: Dict[str, torch.Tensor], coefficients: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """``step`` without any host round trip: the remainder multipliers arrive as a device tensor of four floats
+        (``remainder_coefficients(cur_epoch)``), the GradNorm weight gradient is computed on the device, and the results stay
+        device tensors.  Every operation is capturable, so a whole joint-stage step -- forward included -- can be ONE CUDA
+        graph (``GraphedJointStage``); the optimizers passed to the driver must then be capturable too.  The first call
+        (outside a capture) fixes the reference losses of train_and_test.py:663-666."""
+        t, s = self.t, self.s
+        lt = torch.stack([losses[k] for k in t.names])
+        ls = torch.stack([losses[k] for k in s.names])
+        c = coefficients
+        remainder = (c[0] * losses["cdan_loss"] + c[1] * losses["feature_discriminator_s_loss"]
+                     + c[2] * losses["t_sl_loss"] + c[3] * losses["s_sl_loss"])
+        balanced = torch.sum(t.weights.detach() * lt) + torch.sum(s.weights.detach() * ls)
+        for opt in self.optimizers:
+            opt.zero_grad()
+        sums_t = shared_grad_norm_sums(list(lt.unbind(0)), list(self.shared_t.parameters()))
+        sums_s = shared_grad_norm_sums(list(ls.unbind(0)), list(self.shared_s.parameters()))
+        if t.initial_dev is None:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("the first joint-stage step fixes the reference losses and must run outside a CUDA graph")
+            t.initial_dev = torch.sigmoid(lt.detach()).clone()
+            s.initial_dev = torch.sigmoid(ls.detach()).clone()
+            t.initial, s.initial = t.initial_dev.cpu().numpy(), s.initial_dev.cpu().numpy()
+        norms_t, target_t, grad_t = _weight_gradient_device(t.weights.detach(), sums_t, lt.detach(), t.initial_dev, self.alpha)
+        norms_s, target_s, grad_s = _weight_gradient_device(s.weights.detach(), sums_s, ls.detach(), s.initial_dev, self.alpha)
+        (balanced + 2.0 * remainder).backward()
+        t.weights.grad = grad_t
+        s.weights.grad = grad_s
+        t.optimizer.step()
+        s.optimizer.step()
+        for opt in self.optimizers:
+            opt.step()
+        t.renormalize_()
+        s.renormalize_()
+        with torch.no_grad():
+            for mod, cl in self.clamps:
+                for p in mod.parameters():
+                    p.clamp_(-cl, cl)
+        return dict(norms_t=norms_t, norms_s=norms_s, target_t=target_t, target_s=target_s, grad_w_t=grad_t, grad_w_s=grad_s,
+                    loss_t=lt.detach(), loss_s=ls.detach())
 
     def step(self, losses: Dict[str, torch.Tensor], cur_epoch: int) -> Dict[str, np.ndarray]:
         t, s = self.t, self.s
@@ -151,3 +205,53 @@ class JointStageDriver:
                     p.clamp_(-c, c)
         return dict(norms_t=norms_t, norms_s=norms_s, target_t=target_t, target_s=target_s, grad_w_t=grad_t, grad_w_s=grad_s,
                     loss_t=lv_t, loss_s=lv_s)
+
+
+class GraphedJointStage:
+    """A joint-stage step as ONE CUDA graph: the named losses (forward of every module), the per-loss gradient-norm passes over
+    the shared blocks, the GradNorm weight gradient, the main backward, Adam on the balanced weights, the module optimizers,
+    the renormalisation and the WGAN clamps (train_and_test.py:547-611 + 646-766 for one batch).  Eagerly that step is
+    ~700 launches and 15 ms at cfg2 size (``tools/bench_eval.py``), almost all of it host launch latency.
+
+    loss_fn(*inputs) -> dict of the named losses; it is called on STATIC copies of the inputs.  The driver must have been built
+    with ``capturable=True`` and capturable optimizers (``torch.optim.RMSprop(..., capturable=True)`` or a fused
+    ``train_step.FlatParameters`` step).  The first two calls run eagerly (the first fixes the GradNorm reference losses,
+    both warm the allocator and the libraries up), the third captures, later calls replay; the remainder multipliers of the
+    current epoch travel in a device tensor, so one graph serves every epoch."""
+
+    EAGER_STEPS = 2
+
+    def __init__(self, driver: JointStageDriver, loss_fn: Callable[..., Dict[str, torch.Tensor]]):
+        self.driver, self.loss_fn = driver, loss_fn
+        self.calls = 0
+        self._graph = None
+        self._static_in: Optional[List[torch.Tensor]] = None
+        self._coef = None
+        self._out: Optional[Dict[str, torch.Tensor]] = None
+
+    def _body(self) -> Dict[str, torch.Tensor]:
+        return self.driver.step_device(self.loss_fn(*self._static_in), self._coef)
+
+    def step(self, *inputs: torch.Tensor, cur_epoch: int = 0) -> Dict[str, torch.Tensor]:
+        if self._static_in is None:
+            self._static_in = [t.clone() for t in inputs]
+            self._coef = torch.zeros(4, device=inputs[0].device, dtype=torch.float32)
+        for dst, src in zip(self._static_in, inputs):
+            dst.copy_(src, non_blocking=True)
+        self._coef.copy_(torch.tensor(remainder_coefficients(cur_epoch), dtype=torch.float32), non_blocking=True)
+        self.calls += 1
+        if self.calls <= self.EAGER_STEPS:
+            # on a side stream, as the warm-up of a graph capture has to be
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                out = self._body()
+            torch.cuda.current_stream().wait_stream(side)
+            return out
+        if self._graph is None:
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._out = self._body()
+            # capturing does not execute: the step itself is the first replay
+        self._graph.replay()
+        return self._out

@@ -161,6 +161,95 @@ def test_gradnorm_joint_stage_driver(T, gradnorm, engine, tol_norm, tol_grad, to
         assert float(critic.weight.abs().max()) <= 0.0005 + 1e-9      # WGAN clamp (:763-766)
 
 
+def _joint_stage_setup(T, gradnorm, capturable):
+    from feature_level_style_transfer_for_tsc_b200 import grad_norm as D
+    meta = json.loads(str(gradnorm["meta"]))
+    mods = build_gradnorm_modules(T, gradnorm, meta)
+    opts = [torch.optim.RMSprop(m.parameters(), lr=lr, capturable=capturable) for m, lr in zip(mods, (0.001, 0.003, 0.001, 0.003))]
+    drv = D.JointStageDriver(mods[0].return_last_layer(), mods[2].return_last_layer(), opts, capturable=capturable)
+    return meta, mods, drv
+
+
+def test_joint_stage_device_path_matches_the_host_path(T, gradnorm):
+    """JointStageDriver.step_device (no host round trip: device-side GradNorm weight gradient, remainder multipliers in a device
+    tensor) against JointStageDriver.step -- the path pinned by the reference-executed golden vectors -- for the first batch:
+    same norms / targets / weight gradients, the same parameter gradients, the same balanced weights afterwards."""
+    from feature_level_style_transfer_for_tsc_b200 import grad_norm as D
+    from feature_level_style_transfer_for_tsc_b200 import functional as TF
+    T.set_engine("simt")
+    xt, yt = torch.from_numpy(gradnorm["b0/xt"]).cuda(), torch.from_numpy(gradnorm["b0/yt"]).cuda()
+    xs, ys = torch.from_numpy(gradnorm["b0/xs"]).cuda(), torch.from_numpy(gradnorm["b0/ys"]).cuda()
+    meta, mods_a, drv_a = _joint_stage_setup(T, gradnorm, False)
+    _, mods_b, drv_b = _joint_stage_setup(T, gradnorm, True)
+    la = GN.named_losses(mods_a, xt, yt, xs, ys, meta["style_weight"], adain=TF.adain, gram_style_loss=TF.gram_style_loss)
+    info_a = drv_a.step(la, meta["cur_epoch"])
+    lb = GN.named_losses(mods_b, xt, yt, xs, ys, meta["style_weight"], adain=TF.adain, gram_style_loss=TF.gram_style_loss)
+    coef = torch.tensor(D.remainder_coefficients(meta["cur_epoch"]), dtype=torch.float32, device="cuda")
+    info_b = drv_b.step_device(lb, coef)
+    torch.cuda.synchronize()
+    for k in ("norms_t", "norms_s", "target_t", "target_s", "grad_w_t", "grad_w_s", "loss_t", "loss_s"):
+        assert rel_err(info_b[k].cpu().numpy(), info_a[k]) < 1e-5, k
+    for side in ("t", "s"):
+        assert rel_err(getattr(drv_b, side).weights.detach().cpu(), getattr(drv_a, side).weights.detach().cpu()) < 1e-5
+        assert rel_err(getattr(drv_b, side).initial, getattr(drv_a, side).initial) < 1e-6
+    for ma, mb in zip(mods_a, mods_b):
+        for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+            ga, gb = pa.grad.float(), pb.grad.float()             # the same kernels on the same values
+            assert float((ga - gb).abs().max()) <= 1e-6 * max(1e-6, float(ga.abs().max())), k
+    T.set_engine("tcgen05")
+
+
+def test_graphed_joint_stage_follows_the_eager_steps(T, gradnorm):
+    """GraphedJointStage on the product engine: five joint-stage steps on five different batches -- two eager, the capture, two
+    more replays -- against the same five steps run eagerly through step_device on an identical module set.  A replay that read
+    stale inputs, skipped an optimizer or lost the epoch's multipliers would be off by O(1); what is allowed is the rounding
+    difference of library kernels chosen under capture (RMSprop's first steps are sign-like and amplify it)."""
+    from feature_level_style_transfer_for_tsc_b200 import grad_norm as D
+    from feature_level_style_transfer_for_tsc_b200 import functional as TF
+    T.set_engine("tcgen05")
+    meta, mods_a, drv_a = _joint_stage_setup(T, gradnorm, True)
+    _, mods_b, drv_b = _joint_stage_setup(T, gradnorm, True)
+    sw = meta["style_weight"]
+
+    def loss_fn_b(xt, yt, xs, ys):
+        return GN.named_losses(mods_b, xt, yt, xs, ys, sw, adain=TF.adain, gram_style_loss=TF.gram_style_loss)
+
+    stage = D.GraphedJointStage(drv_b, loss_fn_b)
+    B, C, Ln = gradnorm["b0/xt"].shape
+    K = meta["n_class"]
+    epochs = [0, 0, 0, 13, 30]                                        # the multipliers change while ONE graph is replayed
+    hist_a, hist_b = [], []
+    for i, ep in enumerate(epochs):
+        xt, yt = O.synthetic_batch(B, C, Ln, K, 40 + 2 * i)
+        xs, ys = O.synthetic_batch(B, C, Ln, K, 41 + 2 * i)
+        xt, yt, xs, ys = xt.cuda(), yt.cuda(), xs.cuda(), ys.cuda()
+        la = GN.named_losses(mods_a, xt, yt, xs, ys, sw, adain=TF.adain, gram_style_loss=TF.gram_style_loss)
+        coef = torch.tensor(D.remainder_coefficients(ep), dtype=torch.float32, device="cuda")
+        ia = drv_a.step_device(la, coef)
+        ib = stage.step(xt, yt, xs, ys, cur_epoch=ep)
+        torch.cuda.synchronize()
+        hist_a.append({k: v.detach().cpu().numpy().copy() for k, v in ia.items()})
+        hist_b.append({k: v.detach().cpu().numpy().copy() for k, v in ib.items()})
+    assert stage._graph is not None and stage.calls == 5
+    assert T.ops.read_watchdog() == 0
+    for i, (a, b) in enumerate(zip(hist_a, hist_b)):
+        for k in ("loss_t", "loss_s", "norms_t", "norms_s"):
+            assert rel_err(b[k], a[k]) < 5e-2, (i, k, a[k], b[k])
+    for side in ("t", "s"):
+        wa, wb = getattr(drv_a, side).weights.detach().cpu().numpy(), getattr(drv_b, side).weights.detach().cpu().numpy()
+        assert rel_err(wb, wa) < 1e-2 and abs(wb.sum() - (7.0 if side == "t" else 8.0)) < 1e-4, (side, wa, wb)
+    moved = 0.0
+    for nm, ma, mb in zip(("fe_t", "cl_t", "fe_s", "cl_s"), mods_a, mods_b):
+        for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+            if k.endswith("conv1d.bias"):
+                continue                                              # gradient ~0 behind a BatchNorm: pure sign noise under RMSprop
+            init = torch.from_numpy(gradnorm[f"init/{nm}/{k}"]).cuda()
+            step_size = float((pa.detach() - init).norm())
+            moved += step_size
+            assert float((pa.detach() - pb.detach()).norm()) <= 0.25 * step_size + 1e-6, (nm, k)
+    assert moved > 0.0                                                # the optimizers really stepped inside the graph
+
+
 @pytest.mark.parametrize("engine,tol", [("simt", 3e-4), ("tcgen05", 0.1)])
 def test_dense_wgrad_reproduces_the_reference_masked_tap_gradients(T, gradnorm, engine, tol):
     """F4: with dense_wgrad the kernel-bank gradient equals the reference's autograd result on EVERY tap."""

@@ -167,6 +167,21 @@ def main():
     rec = dict(metric="GradNorm joint-stage step", unit="samples/s", workload=f"cfg2 shape, B={B} per domain, eager (no CUDA graph), "
                "5 balanced losses: 5 extra backward passes with dense weight gradients over the last block",
                value=2 * B / ms_gn * 1e3, ms=ms_gn, plain_step_ms=ms_plain, gradnorm_overhead=ms_gn / ms_plain)
+    # the same step as ONE CUDA graph (grad_norm.GraphedJointStage: forward, norm passes, device-side GradNorm, backward,
+    # capturable optimizers); a failure here is reported, it does not take the other lines down
+    try:
+        torch.manual_seed(0)
+        mods_g = (OS_CNN_res(lpl_e).cuda(), OS_CNN(lpl_c, K).cuda(), OS_CNN_res(lpl_e).cuda(), OS_CNN(lpl_c, K).cuda())
+        for m in mods_g:
+            m.train()
+        opts_g = [torch.optim.RMSprop(m.parameters(), lr=lr, capturable=True) for m, lr in zip(mods_g, (0.001, 0.003, 0.001, 0.003))]
+        drv_g = D.JointStageDriver(mods_g[0].return_last_layer(), mods_g[2].return_last_layer(), opts_g, capturable=True)
+        stage = D.GraphedJointStage(drv_g, lambda a, b, c, d: GN.named_losses(mods_g, a, b, c, d, 1.0, adain=TF.adain,
+                                                                             gram_style_loss=TF.gram_style_loss))
+        ms_graph = timed(lambda: stage.step(xt, yt, xs, ys, cur_epoch=0), max(10, args.steps // 2), args.warmup, flush)
+        rec.update(cuda_graph_ms=ms_graph, cuda_graph_value=2 * B / ms_graph * 1e3, cuda_graph_speedup=ms_gn / ms_graph)
+    except Exception as e:                                  # noqa: BLE001
+        rec.update(cuda_graph_error=repr(e)[:300])
     lines.append(rec)
     for r in lines:
         print(json.dumps(r))
