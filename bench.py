@@ -467,12 +467,22 @@ def run_ours(args):
     T.set_engine(args.engine)
 
     torch.manual_seed(0)
+
+    def per_gpu(b_total: int) -> int:
+        """weak scaling (default): every rank runs the configuration's batch; strong scaling (--scaling strong, BASELINE
+        configs[3] "batch-sharded at 2/4/8 GPUs"): the configuration's batch is sharded over the ranks."""
+        if args.scaling == "weak":
+            return b_total
+        if b_total % world != 0:
+            raise SystemExit(f"--scaling strong: the batch of {b_total} series does not divide over {world} ranks")
+        return b_total // world
+
     cfg4 = args.workload == "cfg4"
     cfg3 = args.workload == "cfg3"
     if cfg3:
         from feature_level_style_transfer_for_tsc_b200.train_step import MultiSourceModelSet
         model = MultiSourceModelSet(CFG3["target"], CFG3["sources"]).to(dev)
-        B = CFG3["B"]
+        B = per_gpu(CFG3["B"])
         n_dom = 1 + len(CFG3["sources"])
         batches = [O.synthetic_batch(B, *CFG3["target"], n_dom * rank)]
         batches += [O.synthetic_batch(B, C, Ln, K, n_dom * rank + 1 + i) for i, (C, Ln, K) in enumerate(CFG3["sources"])]
@@ -481,13 +491,13 @@ def run_ours(args):
     elif cfg4:
         from feature_level_style_transfer_for_tsc_b200.train_step import SingleDomainModelSet
         model = SingleDomainModelSet(CFG4["C"], CFG4["L"], CFG4["K"]).to(dev)
-        B = CFG4["B"]
+        B = per_gpu(CFG4["B"])
         x_h, y_h = O.synthetic_batch(B, CFG4["C"], CFG4["L"], CFG4["K"], rank)
         host = [t.pin_memory() for t in (x_h, y_h)]
         series_per_gpu = B
     else:
         model = StyleTransferModelSet(CFG["C"], CFG["L"], CFG["K"], CFG["C"], CFG["L"], CFG["K"]).to(dev)
-        B = CFG["B"]
+        B = per_gpu(CFG["B"])
         xt_h, yt_h = O.synthetic_batch(B, CFG["C"], CFG["L"], CFG["K"], 2 * rank)
         xs_h, ys_h = O.synthetic_batch(B, CFG["C"], CFG["L"], CFG["K"], 2 * rank + 1)
         host = [t.pin_memory() for t in (xt_h, yt_h, xs_h, ys_h)]
@@ -642,9 +652,11 @@ def run_ours(args):
         cpu = dict(value=v, unit=UNIT, cores=threads, kind="port",
                    sample=f"3 full cfg2 steps (B=128 per domain) of the oracle port, {dt * 1e3:.0f} ms/step, {cores} host cores")
     line = dict(metric=METRIC, value=series / t_dev, unit=UNIT, n_gpus=world, steps=args.steps,
-                warmup=max(args.warmup, 3), ms_per_step=t_dev / args.steps * 1e3, higher_is_better=True, scaling="weak",
+                warmup=max(args.warmup, 3), ms_per_step=t_dev / args.steps * 1e3, higher_is_better=True, scaling=args.scaling,
                 vs_baseline=None, dtype="bf16" if args.engine == "tcgen05" else "f32", data="synthetic",
-                config=step_config(WORKLOAD3 if cfg3 else WORKLOAD4 if cfg4 else WORKLOAD, series_per_gpu),
+                config=step_config((WORKLOAD3 if cfg3 else WORKLOAD4 if cfg4 else WORKLOAD)
+                                   + (f" [strong scaling: that batch sharded over {world} ranks]" if args.scaling == "strong" else ""),
+                                   series_per_gpu),
                 run=dict(engine=args.engine, parallelism=f"dp{world}", cuda_graph=not args.no_graph),
                 e2e=dict(value=series / t_e2e, unit=UNIT, h2d_bytes_per_step=h2d_bytes * world, d2h_bytes_per_step=4 * world,
                          ms_per_step=t_e2e / args.steps * 1e3),
@@ -675,6 +687,9 @@ def main():
                     help="cfg2 = the headline step (default); cfg3 = multi-source transfer with the C-DAN loss; "
                          "cfg4 = long-series OS-CNN forward + backward (both secondary)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the driver's contract): fixed per-GPU batch; strong: the configuration's batch is "
+                         "sharded over the ranks (BASELINE configs[3]: cfg4 B=256 at 2/4/8 GPUs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
