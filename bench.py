@@ -9,7 +9,9 @@ Workload (N = 1): BASELINE.json configs[1] = "cfg2": target and source batches o
 RMSprop.  For N > 1 every rank runs the same per-GPU batch on its own shard (weak scaling) and the
 flat gradient bucket is all-reduced over NCCL.  `value` = series/s of the whole job with inputs resident in HBM,
 `e2e` = the same with host->device copies of the step's inputs and a device->host read of the loss inside the
-timed region.  One JSON line on stdout (rank 0).
+timed region.  One JSON line on stdout (rank 0); besides the contract's keys it carries `roofline` (in-step and isolated),
+`roofline_hbm` / `roofline_gram`, `cpu_baseline`, `gpu_eager_baseline`, the per-kernel table and `step_ms_spread`.
+`--scaling strong` shards the configuration's batch over the ranks instead (not the driver's contract).
 """
 from __future__ import annotations
 

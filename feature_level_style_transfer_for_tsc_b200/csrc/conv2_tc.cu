@@ -1,31 +1,28 @@
-// tcgen05 engine, forward / dgrad, second generation: the omni-scale convolution as a PERSISTENT implicit GEMM on CTA PAIRS.
+// tcgen05 engine, forward / dgrad, second generation: the omni-scale convolution as a PERSISTENT implicit GEMM.
 //
-//   positions (2 x 128 per CTA pair) -> MMA M = 256 (cta_group::2: 128 accumulator rows = TMEM lanes in each CTA)
+//   positions (128 per tile)         -> MMA M      (TMEM lanes; 256 per CTA pair in the cta_group::2 variant)
 //   output channels (<= 256)         -> MMA N      (the whole channel axis is one accumulator tile in TMEM)
 //   (tap, input channel)             -> MMA K      (16 channels per instruction)
 //
-// * cta_group::2.  The round-1 kernel and the first version of this one were bound by the ISSUE RATE of the one thread that may
-//   issue tcgen05.mma: 156 instructions of ~53 tensor cycles each for the cfg2 72->228 bank took 17.9 k cycles whatever the
-//   weight stream did (producer not copying at all: same time; ring depth 2 or 6: same time) -- 3720 instructions of the
-//   issuing warp at 4.8 cycles each (profiles/README.md, round 2).  One instruction of a CTA pair does the work of two: the
-//   pair's two position tiles share every MMA, each CTA holds its own activation tile (A: 128 rows per CTA) and HALF of the
-//   tap's live channels (B: N/2 rows per CTA, the split packed layout of common.cuh), so the issue cost per tile, the
-//   shared-memory operand fetch per instruction (42 + N/8 instead of 42 + N/4 cycles) and the L2 -> shared-memory weight
-//   traffic per tile all halve.  The leader CTA (cluster rank 0) issues; the peer's would-be issuer warp relays "my half of
-//   the stage / my activation tile has landed" to the leader's barriers; tcgen05.commit multicasts "stage consumed" /
-//   "accumulator complete" to both CTAs.
-// What changed against conv_tc.cu (round 1), and why (profiles/README.md, rounds 1-2):
-// * The issuing warp was bound by its own instruction count (~70 SASS instructions per four MMAs: plan entries loaded from
-//   shared memory into vector registers, 17 R2UR per group).  Here the schedule is a table of per-tap RUNS in the kernel
-//   parameter block (constant bank): the whole issue loop runs in the UNIFORM datapath -- LDCU for the run, UIADD3 for the
-//   two descriptor words that change per MMA -- about six uniform instructions per MMA and no R2UR.  For that the warp's
-//   control flow must be provably uniform: every mbarrier wait is a vote (`__all_sync` of try_wait), and nothing a run needs is
-//   modified inside the elected-lane region.
-// * One CTA walks several position tiles (grid = min(tiles, SMs)); the accumulator tile and the activation tile are
-//   double-buffered (2 x <=256 TMEM columns, two shared-memory tiles), so the epilogue of tile i and the TMA load of tile
-//   i+2 overlap the MMAs of tile i+1.  With one tile per CTA (cfg2: 128 tiles) it degenerates to the single-buffered
-//   layout that fits half an SM, so that CTAs of two streams stay co-resident.
-// * No padding MMAs and no plan relocation pass: a weight stage holds whole MMAs of consecutive runs.
+// What changed against conv_tc.cu (round 1), and why -- measurements: profiles/r2_conv2_issue_bisection.md, r2_conv2_dual.md,
+// r2_conv2_B1024.md:
+// * The issue loop lives in the UNIFORM datapath.  The schedule is a table of per-tap RUNS and of weight STAGES in the kernel
+//   parameter block (constant bank); per stage the issuing warp does one vote-wait (`__all_sync` of try_wait: the warp's control
+//   flow stays provably uniform), ONE elected region that walks the stage's runs, and one commit; a run is 4 LDCU + 3 adds +
+//   an inline-PTX K loop of 6 SASS instructions per MMA (descriptors = mad.wide.u32(k, step, base)).  The tensor pipe accepts
+//   an MMA only when its predecessor has fetched its operands (~68 cycles at the cfg2 bank's mean N), so what the issuer
+//   executes between two MMAs is free up to that length and serial beyond: the per-RUN header is what had to shrink (the
+//   number of instructions inside a run, the operand addresses, N and the accumulator column do not matter -- bisection).
+// * One CTA walks several position tiles (grid = min(tiles, SMs)); accumulator and activation tiles are multi-buffered, the
+//   epilogue of one tile overlaps the MMAs of the next, and -- when the accumulator is <= 128 columns or the bank >= 256 KB --
+//   every weight stage serves a PAIR of tiles (`dual`): one L2 -> shared-memory fetch and one barrier round trip per pair.
+//   With one tile per CTA (cfg2: 128 tiles) the kernel degenerates to the single-buffered layout that fits half an SM, so
+//   that CTAs of two streams stay co-resident.
+// * No padding MMAs and no plan relocation pass: a weight stage holds whole runs.
+// * cta_group::2 variant (PAIR, TSC_CONV_PAIR=1): the pair's two position tiles share every MMA, each CTA holds its own
+//   activation tile and HALF of the tap's live channels (split packed layout of common.cuh); the leader CTA issues, the peer's
+//   would-be issuer relays "landed" signals, commits are multicast.  Parity-green but slower than one CTA per tile at every
+//   measured shape (the cross-CTA barrier traffic costs more than the halved B fetch saves): an opt-in, not the default.
 //
 // Unchanged: the c8 activation tile with halo staged by ONE TMA box load (out-of-bounds rows zero-filled = ConstantPad1d,
 // OS_CNN.py:59,70), a tap = "+ t rows" on the A descriptor; the packed bank (live (channel, tap) pairs only) streamed through a
@@ -840,7 +837,8 @@ static const ConvSched* get_sched(bool pair, int direction, int Cin, int Cout, i
 
 static long long* g_timeline2 = nullptr;     // debug only: device buffer of >= 8 clock64 samples
 
-// experiment knobs (environment, read once): TSC_C2_STAGE_KB, TSC_C2_SMEM_FULL, TSC_C2_GRID, TSC_C2_DEBUG
+// experiment knobs (environment, read once): TSC_C2_STAGE_KB, TSC_C2_SMEM_FULL, TSC_C2_GRID, TSC_C2_DUAL (0: one tile per
+// pass), TSC_C2_DEBUG (timing experiments with garbage results; selects the instrumented instantiation)
 static int env_int2(const char* name, int dflt) {
     const char* e = getenv(name);
     return e && e[0] ? atoi(e) : dflt;
