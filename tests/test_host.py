@@ -189,3 +189,28 @@ def test_remaining_ranges_of_the_gradient_bucket():
     assert rest == [(0, 100), (160, 300)]
     covered = sorted(rest + [rng["cl_t"], rng["cl_s"]])
     assert covered[0][0] == 0 and covered[-1][1] == ends[-1] and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+
+
+def test_bench_reference_arm_prints_the_contract_line_and_the_product_arm_fails_loudly_without_a_gpu():
+    """`bench.py --impl reference` (the CPU arm the driver launches beside the product arm) prints ONE JSON line with the same
+    metric / unit / config as the product arm and `impl: reference`; the product arm has no CPU fallback."""
+    import json
+    import subprocess
+    import sys
+    from conftest import ROOT
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    import bench
+    assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == bench.UNIT and d["higher_is_better"] is True
+    assert d["config"] == bench.step_config(bench.WORKLOAD, 2 * bench.CFG["B"])          # identical in both arms
+    assert d["steps"] == 1 and d["warmup"] == 0 and d["n_gpus"] == 1 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] > 0
+    assert d["e2e"] == dict(value=d["value"], unit=bench.UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0)
+    if not torch.cuda.is_available():
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True,
+                           timeout=600, cwd=ROOT)
+        assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
