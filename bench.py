@@ -92,7 +92,10 @@ class ClockSampler:
         while not self._stop.is_set():
             try:
                 if self.nvml is not None:
-                    self.rows.append(self._sample_nvml())
+                    try:
+                        self.rows.append(self._sample_nvml())
+                    except Exception:
+                        self.nvml, self.source = None, "nvidia-smi"       # this NVML cannot answer: fall back for the rest
                 else:
                     out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
                                           str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
