@@ -214,3 +214,23 @@ def test_bench_reference_arm_prints_the_contract_line_and_the_product_arm_fails_
         r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True,
                            timeout=600, cwd=ROOT)
         assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_device_side_gradnorm_weight_gradient_equals_the_host_formula():
+    """grad_norm._weight_gradient_device (torch, used inside the graph-captured joint stage) against grad_norm._weight_gradient
+    (numpy, the transcription of train_and_test.py:691-715 that the golden vectors pin): norms, targets and the sign-valued
+    weight gradient on random balanced weights / norm sums / losses, both side sizes."""
+    from feature_level_style_transfer_for_tsc_b200 import grad_norm as D
+    rng = np.random.default_rng(5)
+    for n in (2, 3):
+        for _ in range(50):
+            w = rng.uniform(0.2, 6.0, n).astype(np.float32)
+            sums = rng.uniform(0.01, 30.0, n).astype(np.float32)
+            lv = rng.uniform(-2.0, 4.0, n).astype(np.float32)
+            init = (1 / (1 + np.exp(-rng.uniform(-1.0, 3.0, n)))).astype(np.float32)
+            norms, target, grad = D._weight_gradient(w, sums, lv, init, D.ALPHA)
+            dn, dt, dg = D._weight_gradient_device(torch.from_numpy(w), torch.from_numpy(sums), torch.from_numpy(lv),
+                                                   torch.from_numpy(init), D.ALPHA)
+            assert np.allclose(dn.numpy(), norms, rtol=1e-6) and np.allclose(dt.numpy(), target, rtol=2e-5)
+            decided = np.abs(norms - target) > 1e-4 * np.abs(target)          # sign(norms - target) away from the tie
+            assert np.array_equal(dg.numpy()[decided], grad[decided])
